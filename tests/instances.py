@@ -1,0 +1,117 @@
+"""Deterministic test instances shared by the golden generator and the tests.
+
+Nothing here depends on the reference or on networkx: graphs are built explicitly and amplitudes come
+from ``random.Random(seed)`` so the GPU box rebuilds bit-identical inputs."""
+from __future__ import annotations
+
+from random import Random
+
+import numpy as np
+
+
+def ring_with_chords(n: int, seed: int, zero_field: bool = False, unit_coupling: bool = False):
+    """3-regular graph: ring i -- i+1 plus chords i -- i + n/2 (n even)."""
+    assert n % 2 == 0
+    rng = Random(seed)
+    nodes = {i: (0.0 if zero_field else rng.uniform(-1.0, 1.0)) for i in range(n)}
+    edges = {}
+    for i in range(n):
+        edges[(i, (i + 1) % n)] = 1.0 if unit_coupling else rng.uniform(-1.0, 1.0)
+    for i in range(n // 2):
+        # alternate orientation so that nodes are lhs and rhs in mixed order
+        e = (i, i + n // 2) if i % 2 == 0 else (i + n // 2, i)
+        edges[e] = 1.0 if unit_coupling else rng.uniform(-1.0, 1.0)
+    return nodes, edges
+
+
+def grid(m: int, n: int, seed: int):
+    rng = Random(seed)
+    nodes = {i * n + j: rng.uniform(-1.0, 1.0) for i in range(m) for j in range(n)}
+    edges = {}
+    for i in range(m):
+        for j in range(n):
+            if j + 1 < n:
+                edges[(i * n + j, i * n + j + 1)] = rng.uniform(-1.0, 1.0)
+            if i + 1 < m:
+                edges[(i * n + j, (i + 1) * n + j)] = rng.uniform(-1.0, 1.0)
+    return nodes, edges
+
+
+def comb(n_spine: int, seed: int):
+    """Heavy-hex flavoured tree: a spine with a pendant qubit on every other spine site (degrees 1, 2, 3),
+    amplitudes +-1 like reference examples/full_size_ibm_heavy_hex.py:12-13."""
+    rng = Random(seed)
+    pm = lambda: float(2 * rng.randint(0, 1) - 1)
+    n_pend = (n_spine + 1) // 2
+    nodes = {i: pm() for i in range(n_spine + n_pend)}
+    edges = {}
+    for i in range(n_spine - 1):
+        edges[(i, i + 1)] = pm()
+    for k in range(n_pend):
+        edges[(n_spine + k, 2 * k)] = pm()
+    return nodes, edges
+
+
+def _anneal(total_time, steps, tail):
+    return {"total_time": total_time, "starting_mixing": 1.0,
+            "actions": [{"weight": 1.0, "steps_number": steps, "final_mixing": 0.0}, *tail]}
+
+
+def cfg_small6():
+    # reference tests/test_small_circuit_final_density.py:9-15 (default schedule: 100 steps, T=10, Bloch vectors)
+    return {
+        "nodes": {0: 1., 1: -1., 2: 0.5, 3: -0.5, 4: 1.1, 5: 0.4},
+        "edges": {(0, 1): 1., (2, 1): -1., (1, 3): 1., (4, 3): -1., (5, 3): 1.},
+        "pinv_eps": 1e-9, "bp_eps": 1e-9, "max_bond_dim": 8,
+    }
+
+
+def cfg_ring24():
+    nodes, edges = ring_with_chords(24, seed=7)
+    return {"nodes": nodes, "edges": edges, "max_bond_dim": 4,
+            "schedule": _anneal(4.0, 20, ["get_bloch_vectors", "measure"])}
+
+
+def cfg_ring24_capped():
+    nodes, edges = ring_with_chords(24, seed=11)
+    return {"nodes": nodes, "edges": edges, "max_bond_dim": 3, "max_bp_iter_number": 3, "damping": 0.2,
+            "schedule": _anneal(3.0, 12, ["get_bloch_vectors"])}
+
+
+def cfg_grid4():
+    nodes, edges = grid(4, 4, seed=42)
+    return {"nodes": nodes, "edges": edges, "max_bond_dim": 4, "damping": 0.3,
+            "schedule": _anneal(4.0, 16, ["get_bloch_vectors", "measure"])}
+
+
+def cfg_comb():
+    nodes, edges = comb(9, seed=42)
+    return {"nodes": nodes, "edges": edges, "max_bond_dim": 8, "measurement_threshold": 0.9,
+            "schedule": _anneal(10.0, 10, ["get_bloch_vectors", "measure"])}
+
+
+GOLDEN_CONFIGS = {
+    "small6": cfg_small6,
+    "ring24": cfg_ring24,
+    "ring24_capped": cfg_ring24_capped,
+    "grid4": cfg_grid4,
+    "comb": cfg_comb,
+}
+
+
+def random_psd_msgs(rng: np.random.Generator, B: int, D: int) -> np.ndarray:
+    a = rng.normal(size=(B, D, D)) + 1j * rng.normal(size=(B, D, D))
+    m = a @ np.swapaxes(a.conj(), 1, 2)
+    return m / np.trace(m, axis1=1, axis2=2)[:, None, None]
+
+
+def random_node_batch(B: int, d: int, D: int, seed: int):
+    """(T (B, 2, D^d) complex128 unit-norm per node, d Hermitian PSD trace-1 messages (B, D, D),
+    d coupling angles (B,) float64 in (-1, 1))."""
+    rng = np.random.default_rng(seed)
+    shape = (B, 2) + (D,) * d
+    t = rng.normal(size=shape) + 1j * rng.normal(size=shape)
+    t /= np.linalg.norm(t.reshape(B, -1), axis=1).reshape((B,) + (1,) * (d + 1))
+    msgs = [random_psd_msgs(rng, B, D) for _ in range(d)]
+    thetas = [rng.uniform(-1.0, 1.0, size=B) for _ in range(d)]
+    return t, msgs, thetas

@@ -1,0 +1,89 @@
+"""ctypes binding of libbqa_b200.so (C ABI: include/bqa_b200.h).
+
+The product path loads the CUDA library or raises -- there is no CPU fallback.  (The test-suite may bind a
+host emulation of the same ABI through `bind(path)`; nothing in the package does.)"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libbqa_b200.so")
+
+C64, C128 = 0, 1
+_vp, _i, _ll, _d, _sz = C.c_void_p, C.c_int, C.c_longlong, C.c_double, C.c_size_t
+
+# name -> argtypes, exactly as declared in include/bqa_b200.h
+SIGNATURES = {
+    "bqa_b200_bp_sweep": [_i, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp, _d, _i, _d, _i, _vp, _vp, _vp, _sz, _vp],
+    "bqa_b200_ext_msgs": [_i, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _d, _vp, _sz, _vp],
+    "bqa_b200_canonicalize": [_i, _i, _ll, _vp, _vp, _vp, _vp, _d, _vp],
+    "bqa_b200_apply_update": [_i, _i, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _vp, _sz, _vp],
+    "bqa_b200_density": [_i, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp],
+    "bqa_b200_argmax_unmeasured": [_i, _ll, _vp, _vp, _vp, _vp, _vp],
+    "bqa_b200_project_node": [_i, _i, _i, _vp, _ll, _i, _vp],
+    "bqa_b200_threshold_project": [_i, _i, _i, _ll, _vp, _vp, _vp, _vp, _d, _vp, _vp],
+}
+EXPORTS = list(SIGNATURES) + ["bqa_b200_last_error", "bqa_b200_version", "bqa_b200_launch_count",
+                              "bqa_b200_workspace_bytes"]
+
+
+class Library:
+    """Thin checked wrapper: every entry point returns 0 or raises RuntimeError(last_error)."""
+
+    def __init__(self, path: str):
+        self.path = path
+        self._dll = C.CDLL(path)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(self._dll, name)
+            fn.argtypes = argtypes
+            fn.restype = _i
+            setattr(self, name[len("bqa_b200_"):], self._checked(name, fn))
+        self._dll.bqa_b200_last_error.restype = C.c_char_p
+        self._dll.bqa_b200_version.restype = _i
+        self._dll.bqa_b200_launch_count.restype = _ll
+        self._dll.bqa_b200_workspace_bytes.argtypes = [_i, _i, _i, _i]
+        self._dll.bqa_b200_workspace_bytes.restype = _sz
+
+    def _checked(self, name, fn):
+        def call(*args):
+            rc = fn(*args)
+            if rc != 0:
+                raise RuntimeError(f"{name}: {self._dll.bqa_b200_last_error().decode()}")
+        call.__name__ = name
+        return call
+
+    def version(self) -> int:
+        return int(self._dll.bqa_b200_version())
+
+    def launch_count(self) -> int:
+        return int(self._dll.bqa_b200_launch_count())
+
+    def workspace_bytes(self, prec: int, degree: int, D: int, D_new: int) -> int:
+        return int(self._dll.bqa_b200_workspace_bytes(prec, degree, D, D_new))
+
+    @property
+    def is_host_emulation(self) -> bool:
+        return self.version() < 0
+
+
+_cached: Library | None = None
+
+
+def bind(path: str) -> Library:
+    return Library(path)
+
+
+def load_library() -> Library:
+    """The CUDA library, built in-tree by `python -m bqa_b200.build` / `__graft_entry__.build()`."""
+    global _cached
+    if _cached is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m bqa_b200.build` (needs nvcc). "
+                "bqa_b200 has no CPU fallback.")
+        lib = Library(LIB_PATH)
+        if lib.is_host_emulation:
+            raise RuntimeError(f"{LIB_PATH} is not the CUDA build")
+        _cached = lib
+    return _cached

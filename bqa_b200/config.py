@@ -45,7 +45,7 @@ DEFAULTS = {
     "pinv_eps": 1e-6,
     "measurement_threshold": 0.95,
     "damping": 0.0,
-    "backend": "numpy",
+    "backend": "b200",
 }
 EVOLUTION_TYPES = ("real_time_evolution", "imag_time_evolution")
 SIMPLE_ACTIONS = ("measure", "get_bloch_vectors")
@@ -59,8 +59,9 @@ DEFAULT_SCHEDULE = {
 }
 
 # Backend names accepted by the syntax check.  The reference validates against its registry dict
-# (config_syntax.py:63-70); here the registry is this set, extended by ``register_backend_name``.
-KNOWN_BACKENDS = {"numpy", "cupy", "b200"}
+# (config_syntax.py:63-70) and defaults to "numpy"; this package provides exactly one backend, "b200",
+# which is therefore also the default.  There is no CPU backend here: "numpy" / "cupy" configs belong to bqa.
+KNOWN_BACKENDS = {"b200"}
 
 
 def register_backend_name(name: str) -> None:

@@ -1,0 +1,136 @@
+// bqa_capi.cu -- extern "C" entry points declared in include/bqa_b200.h: argument checks, precision and
+// shape dispatch (specialised kernels where they exist, generic kernels otherwise).  No CPU fallback.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/bqa_b200.h"
+#include "bqa_core.cuh"
+#include "bqa_launch.cuh"
+
+namespace bqa {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+int set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+
+int after_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+  return 0;
+}
+
+static int check_shape(int prec, int degree, int D) {
+  if (prec != BQA_C64 && prec != BQA_C128) return set_error("unknown precision code %d", prec);
+  if (degree < 0 || degree > BQA_MAX_DEGREE) return set_error("degree %d outside [0, %d]", degree, BQA_MAX_DEGREE);
+  if (D < 1 || D > BQA_MAX_D) return set_error("bond dimension %d outside [1, %d]", D, BQA_MAX_D);
+  return 0;
+}
+
+}  // namespace bqa
+
+using namespace bqa;
+
+extern "C" {
+
+const char* bqa_b200_last_error(void) { return g_err; }
+int bqa_b200_version(void) { return 1; }
+long long bqa_b200_launch_count(void) { return g_launches.load(); }
+
+size_t bqa_b200_workspace_bytes(int prec, int degree, int D, int D_new) {
+  const size_t elem = prec == BQA_C64 ? sizeof(cx<float>) : sizeof(cx<double>);
+  return generic_ws_elems_per_warp(degree, D, D_new) * elem * BQA_GENERIC_MAX_WARPS;
+}
+
+int bqa_b200_bp_sweep(int prec, int degree, int D, long long B, const void* T, const void* msgs_cur,
+                      void* msgs_nxt, const int32_t* in_pos, const int32_t* out_pos, double damping,
+                      int write_undamped, double bp_eps, int it, void* resid, int32_t* status, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  if (int rc = check_shape(prec, degree, D)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (prec == BQA_C64)
+    return launch_node_msgs<float>(false, degree, D, B, T, msgs_cur, msgs_nxt, in_pos, out_pos, nullptr, 0.0, damping,
+                                   write_undamped, bp_eps, it, resid, status, workspace, workspace_bytes, st);
+  return launch_node_msgs<double>(false, degree, D, B, T, msgs_cur, msgs_nxt, in_pos, out_pos, nullptr, 0.0, damping,
+                                  write_undamped, bp_eps, it, resid, status, workspace, workspace_bytes, st);
+}
+
+int bqa_b200_ext_msgs(int prec, int degree, int D, long long B, const void* T, const void* msgs_cur, void* ext,
+                      const int32_t* in_pos, const int32_t* out_pos, const void* edge_ampls, double ztime,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = check_shape(prec, degree, D)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (prec == BQA_C64)
+    return launch_node_msgs<float>(true, degree, D, B, T, msgs_cur, ext, in_pos, out_pos, edge_ampls, ztime, 0.0, 0,
+                                   0.0, 0, nullptr, nullptr, workspace, workspace_bytes, st);
+  return launch_node_msgs<double>(true, degree, D, B, T, msgs_cur, ext, in_pos, out_pos, edge_ampls, ztime, 0.0, 0,
+                                  0.0, 0, nullptr, nullptr, workspace, workspace_bytes, st);
+}
+
+int bqa_b200_canonicalize(int prec, int D, long long L, const void* ext, void* canon, void* lmbds, void* colmax,
+                          double pinv_eps, void* stream) {
+  if (int rc = check_shape(prec, 0, D)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (prec == BQA_C64) return launch_canonicalize<float>(D, L, ext, canon, lmbds, colmax, pinv_eps, st);
+  return launch_canonicalize<double>(D, L, ext, canon, lmbds, colmax, pinv_eps, st);
+}
+
+int bqa_b200_apply_update(int prec, int degree, int D, int D_new, long long B, const void* T_in, void* T_out,
+                          const void* canon, const void* lmbds, void* msgs_out, const int32_t* in_pos,
+                          const int32_t* out_pos, const int32_t* lmbd_pos, const void* node_ampls,
+                          const void* edge_ampls, double ztime, double xtime, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  if (int rc = check_shape(prec, degree, D)) return rc;
+  if (D_new < 1 || D_new > 2 * D || D_new > BQA_MAX_D) return set_error("new bond dimension %d invalid for D = %d", D_new, D);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (prec == BQA_C64)
+    return launch_apply_update<float>(degree, D, D_new, B, T_in, T_out, canon, lmbds, msgs_out, in_pos, out_pos,
+                                      lmbd_pos, node_ampls, edge_ampls, ztime, xtime, workspace, workspace_bytes, st);
+  return launch_apply_update<double>(degree, D, D_new, B, T_in, T_out, canon, lmbds, msgs_out, in_pos, out_pos,
+                                     lmbd_pos, node_ampls, edge_ampls, ztime, xtime, workspace, workspace_bytes, st);
+}
+
+int bqa_b200_density(int prec, int degree, int D, long long B, const void* T, const void* msgs, const int32_t* in_pos,
+                     const int32_t* node_ids, void* bloch, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = check_shape(prec, degree, D)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (prec == BQA_C64)
+    return launch_density<float>(degree, D, B, T, msgs, in_pos, node_ids, bloch, workspace, workspace_bytes, st);
+  return launch_density<double>(degree, D, B, T, msgs, in_pos, node_ids, bloch, workspace, workspace_bytes, st);
+}
+
+int bqa_b200_argmax_unmeasured(int prec, long long N, const void* bloch, const int32_t* outcomes, int32_t* result,
+                               void* result_p0, void* stream) {
+  if (int rc = check_shape(prec, 0, 1)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (prec == BQA_C64) return launch_argmax<float>(N, bloch, outcomes, result, result_p0, st);
+  return launch_argmax<double>(N, bloch, outcomes, result, result_p0, st);
+}
+
+int bqa_b200_project_node(int prec, int degree, int D, void* T, long long pos, int bit, void* stream) {
+  if (int rc = check_shape(prec, degree, D)) return rc;
+  if (bit != 0 && bit != 1) return set_error("bit must be 0 or 1, got %d", bit);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (prec == BQA_C64) return launch_project<float>(degree, D, T, pos, bit, st);
+  return launch_project<double>(degree, D, T, pos, bit, st);
+}
+
+int bqa_b200_threshold_project(int prec, int degree, int D, long long B, void* T, const int32_t* node_ids,
+                               const void* bloch, int32_t* outcomes, double thr, int32_t* n_projected, void* stream) {
+  if (int rc = check_shape(prec, degree, D)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (prec == BQA_C64) return launch_threshold<float>(degree, D, B, T, node_ids, bloch, outcomes, thr, n_projected, st);
+  return launch_threshold<double>(degree, D, B, T, node_ids, bloch, outcomes, thr, n_projected, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,43 @@
+// bqa_launch.cuh -- host-side launch plumbing shared by the .cu files (error string, launch counter,
+// declarations of the templated launchers).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+#define BQA_GENERIC_MAX_WARPS (148 * 32)
+
+namespace bqa {
+
+int set_error(const char* fmt, ...);
+int after_launch(const char* what);      // counts the launch, maps cudaGetLastError to a return code
+
+size_t generic_ws_elems_per_warp(int d, int D, int Dn);
+
+template <typename R>
+int launch_node_msgs(bool ext, int d, int D, long long B, const void* T, const void* msgs_cur, void* msgs_out,
+                     const int32_t* in_pos, const int32_t* out_pos, const void* edge_ampls, double ztime,
+                     double damping, int write_undamped, double bp_eps, int it, void* resid, int32_t* status,
+                     void* ws, size_t ws_bytes, cudaStream_t st);
+template <typename R>
+int launch_canonicalize(int D, long long L, const void* ext, void* canon, void* lmbds, void* colmax,
+                        double pinv_eps, cudaStream_t st);
+template <typename R>
+int launch_apply_update(int d, int D, int Dn, long long B, const void* T_in, void* T_out, const void* canon,
+                        const void* lmbds, void* msgs_out, const int32_t* in_pos, const int32_t* out_pos,
+                        const int32_t* lmbd_pos, const void* node_ampls, const void* edge_ampls, double ztime,
+                        double xtime, void* ws, size_t ws_bytes, cudaStream_t st);
+template <typename R>
+int launch_density(int d, int D, long long B, const void* T, const void* msgs, const int32_t* in_pos,
+                   const int32_t* node_ids, void* bloch, void* ws, size_t ws_bytes, cudaStream_t st);
+template <typename R>
+int launch_argmax(long long N, const void* bloch, const int32_t* outcomes, int32_t* result, void* result_p0,
+                  cudaStream_t st);
+template <typename R>
+int launch_project(int d, int D, void* T, long long pos, int bit, cudaStream_t st);
+template <typename R>
+int launch_threshold(int d, int D, long long B, void* T, const int32_t* node_ids, const void* bloch,
+                     int32_t* outcomes, double thr, int32_t* n_proj, cudaStream_t st);
+
+}  // namespace bqa

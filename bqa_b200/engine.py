@@ -1,0 +1,406 @@
+"""Device-resident annealing engine: the B200 replacement of the reference "VM" (src/bqa/state.py).
+
+It consumes the same compiled ``Context`` (ours from ``bqa_b200.config`` or bqa's own from
+``bqa.config.core.config_to_context``) and keeps the reference control flow:
+
+    run_layer  = simple update -> Rz layer -> Rx layer -> symmetric gauge -> BP      (state.py:315-321)
+    run_bp     = damped BP with the reference termination rules                      (state.py:97-124)
+    measure    = sequential decimation sampler with the host numpy RNG stream        (state.py:250-312)
+    bloch_vectors / density_matrices                                                 (state.py:77-94)
+
+All state (node tensors per degree class, messages, lambdas) lives in HBM; every numerical stage is a
+CUDA kernel reached through the C ABI (include/bqa_b200.h).  PyTorch is used only to own device memory and
+streams.  Host synchronisations per annealing step: one (the global bond-dimension decision, the
+reference's ``truncate_lmbds`` host round trip) plus one per *chunk* of BP sweeps instead of one per sweep:
+sweep kernels test the previous sweep's residual on the device and turn into no-ops after convergence.
+"""
+from __future__ import annotations
+
+import logging
+import os
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+
+log = logging.getLogger(__name__)
+
+MAX_BOND_DIM = 16
+MAX_DEGREE = 8
+
+
+def default_precision() -> str:
+    """``BQA_PRECISION`` = single | double like the reference (src/bqa/utils.py:9-20); unset means single
+    (complex64, what the reference's GPU backend always uses, backends.py:772)."""
+    p = (os.environ.get("BQA_PRECISION") or "single").lower()
+    if p not in ("single", "double"):
+        raise ValueError(f"Unknown value of BQA_PRECISION environment variable {p}")
+    return p
+
+
+def _np(x) -> np.ndarray:
+    """numpy view of a layout field: ours are arrays, bqa's are Tensor wrappers (.numpy) or lists of them."""
+    if isinstance(x, (list, tuple)):
+        return np.stack([_np(e) for e in x]) if len(x) else np.zeros((0, 0))
+    if hasattr(x, "numpy") and not isinstance(x, np.ndarray):
+        x = x.numpy
+    return np.asarray(x)
+
+
+@dataclass
+class _DegreeClass:
+    degree: int
+    B: int
+    node_ids: torch.Tensor
+    in_pos: torch.Tensor
+    out_pos: torch.Tensor
+    lmbd_pos: torch.Tensor
+    node_ampls: torch.Tensor
+    edge_ampls: torch.Tensor
+    T: list            # two flat complex buffers (ping-pong across bond-dimension changes)
+    cur: int = 0
+    node_ids_host: np.ndarray = None
+
+
+class Engine:
+    def __init__(self, context, precision: str | None = None, device=None, _testing_lib=None):
+        self.ctx = context
+        self.precision = precision or default_precision()
+        if self.precision not in ("single", "double"):
+            raise ValueError(f"precision must be 'single' or 'double', got {self.precision}")
+        if _testing_lib is not None:                       # tests only: host emulation of the kernels
+            self.lib = _testing_lib
+            self.dev = torch.device("cpu")
+        else:
+            self.lib = _lib.load_library()
+            if not torch.cuda.is_available():
+                raise RuntimeError("bqa_b200 needs a CUDA device (no CPU fallback)")
+            self.dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+            if self.dev.type != "cuda":
+                raise RuntimeError(f"bqa_b200 runs on CUDA devices only, got {self.dev}")
+        self.cuda = self.dev.type == "cuda"
+        self.prec = _lib.C64 if self.precision == "single" else _lib.C128
+        self.cdtype = torch.complex64 if self.precision == "single" else torch.complex128
+        self.rdtype = torch.float32 if self.precision == "single" else torch.float64
+        self.np_rdtype = np.float32 if self.precision == "single" else np.float64
+
+        ctx = context
+        self.N = int(ctx.nodes_number)
+        self.E2 = int(ctx.edges_number)
+        self.L = self.E2 // 2
+        self.Dmax = int(ctx.max_bond_dim)
+        if self.Dmax > MAX_BOND_DIM:
+            raise ValueError(f"max_bond_dim {self.Dmax} exceeds the supported maximum {MAX_BOND_DIM}")
+        self.max_iters = int(ctx.max_bp_iters_number)
+        self.bp_eps = float(ctx.bp_eps)
+        self.pinv_eps = float(ctx.pinv_eps)
+        self.damping = float(ctx.damping)
+        self.threshold = float(ctx.measurement_threshold)
+        self.rng = np.random.default_rng(int(ctx.seed))
+        self.D = 1
+        self.stats = {"bp_sweeps": [], "bp_dist": [], "bond_dims": [], "trunc_err": []}
+        self._bp_chunk = 4
+
+        self.classes: list[_DegreeClass] = []
+        self._node_class = np.zeros(self.N, np.int64)
+        self._node_slot = np.zeros(self.N, np.int64)
+        for ci, (degree, lay) in enumerate(ctx.degree_to_layout.items()):
+            degree = int(degree)
+            if degree > MAX_DEGREE:
+                raise ValueError(f"node degree {degree} exceeds the supported maximum {MAX_DEGREE}")
+            ids = _np(lay.node_ids).astype(np.int64)
+            B = int(ids.shape[0])
+            self._node_class[ids] = ci
+            self._node_slot[ids] = np.arange(B)
+            elems = B * 2 * self.Dmax ** degree
+            if elems * (8 if self.precision == "single" else 16) > 64 * 2 ** 30:
+                raise MemoryError(f"degree class {degree} with max_bond_dim {self.Dmax} needs more than 64 GiB")
+            i32 = lambda a: torch.from_numpy(np.ascontiguousarray(_np(a).reshape(degree, B).astype(np.int32))).to(self.dev)
+            real = lambda a, shp: torch.from_numpy(
+                np.ascontiguousarray(np.real(_np(a)).reshape(shp).astype(self.np_rdtype))).to(self.dev)
+            self.classes.append(_DegreeClass(
+                degree=degree, B=B,
+                node_ids=torch.from_numpy(ids.astype(np.int32)).to(self.dev),
+                in_pos=i32(lay.input_msgs_position), out_pos=i32(lay.output_msgs_position),
+                lmbd_pos=i32(lay.lmbds_position),
+                node_ampls=real(lay.node_ampls, (B,)), edge_ampls=real(lay.edge_ampls, (degree, B)),
+                T=[torch.zeros(elems, dtype=self.cdtype, device=self.dev) for _ in range(2)],
+                node_ids_host=ids))
+        Dm = self.Dmax
+        self._msgs = [torch.zeros(self.E2 * Dm * Dm, dtype=self.cdtype, device=self.dev) for _ in range(2)]
+        self._msgs_cur = 0
+        self._ext = None         # allocated on first simple update (size depends on the largest D reached)
+        self._canon = None
+        self._lmbds = torch.ones(self.L * 2 * Dm, dtype=self.rdtype, device=self.dev)
+        self._lmbd_stride = 2      # row stride of the lambda array = 2 * D of the update that produced it
+        self._colmax = torch.zeros(2 * Dm, dtype=self.rdtype, device=self.dev)
+        # BP control block, read back with one copy per chunk of sweeps: [resid (max_iters, 2) reals | status int32 x4]
+        rbytes = ((max(self.max_iters, 1) * 2 * (4 if self.precision == "single" else 8)) + 15) // 16 * 16
+        self._ctrl = torch.zeros(rbytes + 16, dtype=torch.uint8, device=self.dev)
+        self._ctrl_rbytes = rbytes
+        self._resid = self._ctrl[:rbytes].view(self.rdtype)
+        self._status = self._ctrl[rbytes:].view(torch.int32)
+        self._bloch = torch.zeros(self.N * 4, dtype=self.rdtype, device=self.dev)
+        self._ws = torch.zeros(16, dtype=torch.uint8, device=self.dev)
+        self._argmax_i = torch.zeros(2, dtype=torch.int32, device=self.dev)
+        self._argmax_p = torch.zeros(1, dtype=self.rdtype, device=self.dev)
+        self._nproj = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self._init_state()
+
+    # ------------------------------------------------------------------------------------------
+    # plumbing
+    # ------------------------------------------------------------------------------------------
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.dev).cuda_stream if self.cuda else 0
+
+    def _to_host(self, t: torch.Tensor) -> np.ndarray:
+        return t.cpu().numpy()          # synchronises the current stream
+
+    def _ensure_ws(self, D: int, Dn: int) -> None:
+        need = max([self.lib.workspace_bytes(self.prec, c.degree, D, Dn) for c in self.classes] + [16])
+        if self._ws.numel() < need:
+            self._ws = torch.zeros(need, dtype=torch.uint8, device=self.dev)
+
+    def _ensure_edge_buffers(self, D: int) -> None:
+        need = self.E2 * 4 * D * D
+        if self._ext is None or self._ext.numel() < need:
+            self._ext = torch.zeros(need, dtype=self.cdtype, device=self.dev)
+            self._canon = torch.zeros(need, dtype=self.cdtype, device=self.dev)
+
+    @property
+    def msgs_buffer(self) -> torch.Tensor:
+        return self._msgs[self._msgs_cur]
+
+    # ------------------------------------------------------------------------------------------
+    # state
+    # ------------------------------------------------------------------------------------------
+    def _init_state(self) -> None:
+        """|-> on every qubit, bond dimension 1, lambdas 1, messages 1 (state.py:21, :41-74)."""
+        self.D = 1
+        amp = np.sqrt(0.5)
+        for c in self.classes:
+            t = c.T[0][: c.B * 2].view(c.B, 2)
+            t[:, 0] = amp
+            t[:, 1] = -amp
+            c.cur = 0
+        self._msgs_cur = 0
+        self._msgs[0][: self.E2] = 1.0
+        self._lmbds[:] = 1.0
+        self._lmbd_stride = 2
+
+    def tensors_numpy(self) -> dict:
+        """{degree: (B, 2, D, ..., D)} copies on the host."""
+        D = self.D
+        return {c.degree: self._to_host(c.T[c.cur][: c.B * 2 * D ** c.degree]).reshape((c.B, 2) + (D,) * c.degree)
+                for c in self.classes}
+
+    def msgs_numpy(self) -> np.ndarray:
+        D = self.D
+        return self._to_host(self.msgs_buffer[: self.E2 * D * D]).reshape(self.E2, D, D)
+
+    def lmbds_numpy(self) -> np.ndarray:
+        s = self._lmbd_stride
+        return self._to_host(self._lmbds[: self.L * s]).reshape(self.L, s)[:, : self.D].copy()
+
+    def state_to_host(self) -> dict:
+        """Checkpoint of the run-time state (the reference has none)."""
+        return {"D": self.D, "tensors": self.tensors_numpy(), "msgs": self.msgs_numpy(), "lmbds": self.lmbds_numpy()}
+
+    def load_state(self, snap: dict) -> None:
+        """Uploads a checkpoint / an oracle state: tensors {degree: (B, 2, D..)}, msgs (2L, D, D), lmbds (L, D)."""
+        D = int(snap["D"])
+        if not 1 <= D <= self.Dmax:
+            raise ValueError(f"bond dimension {D} outside [1, {self.Dmax}]")
+        np_c = np.complex64 if self.precision == "single" else np.complex128
+        for c in self.classes:
+            t = np.ascontiguousarray(np.asarray(snap["tensors"][c.degree]).astype(np_c)).reshape(-1)
+            assert t.shape[0] == c.B * 2 * D ** c.degree, "tensor batch has the wrong shape"
+            c.cur = 0
+            c.T[0][: t.shape[0]].copy_(torch.from_numpy(t).to(self.dev))
+        m = np.ascontiguousarray(np.asarray(snap["msgs"]).astype(np_c)).reshape(-1)
+        assert m.shape[0] == self.E2 * D * D
+        self._msgs_cur = 0
+        self._msgs[0][: m.shape[0]].copy_(torch.from_numpy(m).to(self.dev))
+        lm = np.zeros((self.L, 2 * D), self.np_rdtype)
+        lm[:, :D] = np.real(np.asarray(snap["lmbds"]))
+        self._lmbd_stride = 2 * D
+        self._lmbds[: lm.size].copy_(torch.from_numpy(lm.reshape(-1)).to(self.dev))
+        self.D = D
+
+    # ------------------------------------------------------------------------------------------
+    # BP  (state.py:97-124)
+    # ------------------------------------------------------------------------------------------
+    def _enqueue_sweep(self, it: int, write_undamped: bool) -> None:
+        D = self.D
+        cur = self._msgs[(self._msgs_cur + it) % 2]
+        nxt = self._msgs[(self._msgs_cur + it + 1) % 2]
+        st = self._stream()
+        for c in self.classes:
+            if c.degree == 0:
+                continue
+            self.lib.bp_sweep(self.prec, c.degree, D, c.B, c.T[c.cur].data_ptr(), cur.data_ptr(), nxt.data_ptr(),
+                              c.in_pos.data_ptr(), c.out_pos.data_ptr(), self.damping, int(write_undamped),
+                              self.bp_eps, it, self._resid.data_ptr(), self._status.data_ptr(),
+                              self._ws.data_ptr(), self._ws.numel(), st)
+        self._after_sweep(it, nxt)
+
+    def _after_sweep(self, it: int, nxt: torch.Tensor) -> None:
+        """Hook for the partitioned engine: halo exchange + residual all-reduce (no-op on one GPU)."""
+
+    def run_bp(self) -> int:
+        max_it = self.max_iters
+        assert max_it > 0, "max_bp_iter_number must be positive"      # reference: assert best_msgs is not None
+        self._ensure_ws(self.D, self.D)
+        self._ctrl.zero_()
+        eps = self.np_rdtype(self.bp_eps)
+        it = 0
+        done = False
+        sweeps = max_it
+        while it < max_it and not done:
+            n = min(self._bp_chunk, max_it - it)
+            for _ in range(n):
+                self._enqueue_sweep(it, write_undamped=(it == max_it - 1))
+                it += 1
+            ctrl = self._to_host(self._ctrl)                 # one D2H + sync per chunk of sweeps
+            resid = ctrl[: self._ctrl_rbytes].view(self.np_rdtype).reshape(-1, 2)
+            status = ctrl[self._ctrl_rbytes:].view(np.int32)
+            if status[0]:                                    # a later sweep saw convergence on the device
+                done, sweeps = True, int(status[1])
+            else:                                            # the last enqueued sweep is tested here
+                num, den = resid[it - 1]
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    if np.sqrt(num / den) < eps:
+                        done, sweeps = True, it
+        num, den = resid[sweeps - 1]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            dist = float(np.sqrt(num / den))
+        if done:
+            # converged: keep the *input* of the converging sweep (state.py:118-120)
+            self._msgs_cur = (self._msgs_cur + sweeps - 1) % 2
+            log.debug(f"BP algorithm completed after {sweeps - 1} iterations")
+        else:
+            # cap reached: the last, undamped sweep output becomes the state (state.py:122-124)
+            self._msgs_cur = (self._msgs_cur + max_it) % 2
+            log.warning(f"BP algorithm exceeds iterations limit set to {max_it}, obtained bp_eps {dist}")
+        self.stats["bp_sweeps"].append(sweeps)
+        self.stats["bp_dist"].append(dist)
+        # next run: enqueue about as many sweeps as this one needed before the first status read
+        self._bp_chunk = int(min(max(sweeps + 1, 2), 64))
+        return sweeps
+
+    # ------------------------------------------------------------------------------------------
+    # one annealing step  (state.py:230-247, :142-156, :219-227, :315-321)
+    # ------------------------------------------------------------------------------------------
+    def _reduce_colmax(self, colmax: torch.Tensor) -> None:
+        """Hook for the partitioned engine (all-reduce max); no-op on one GPU."""
+
+    def run_layer(self, xtime: float, ztime: float) -> None:
+        D = self.D
+        st = self._stream()
+        self._ensure_ws(D, min(2 * D, self.Dmax))
+        self._ensure_edge_buffers(D)
+        cur = self.msgs_buffer
+        for c in self.classes:
+            if c.degree == 0:
+                continue
+            self.lib.ext_msgs(self.prec, c.degree, D, c.B, c.T[c.cur].data_ptr(), cur.data_ptr(),
+                              self._ext.data_ptr(), c.in_pos.data_ptr(), c.out_pos.data_ptr(),
+                              c.edge_ampls.data_ptr(), float(ztime), self._ws.data_ptr(), self._ws.numel(), st)
+        self._exchange_ext()
+        self._colmax.zero_()
+        self.lib.canonicalize(self.prec, D, self.L, self._ext.data_ptr(), self._canon.data_ptr(),
+                              self._lmbds.data_ptr(), self._colmax.data_ptr(), self.pinv_eps, st)
+        self._lmbd_stride = 2 * D
+        self._reduce_colmax(self._colmax)
+        colmax = self._to_host(self._colmax)[: 2 * D].astype(np.float64)        # the one host sync per step
+        rank = 2 * D - int(np.sum(colmax < self.pinv_eps))                        # backends.py:297-303
+        Dn = min(rank, self.Dmax)
+        err = float(np.sqrt(np.sum(colmax[Dn:] ** 2)))
+        if Dn < 1:
+            raise FloatingPointError("all singular values fell below pinv_eps: the state collapsed")
+        log.info(f"Truncation performed, per edge error upper bound: {err}")
+        msgs_out = self._msgs[0]
+        for c in self.classes:
+            self.lib.apply_update(self.prec, c.degree, D, Dn, c.B, c.T[c.cur].data_ptr(), c.T[1 - c.cur].data_ptr(),
+                                  self._canon.data_ptr(), self._lmbds.data_ptr(), msgs_out.data_ptr(),
+                                  c.in_pos.data_ptr(), c.out_pos.data_ptr(), c.lmbd_pos.data_ptr(),
+                                  c.node_ampls.data_ptr(), c.edge_ampls.data_ptr(), float(ztime), float(xtime),
+                                  self._ws.data_ptr(), self._ws.numel(), st)
+            c.cur = 1 - c.cur
+        self._msgs_cur = 0
+        self.D = Dn
+        self.stats["bond_dims"].append(Dn)
+        self.stats["trunc_err"].append(err)
+        log.debug(f"Layer of interaction gates with truncation has been applied, current bond dimension is {Dn}")
+        self._after_update()
+        self.run_bp()
+        log.info(f"Layer with ztime {ztime} and xtime {xtime} has been applied")
+
+    def _exchange_ext(self) -> None:
+        """Hook for the partitioned engine (extended messages of cut edges); no-op on one GPU."""
+
+    def _after_update(self) -> None:
+        """Hook for the partitioned engine (halo slots of the re-initialised messages); no-op on one GPU."""
+
+    # ------------------------------------------------------------------------------------------
+    # marginals  (state.py:77-94, utils.py:23-27)
+    # ------------------------------------------------------------------------------------------
+    def _compute_bloch(self) -> None:
+        D = self.D
+        self._ensure_ws(D, D)
+        st = self._stream()
+        cur = self.msgs_buffer
+        for c in self.classes:
+            self.lib.density(self.prec, c.degree, D, c.B, c.T[c.cur].data_ptr(), cur.data_ptr(),
+                             c.in_pos.data_ptr(), c.node_ids.data_ptr(), self._bloch.data_ptr(),
+                             self._ws.data_ptr(), self._ws.numel(), st)
+
+    def bloch_vectors(self) -> np.ndarray:
+        """(N, 3) array of (x, y, z) per qubit in node-id order."""
+        self._compute_bloch()
+        log.info("Density matrices have been computed")
+        return self._to_host(self._bloch).reshape(self.N, 4)[:, :3].astype(np.float64)
+
+    def density_matrices(self) -> np.ndarray:
+        """(N, 2, 2) trace-normalised single-qubit density matrices (state.py:77-94)."""
+        b = self.bloch_vectors()
+        rho = np.empty((self.N, 2, 2), np.complex128)
+        rho[:, 0, 0] = 0.5 * (1 + b[:, 2])
+        rho[:, 1, 1] = 0.5 * (1 - b[:, 2])
+        rho[:, 0, 1] = 0.5 * (b[:, 0] - 1j * b[:, 1])
+        rho[:, 1, 0] = 0.5 * (b[:, 0] + 1j * b[:, 1])
+        return rho
+
+    # ------------------------------------------------------------------------------------------
+    # sampling  (state.py:250-312)
+    # ------------------------------------------------------------------------------------------
+    def measure(self) -> list:
+        st = self._stream()
+        outcomes = torch.zeros(self.N, dtype=torch.int32, device=self.dev)
+        log.debug("Measurement outcomes sampling started")
+        while True:
+            self._compute_bloch()
+            self.lib.argmax_unmeasured(self.prec, self.N, self._bloch.data_ptr(), outcomes.data_ptr(),
+                                       self._argmax_i.data_ptr(), self._argmax_p.data_ptr(), st)
+            node, left = (int(v) for v in self._to_host(self._argmax_i))
+            if left == 0:
+                break
+            p0 = float(self._to_host(self._argmax_p)[0])
+            u = self.rng.uniform(0.0, 1.0)                  # one draw per pass, same stream as the reference
+            bit = 0 if p0 > u else 1
+            log.debug(f"Node {node} the most determined (spin-up probability {p0} and spin-down probability {1 - p0}) and has been measured")
+            c = self.classes[int(self._node_class[node])]
+            self.lib.project_node(self.prec, c.degree, self.D, c.T[c.cur].data_ptr(), int(self._node_slot[node]), bit, st)
+            outcomes[node] = 1 - 2 * bit
+            self.run_bp()
+            self._compute_bloch()
+            self._nproj.zero_()
+            for c in self.classes:
+                self.lib.threshold_project(self.prec, c.degree, self.D, c.B, c.T[c.cur].data_ptr(), c.node_ids.data_ptr(),
+                                           self._bloch.data_ptr(), outcomes.data_ptr(), self.threshold,
+                                           self._nproj.data_ptr(), st)
+            self.run_bp()
+        log.info("Measurement outcomes sampling completed")
+        return [int(v) for v in self._to_host(outcomes)]

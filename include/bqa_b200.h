@@ -1,0 +1,115 @@
+/* bqa_b200.h -- C ABI of libbqa_b200.so: the sm_100a kernels behind bqa's backend interface.
+ *
+ * The reference (LuchnikovI/bqa v0.1.6) has no FFI of its own: its plugin boundary is the Python ABC
+ * `bqa.backends.Tensor` plus the registry dict `BACKEND_STR_TO_BACKEND` (src/bqa/backends.py:26-252) and
+ * the engine calls in src/bqa/state.py.  Each entry point below is the fused device-side replacement of
+ * one group of those calls; the Python side (bqa_b200/engine.py, bqa_b200/backend.py) binds them with
+ * ctypes.  See INTEGRATION.md for the binding a bqa maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - complex arrays are interleaved (re, im): complex64 when prec == BQA_C64, complex128 when BQA_C128;
+ *     "real" arrays are float / double accordingly;
+ *   - tensors of a degree class: (B, 2, D, ..., D) row-major, d bond legs (state.py:24-29);
+ *     messages: (2L, D, D) row-major [slot][bra][ket];  index arrays: int32, shape (d, B) leg-major;
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - every function returns 0 on success; otherwise bqa_b200_last_error() describes the failure
+ *     (thread-local string).  Nothing here falls back to the CPU.
+ */
+#ifndef BQA_B200_H
+#define BQA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BQA_C64 0
+#define BQA_C128 1
+
+#define BQA_B200_MAX_BOND_DIM 16
+#define BQA_B200_MAX_DEGREE 8
+
+const char* bqa_b200_last_error(void);
+int bqa_b200_version(void);
+/* number of this library's kernel launches since load (bench.py reports it as gpu_launches) */
+long long bqa_b200_launch_count(void);
+
+/* bytes of device scratch the node kernels need for a degree class (pass the max over classes) */
+size_t bqa_b200_workspace_bytes(int prec, int degree, int D, int D_new);
+
+/* ---- K1 + K2: one BP sweep over a degree class ------------------------------------------------
+ * replaces, per sweep and class: batch_slice gathers (state.py:109), Tensor.pass_msgs
+ * (backends.py:406-408), assign_at_batch_indices scatters (state.py:111-112), get_dist (state.py:113,
+ * backends.py:492-495) and make_inplace_damping_update (state.py:121, backends.py:539-540).
+ *
+ * reads msgs_cur, writes msgs_nxt[out_pos] = damping * msgs_cur[out_pos] + (1 - damping) * new
+ * (the undamped `new` when write_undamped != 0: the reference keeps the undamped last sweep when the
+ * iteration cap is hit, state.py:122-123).  resid is a real array [max_iters][2]; sweep `it` folds
+ * max |new - old|^2 and max |new + old|^2 into resid[it] with atomic max.  Device-side early exit:
+ * sweep it > 0 first tests resid[it-1] (sqrt(num/den) < bp_eps) and, if converged, sets
+ * status[0] = 1, status[1] = it and returns without touching the messages -- so the host can enqueue
+ * sweeps ahead without a sync per sweep.  resid and status must be zeroed before sweep 0. */
+int bqa_b200_bp_sweep(int prec, int degree, int D, long long B, const void* T, const void* msgs_cur,
+                      void* msgs_nxt, const int32_t* in_pos, const int32_t* out_pos, double damping,
+                      int write_undamped, double bp_eps, int it, void* resid, int32_t* status,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K3a: ZZ-extended messages of a degree class -----------------------------------------------
+ * replaces _get_extended_msgs (state.py:127-139): pass_msgs with evolution_times, i.e. the open leg is
+ * extended D -> 2D by the ZZ half gate (backends.py:519-526) with theta = edge_ampl * ztime.
+ * ext: (2L, 2D, 2D).  edge_ampls: real (d, B). */
+int bqa_b200_ext_msgs(int prec, int degree, int D, long long B, const void* T, const void* msgs_cur,
+                      void* ext, const int32_t* in_pos, const int32_t* out_pos, const void* edge_ampls,
+                      double ztime, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K3b: canonicalizers + lambdas of every undirected edge ------------------------------------
+ * replaces _get_canonicalizers (state.py:171-200): masked SVD of every extended message
+ * (backends.py:483-490, 709-727), ker = lu_f lu_b^T, masked SVD of ker, canonicalizers = [ul_b vs ; ul_f us],
+ * lmbds = s / |s|.  ext, canon: (2L, 2D, 2D); lmbds: real (L, 2D); colmax: real (2D), zeroed by the
+ * caller, receives the column-wise max of lmbds over all edges (truncate_lmbds, backends.py:297-299). */
+int bqa_b200_canonicalize(int prec, int D, long long L, const void* ext, void* canon, void* lmbds,
+                          void* colmax, double pinv_eps, void* stream);
+
+/* ---- K3c + K4: apply the simple update to a degree class ---------------------------------------
+ * replaces batch_truncate_all_but + apply_canonicalizers_with_extensions (state.py:235-246,
+ * backends.py:416-432), _apply_z_layer / _apply_x_layer (state.py:142-156, backends.py:506-510) and
+ * _set_to_symmetric_gauge (state.py:219-227, backends.py:450-462) incl. the message re-initialisation
+ * msgs[p] = diag(lmbd[p mod L]) / trace (state.py:56-57).
+ * T_in: (B, 2, D^d) -> T_out: (B, 2, D_new^d); canon: (2L, 2D, 2D) (first D_new columns are used);
+ * lmbds: real (L, 2D) (first D_new entries are used); msgs_out: (2L, D_new, D_new);
+ * node_ampls: real (B); edge_ampls: real (d, B). */
+int bqa_b200_apply_update(int prec, int degree, int D, int D_new, long long B, const void* T_in,
+                          void* T_out, const void* canon, const void* lmbds, void* msgs_out,
+                          const int32_t* in_pos, const int32_t* out_pos, const int32_t* lmbd_pos,
+                          const void* node_ampls, const void* edge_ampls, double ztime, double xtime,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K5a: single-qubit marginals of a degree class ---------------------------------------------
+ * replaces get_density_matrices (state.py:77-94, backends.py:440-448) + Bloch conversion (utils.py:23-27).
+ * bloch: real (N, 4) = (x, y, z, p0) written at rows node_ids[i]. */
+int bqa_b200_density(int prec, int degree, int D, long long B, const void* T, const void* msgs,
+                     const int32_t* in_pos, const int32_t* node_ids, void* bloch, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
+/* ---- K5b: sampling helpers (measure, state.py:250-312) -----------------------------------------
+ * outcomes: int32 (N), 0 = not measured yet, +1 / -1 = measured (state.py:276).
+ * argmax: result[0] = first node id maximising |2 p0 - 1| among unmeasured (state.py:301), result[1] =
+ * number of unmeasured nodes; result_p0[0] = its p0.  result: int32[2], result_p0: real[1]. */
+int bqa_b200_argmax_unmeasured(int prec, long long N, const void* bloch, const int32_t* outcomes,
+                               int32_t* result, void* result_p0, void* stream);
+/* project node at class position `pos` onto bit `bit` (zero the other physical slice, renormalise the
+ * node; backends.py:729-734 divides the whole class batch instead, which is a pure gauge) */
+int bqa_b200_project_node(int prec, int degree, int D, void* T, long long pos, int bit, void* stream);
+/* project every unmeasured node of the class with p0 > thr (bit 0) or p0 < 1 - thr (bit 1) and record
+ * the outcome (state.py:286-296); n_projected (int32[1]) is incremented by the number of projections */
+int bqa_b200_threshold_project(int prec, int degree, int D, long long B, void* T, const int32_t* node_ids,
+                               const void* bloch, int32_t* outcomes, double thr, int32_t* n_projected,
+                               void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BQA_B200_H */

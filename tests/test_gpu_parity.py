@@ -1,0 +1,168 @@
+"""GPU parity tests (-m gpu): the CUDA path, reached through the C ABI, against the reference goldens,
+against the oracle on seeded instances, and through size-independent properties at full size."""
+import os
+
+import numpy as np
+import pytest
+
+import instances
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from bqa_b200 import _lib
+    from bqa_b200.build import build
+    build()
+    lib = _lib.load_library()
+    assert lib.version() > 0, "the CUDA build must be the one that is loaded"
+    return lib
+
+
+def _run(cfg, precision):
+    from bqa_b200.config import config_to_context
+    from bqa_b200.core import run_context
+    from bqa_b200.engine import Engine
+    holder = {}
+
+    class Probe(Engine):
+        def __init__(self, *a, **k):
+            super().__init__(*a, **k)
+            holder["e"] = self
+
+    res = dict(run_context(config_to_context(cfg), precision=precision, engine_cls=Probe))
+    return res, holder["e"]
+
+
+@pytest.mark.parametrize("name", list(instances.GOLDEN_CONFIGS))
+def test_goldens_double(golden_dir, lib, name):
+    g = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    before = lib.launch_count()
+    res, eng = _run(instances.GOLDEN_CONFIGS[name](), "double")
+    assert lib.launch_count() > before
+    assert np.abs(np.array(res["bloch_vectors"]) - g["bloch"]).max() < 1e-8
+    n = len(g["bond_dims"])
+    assert eng.stats["bond_dims"] == g["bond_dims"].tolist()
+    assert eng.stats["bp_sweeps"][:n] == g["bp_sweeps"].tolist()
+    if "outcomes" in g:
+        assert res["measurement_outcomes"] == g["outcomes"].tolist()     # same host RNG stream => same bitstring
+
+
+@pytest.mark.parametrize("name", ["ring24", "grid4", "comb", "small6"])
+def test_goldens_single(golden_dir, lib, name):
+    # fp32 tolerance: <= 5e-3 max-abs and <= 1e-4 mean-abs... on Bloch components
+    g = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    res, eng = _run(instances.GOLDEN_CONFIGS[name](), "single")
+    diff = np.abs(np.array(res["bloch_vectors"]) - g["bloch"])
+    assert diff.max() < 5e-3 and diff.mean() < 5e-4
+    assert eng.stats["bond_dims"] == g["bond_dims"].tolist()
+
+
+@pytest.mark.parametrize("prec_name", ["double", "single"])
+@pytest.mark.parametrize("d,D", [(1, 3), (2, 4), (3, 4), (3, 2), (4, 3)])
+def test_kernel_level_goldens(golden_dir, lib, d, D, prec_name):
+    import torch
+    from bqa_b200 import _lib
+    from oracle import bqa_oracle as O
+    g = np.load(os.path.join(golden_dir, "kernel_level.npz"))
+    dbl = prec_name == "double"
+    prec = _lib.C128 if dbl else _lib.C64
+    cdt, rdt = (np.complex128, np.float64) if dbl else (np.complex64, np.float32)
+    tol = 1e-12 if dbl else 2e-5
+    B = 5
+    t, msgs, thetas = instances.random_node_batch(B, d, D, seed=100 + 10 * d + D)
+    dev = torch.device("cuda:0")
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    T = up(t.astype(cdt).reshape(-1))
+    cur = up(np.concatenate(msgs, 0).astype(cdt).reshape(-1))
+    in_pos = up(np.arange(d * B, dtype=np.int32).reshape(d, B))
+    nxt = torch.zeros_like(cur)
+    resid = torch.zeros(2, dtype=torch.float64 if dbl else torch.float32, device=dev)
+    status = torch.zeros(4, dtype=torch.int32, device=dev)
+    ws = torch.zeros(lib.workspace_bytes(prec, d, D, D), dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    lib.bp_sweep(prec, d, D, B, T.data_ptr(), cur.data_ptr(), nxt.data_ptr(), in_pos.data_ptr(), in_pos.data_ptr(),
+                 0.0, 0, 1e-6, 0, resid.data_ptr(), status.data_ptr(), ws.data_ptr(), ws.numel(), st)
+    got = nxt.cpu().numpy().reshape(d, B, D, D)
+    assert np.abs(got - g[f"pass_d{d}_D{D}"]).max() < tol
+    new, old = g[f"pass_d{d}_D{D}"], np.stack(msgs)
+    r = resid.cpu().numpy().astype(np.float64)
+    assert np.isclose(np.sqrt(r[0] / r[1]), np.abs(new - old).max() / np.abs(new + old).max(), rtol=1e-9 if dbl else 1e-4)
+    ext = torch.zeros(d * B * 4 * D * D, dtype=T.dtype, device=dev)
+    ea = up(np.stack(thetas).astype(rdt))
+    lib.ext_msgs(prec, d, D, B, T.data_ptr(), cur.data_ptr(), ext.data_ptr(), in_pos.data_ptr(), in_pos.data_ptr(),
+                 ea.data_ptr(), 1.0, ws.data_ptr(), ws.numel(), st)
+    assert np.abs(ext.cpu().numpy().reshape(d, B, 2 * D, 2 * D) - g[f"ext_d{d}_D{D}"]).max() < tol
+    bloch = torch.zeros(B * 4, dtype=resid.dtype, device=dev)
+    ids = torch.arange(B, dtype=torch.int32, device=dev)
+    lib.density(prec, d, D, B, T.data_ptr(), cur.data_ptr(), in_pos.data_ptr(), ids.data_ptr(), bloch.data_ptr(),
+                ws.data_ptr(), ws.numel(), st)
+    assert np.abs(bloch.cpu().numpy().reshape(B, 4)[:, :3] - O.bloch_vectors(g[f"rho_d{d}_D{D}"])).max() < tol
+
+
+def _rr_config(n, steps, total_time, tail, seed=42, **extra):
+    from bqa_b200.benchmarking import generate_qubo_on_random_regular_graph
+    nodes, edges = generate_qubo_on_random_regular_graph(n, 3, seed=seed)
+    return {"nodes": nodes, "edges": edges, "max_bond_dim": 4,
+            "schedule": {"total_time": total_time, "starting_mixing": 1.0,
+                         "actions": [{"weight": 1.0, "steps_number": steps, "final_mixing": 0.0}, *tail]}, **extra}
+
+
+def test_random_regular_2000_vs_oracle(lib):
+    """Seeded 3-regular QUBO, dt = 0.2 like the 100k benchmark script, against the oracle (complex128)."""
+    from bqa_b200.benchmarking import ising_energy
+    from oracle import bqa_oracle as O
+    cfg = _rr_config(2000, 30, 6.0, ["get_bloch_vectors"])
+    want, octx, ost = O.run_qa(cfg, return_state=True)
+    want = np.array(want[0][1])
+    res, eng = _run(cfg, "double")
+    got = np.array(res["bloch_vectors"])
+    assert np.abs(got - want).max() < 1e-7
+    assert eng.stats["bond_dims"] == ost.stats["bond_dims"]
+    assert eng.stats["bp_sweeps"] == ost.stats["bp_sweeps"][:len(eng.stats["bp_sweeps"])]
+    res32, eng32 = _run(cfg, "single")
+    got32 = np.array(res32["bloch_vectors"])
+    diff = np.abs(got32 - want)
+    assert diff.max() < 5e-3 and diff.mean() < 1e-4                     # stated fp32 tolerance
+    assert eng32.stats["bond_dims"] == ost.stats["bond_dims"]
+    assert np.abs(np.array(eng32.stats["bp_sweeps"]) - np.array(ost.stats["bp_sweeps"])).max() <= 1
+    s_ref = np.where(want[:, 2] > 0, 1, -1)
+    s_32 = np.where(got32[:, 2] > 0, 1, -1)
+    e_ref = ising_energy(cfg["edges"], cfg["nodes"], s_ref)
+    e_32 = ising_energy(cfg["edges"], cfg["nodes"], s_32)
+    assert abs(e_32 - e_ref) <= 1e-4 * abs(e_ref)                         # 1e-4 relative on the energy
+
+
+def test_full_size_properties_100k(lib):
+    """100k-qubit 3-regular QUBO (BASELINE config 4), fp32: invariants that need no oracle run."""
+    import torch
+    cfg = _rr_config(100_000, 30, 6.0, [])
+    from bqa_b200.config import config_to_context
+    from bqa_b200.engine import Engine
+    eng = Engine(config_to_context(cfg), precision="single")
+    layers = [i for i in eng.ctx.instructions if isinstance(i, dict)]
+    for ins in layers:
+        eng.run_layer(ins["xtime"], ins["ztime"])
+    assert eng.D == 4
+    D = eng.D
+    m = eng.msgs_buffer[: eng.E2 * D * D].view(eng.E2, D, D)
+    tr = torch.diagonal(m, dim1=1, dim2=2).sum(1)
+    assert float((tr - 1).abs().max()) < 1e-5                             # messages are trace-normalised
+    assert float((m - m.transpose(1, 2).conj()).abs().max()) < 1e-5       # ... and Hermitian
+    c = eng.classes[0]
+    t = c.T[c.cur][: c.B * 2 * D ** 3].view(c.B, -1)
+    assert float((torch.linalg.vector_norm(t, dim=1) - 1).abs().max()) < 1e-5   # node tensors are L2-normalised
+    lm = eng.lmbds_numpy()
+    assert np.all(lm >= 0) and np.all(np.diff(lm, axis=1) <= 1e-6)              # lambdas sorted descending
+    # BP fixed point: one more run converges immediately and leaves the marginals unchanged
+    b0 = eng.bloch_vectors()
+    sweeps = eng.run_bp()
+    assert sweeps <= 2
+    assert np.abs(eng.bloch_vectors() - b0).max() < 1e-4
+    assert np.all(np.abs(b0) <= 1 + 1e-5) and np.all(np.linalg.norm(b0, axis=1) <= 1 + 1e-4)
+    # checkpoint round trip is exact
+    snap = eng.state_to_host()
+    eng2 = Engine(eng.ctx, precision="single")
+    eng2.load_state(snap)
+    assert np.abs(eng2.bloch_vectors() - eng.bloch_vectors()).max() == 0.0

@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""bench.py -- annealing steps/s and BP msg-updates/s on the 100k-qubit random 3-regular QUBO (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]              our arm (CUDA kernels through the C ABI)
+    python bench.py --impl reference [--steps K] [--warmup W]        reference arm (CPU oracle port, host cores)
+
+A "step" is one annealing step = one ``run_layer`` (reference src/bqa/state.py:315-321): simple update
+(extended messages, canonicalizers, truncation, Rz/Rx, symmetric gauge) followed by BP to convergence.
+
+Workload (BASELINE.md section 2 protocol): ``generate_qubo_on_random_regular_graph(100_000, 3, seed=42)``,
+max_bond_dim 4, bp_eps = pinv_eps = 1e-6, damping 0, max_bp_iter_number 75, dt = 0.2 like
+benchmarks_against_mqlib/random_3_regular_qubo_100000.py, schedule ``total_time = 0.2 S, steps_number = S``,
+mixing 1 -> 0; the first RAMP steps (bond dimension 1 -> 4) are executed untimed, then W warm-up steps, then
+exactly K timed steps of the same schedule.  complex64 (what the reference's GPU backend uses).
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for the definition of every key.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_QUBITS = 100_000
+SCHEDULE_STEPS = 100          # S
+RAMP = 30                     # untimed steps that take the bond dimension from 1 to 4
+DT = 0.2
+CPU_SAMPLE_QUBITS = 5_000     # bounded sample for the CPU legs (see cpu_baseline.sample)
+METRIC = "annealing steps/s @100k-qubit random 3-regular QUBO (D=4, complex64)"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def make_config(n: int, total_steps: int) -> dict:
+    from bqa_b200.benchmarking import generate_qubo_on_random_regular_graph
+    nodes, edges = generate_qubo_on_random_regular_graph(n, 3, seed=42)
+    return {"nodes": nodes, "edges": edges, "max_bond_dim": 4, "bp_eps": 1e-6, "pinv_eps": 1e-6,
+            "damping": 0.0, "max_bp_iter_number": 75, "seed": 42, "default_field": 0.0,
+            "measurement_threshold": 0.95, "backend": "b200",
+            "schedule": {"total_time": DT * total_steps, "starting_mixing": 1.0,
+                         "actions": [{"type": "real_time_evolution", "weight": 1.0, "steps_number": total_steps,
+                                      "final_mixing": 0.0}]}}
+
+
+def schedule_len(steps: int, warmup: int) -> int:
+    return max(SCHEDULE_STEPS, RAMP + warmup + 2 * steps + 2)
+
+
+# -------------------------------------------------------------------------------------------------
+# clocks (B200_PROFILING.md "clocks DURING the timed region")
+# -------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0])); smax.append(float(f[1])); power.append(float(f[2]))
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w": float(np.median(power)) if power else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# -------------------------------------------------------------------------------------------------
+# CPU legs: the oracle port of the reference numpy backend on the host cores
+# -------------------------------------------------------------------------------------------------
+def cpu_steps_per_s(n_sample: int, steps: int, warmup: int, inject=None) -> dict:
+    """Times `steps` steady-state (D = 4) annealing steps of the oracle on an n_sample-qubit instance of the
+    same generator/schedule and scales by n_sample / 100k (cost is linear in the qubit count; the measured
+    per-qubit cost grows slightly with size, BASELINE.md section 2, so the scaling flatters the CPU).
+    `inject` = (engine factory) lets the GPU arm hand over a D = 4 state instead of ramping on the CPU."""
+    from oracle import bqa_oracle as O
+    total = schedule_len(steps, warmup)
+    cfg = make_config(n_sample, total)
+    octx = O.compile_config(cfg)
+    layers = [i for i in octx.instructions if isinstance(i, dict)]
+    ost = O.init_state(octx)
+    t_ramp = time.perf_counter()
+    if inject is not None:
+        snap = inject(cfg, layers[:RAMP])
+        ost.tensors = {d: np.asarray(t, octx.dtype) for d, t in snap["tensors"].items()}
+        ost.msgs = np.asarray(snap["msgs"], octx.dtype)
+        ost.lmbds = np.asarray(snap["lmbds"], octx.dtype)
+        how = "D=4 state handed over from the GPU run"
+    else:
+        for ins in layers[:RAMP]:
+            O.run_layer(octx, ost, ins["xtime"], ins["ztime"])
+        how = f"ramped on the CPU ({RAMP} untimed steps)"
+    t_ramp = time.perf_counter() - t_ramp
+    assert ost.bond_dim == 4, f"bond dimension {ost.bond_dim} after the ramp"
+    k = RAMP
+    for ins in layers[k:k + warmup]:
+        O.run_layer(octx, ost, ins["xtime"], ins["ztime"])
+    k += warmup
+    n0 = len(ost.stats["bp_sweeps"])
+    t0 = time.perf_counter()
+    for ins in layers[k:k + steps]:
+        O.run_layer(octx, ost, ins["xtime"], ins["ztime"])
+    dt = time.perf_counter() - t0
+    sweeps = ost.stats["bp_sweeps"][n0:]
+    scale = n_sample / N_QUBITS
+    return {"value": steps / dt * scale, "unit": "steps/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": (f"{steps} steady-state steps (D=4, complex128 like the reference default) of a "
+                       f"{n_sample}-qubit instance of the same generator and schedule, {how}; "
+                       f"{dt / steps:.3f} s/step measured, scaled by {n_sample}/{N_QUBITS} to 100k qubits; "
+                       f"numpy/OpenBLAS may use all {os.cpu_count()} host cores"),
+            "s_per_step_sample": dt / steps, "sweeps_per_step": float(np.mean(sweeps)) if sweeps else None,
+            "ramp_s": t_ramp}
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = args.steps, args.warmup
+    t0 = time.perf_counter()
+    r = cpu_steps_per_s(CPU_SAMPLE_QUBITS, steps, warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "steps/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": 1e3 / r["value"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
+            "config": make_bench_config(args.gpus),
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "sweeps_per_step": r["sweeps_per_step"], "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line), flush=True)
+
+
+def make_bench_config(n_gpus: int) -> dict:
+    return {"workload": "random 3-regular QUBO, 100,000 qubits (BASELINE.json configs[3]), "
+                        "generate_qubo_on_random_regular_graph(100000, 3, seed=42)",
+            "max_bond_dim": 4, "bp_eps": 1e-6, "pinv_eps": 1e-6, "damping": 0.0, "dt": DT,
+            "schedule": f"total_time=0.2*S, steps=S>={SCHEDULE_STEPS}, mixing 1->0; first {RAMP} steps untimed (D 1->4)",
+            "partition": "none" if n_gpus == 1 else f"node-partitioned over {n_gpus} GPUs, halo exchange per BP sweep",
+            "l2": "state (T 102 MB + 2 x 38 MB messages + ext/canon 2 x 154 MB) exceeds the 126 MB L2; no explicit flush"}
+
+
+# -------------------------------------------------------------------------------------------------
+# our arm
+# -------------------------------------------------------------------------------------------------
+def run_ours(args) -> None:
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            # convenience: re-launch under torchrun
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000), __file__,
+                   "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)]
+            raise SystemExit(subprocess.call(cmd))
+        raise SystemExit(f"--gpus {args.gpus} does not match WORLD_SIZE {world}")
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from bqa_b200 import _lib
+    from bqa_b200.build import build
+    from bqa_b200.config import config_to_context
+    if rank == 0:
+        build()
+    if world > 1:
+        dist.barrier()
+    lib = _lib.load_library()
+    steps, warmup = args.steps, args.warmup
+    total = schedule_len(steps, warmup)
+    t_setup = time.perf_counter()
+    cfg = make_config(N_QUBITS, total)
+    ctx = config_to_context(cfg)
+    layers = [i for i in ctx.instructions if isinstance(i, dict)]
+    if world == 1:
+        from bqa_b200.engine import Engine
+        eng = Engine(ctx, precision="single", device=dev)
+    else:
+        from bqa_b200.partitioned import PartitionedEngine
+        eng = PartitionedEngine(ctx, precision="single", device=dev)
+    log(f"[rank {rank}] setup {time.perf_counter() - t_setup:.1f} s")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    k = 0
+    for ins in layers[:RAMP]:
+        eng.run_layer(ins["xtime"], ins["ztime"])
+    k = RAMP
+    assert eng.D == 4, f"bond dimension {eng.D} after the ramp"
+    for ins in layers[k:k + warmup]:
+        eng.run_layer(ins["xtime"], ins["ztime"])
+    k += warmup
+    snapshot = eng.state_to_host(pinned=True) if world == 1 else None
+
+    # ---- timed region: exactly K steps, state resident in HBM --------------------------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    n0 = len(eng.stats["bp_sweeps"])
+    launches0 = lib.launch_count()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tw0 = time.perf_counter()
+    ev0.record()
+    for ins in layers[k:k + steps]:
+        eng.run_layer(ins["xtime"], ins["ztime"])
+    ev1.record()
+    barrier()
+    tw1 = time.perf_counter()
+    ms = ev0.elapsed_time(ev1)
+    launches = lib.launch_count() - launches0
+    sweeps = eng.stats["bp_sweeps"][n0:]
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop(tw0, tw1) if sampler else None
+    bloch_resident = eng.bloch_vectors()
+
+    # ---- instrumented pass: per-launch duration of the dominant kernel (BP sweep) ------------
+    roof = measure_roofline(eng, lib, layers[k + steps:k + 2 * steps], torch, dev) if rank == 0 or world > 1 else None
+
+    # ---- end-to-end through the public engine API with HOST buffers --------------------------
+    e2e = None
+    if world == 1:
+        e2e = measure_e2e(eng, snapshot, layers[k:k + steps], torch, dev, bloch_resident)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    E2 = int(ctx.edges_number)
+    value = steps / (ms * 1e-3)
+    bp_updates = float(np.sum(sweeps)) * E2
+    line = {"metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "c64", "data": "synthetic", "config": make_bench_config(world),
+            "sweeps_per_step": float(np.mean(sweeps)), "bp_sweep_msg_updates_per_step": bp_updates / steps,
+            "clocks": clocks, "gpu_launches": int(launches), "wall_ms_per_step": (tw1 - tw0) * 1e3 / steps}
+    if roof:
+        line["roofline"] = roof["roofline"]
+        line["bp_msg_updates_per_s"] = roof["bp_msg_updates_per_s"]
+        line["kernel_ms_per_step"] = roof["kernel_ms_per_step"]
+    if e2e:
+        line["e2e"] = e2e
+    if world == 1 and not args.no_cpu:
+        def inject(cfg_s, ramp_layers):
+            from bqa_b200.engine import Engine
+            e = Engine(config_to_context(cfg_s), precision="double", device=dev)
+            for ins in ramp_layers:
+                e.run_layer(ins["xtime"], ins["ztime"])
+            return e.state_to_host()
+        r = cpu_steps_per_s(CPU_SAMPLE_QUBITS, args.cpu_steps, 0, inject=inject)
+        line["cpu_baseline"] = {kk: r[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def measure_roofline(eng, lib, layers, torch, dev) -> dict:
+    """Re-runs steps with CUDA events around every launch of the instrumented entry points (same stream the
+    kernels are launched on).  roofline.achieved = algorithmic bytes of a BP sweep launch / its mean duration."""
+    peaks = {}
+    ppath = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(ppath):
+        with open(ppath) as f:
+            peaks = json.load(f)
+    peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks \
+        else (6650.0, "fallback (B200_PROFILING.md)")
+    names = ["bp_sweep", "ext_msgs", "canonicalize", "apply_update"]
+    events = {n: [] for n in names}
+    orig = {n: getattr(lib, n) for n in names}
+
+    def wrap(name):
+        fn = orig[name]
+
+        def call(*a):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn(*a)
+            e1.record()
+            events[name].append((e0, e1, a))
+        return call
+    for n in names:
+        setattr(lib, n, wrap(n))
+    try:
+        for ins in layers:
+            eng.run_layer(ins["xtime"], ins["ztime"])
+        torch.cuda.synchronize(dev)
+    finally:
+        for n in names:
+            setattr(lib, n, orig[n])
+    nsteps = max(len(layers), 1)
+    out = {"kernel_ms_per_step": {}}
+    for n in names:
+        out["kernel_ms_per_step"][n] = sum(e0.elapsed_time(e1) for e0, e1, _ in events[n]) / nsteps
+    # BP sweep launches of the 3-regular class: args = (prec, degree, D, B, ...)
+    bp = [(e0.elapsed_time(e1), a) for e0, e1, a in events["bp_sweep"]]
+    # converged sweeps exit early (device-side no-op): keep launches that did the work = all but the trailing
+    # no-op launches of each BP run; identify them by duration (a no-op takes a few microseconds)
+    durs = np.array([d for d, _ in bp])
+    work = durs > 0.5 * np.median(durs)
+    a0 = bp[0][1]
+    degree, D, B = int(a0[1]), int(a0[2]), int(a0[3])
+    s = 8
+    bytes_per_node = s * (2 * D ** degree + 3 * degree * D * D)
+    alg_bytes = bytes_per_node * B
+    mean_ms = float(durs[work].mean())
+    achieved = alg_bytes / (mean_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "bp_sweep_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                       "traffic": traffic, "kernel": "bp_sweep (degree 3, D=4, c64)", "launch_ms": mean_ms,
+                       "algorithmic_bytes_per_launch": alg_bytes, "launches_timed": int(work.sum()),
+                       "noop_launches_skipped": int((~work).sum()), "peak_source": peak_src}
+    out["bp_msg_updates_per_s"] = degree * B / (mean_ms * 1e-3)
+    return out
+
+
+def measure_e2e(eng, snapshot, layers, torch, dev, bloch_resident) -> dict:
+    """Same K steps driven from HOST buffers through the public engine API: load_state (pinned host -> HBM),
+    K x run_layer (each reads its bond-dimension decision and BP residuals back), bloch_vectors (HBM -> host)."""
+    h2d = sum(int(t.numel() * t.element_size()) for t in snapshot["_pinned"])
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    eng.load_state(snapshot)
+    for ins in layers:
+        eng.run_layer(ins["xtime"], ins["ztime"])
+    b = eng.bloch_vectors()
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    K = len(layers)
+    assert np.abs(b - bloch_resident).max() < 1e-6, "end-to-end run disagrees with the HBM-resident run"
+    d2h = b.shape[0] * 4 * 4 + K * (eng.ctrl_bytes_per_bp_read * 2 + eng.colmax_bytes)
+    return {"value": K / dt, "unit": "steps/s", "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
+            "what": "Engine.load_state(pinned host snapshot) + K x Engine.run_layer + Engine.bloch_vectors(), "
+                    "wall clock incl. all copies"}
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-steps", type=int, default=3, help="steps of the cpu_baseline leg (N=1 only)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -10,7 +10,9 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libbqa_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "--use_fast_math=false"]
+              "-Xcompiler", "-fPIC"]
+# translation units named *_nofma.cu are compiled without FMA contraction (see bqa_generic_f64_nofma.cu)
+NOFMA_FLAGS = ["-fmad=false"]
 
 
 def _nvcc() -> str:
@@ -41,7 +43,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for src in sources():
         obj = os.path.join(build_dir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+        flags = NVCC_FLAGS + (NOFMA_FLAGS if src.endswith("_nofma.cu") else [])
         cmd = [_nvcc(), *flags, "-c", src, "-o", obj] + (["-Xptxas", "-v"] if verbose else [])
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for cmd, p in procs:

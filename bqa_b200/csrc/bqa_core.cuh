@@ -252,6 +252,15 @@ BQA_HDN void jacobi_svd(G g, int n, cx<R>* A, cx<R>* V, R* sigma, int* order) {
   for (int i = g.rank(); i < n * n; i += g.size()) V[i] = mk<R>((i / n == i % n) ? R(1) : R(0), R(0));
   g.sync();
   const R tol = num_traits<R>::eps() * R(2) * msqrt((R)n);
+  // columns whose norm has fallen below eps * |A|_F are numerically zero (the absolute accuracy LAPACK's
+  // gesdd works to, and far below every pinv_eps cut): they are left alone.  Rotating them is not only
+  // wasted work -- once <a_p, a_q> reaches the denormal range the phase g / |g| stops being unimodular and
+  // would rescale the healthy column of the pair.
+  R fro2 = 0;
+  for (int r = g.rank(); r < n; r += g.size())
+    for (int j = 0; j < n; ++j) fro2 += norm2(A[r * n + j]);
+  fro2 = g.sum(fro2);
+  const R nul = num_traits<R>::eps() * num_traits<R>::eps() * fro2;
   for (int sweep = 0; sweep < 40; ++sweep) {
     bool rotated = false;
     for (int p = 0; p < n - 1; ++p) {
@@ -266,7 +275,7 @@ BQA_HDN void jacobi_svd(G g, int n, cx<R>* A, cx<R>* V, R* sigma, int* order) {
         }
         al = g.sum(al); be = g.sum(be); gr = g.sum(gr); gi = g.sum(gi);
         const R g2 = gr * gr + gi * gi;
-        if (g2 == R(0) || g2 <= tol * tol * al * be) continue;
+        if (al <= nul || be <= nul || g2 <= tol * tol * al * be) continue;
         rotated = true;
         const R ag = msqrt(g2);
         const R zeta = (be - al) / (R(2) * ag);

@@ -1,8 +1,9 @@
-// bqa_generic.cu -- shape-generic kernels (any degree <= 8, any bond dimension <= 16, c64 / c128).
+// bqa_generic.cuh -- shape-generic kernels (any degree <= 8, any bond dimension <= 16, c64 / c128).
 // One warp per node (or per undirected edge); scratch for the contracted tensors lives in a
 // per-warp slab of a global workspace (L1/L2 resident), the small Jacobi matrices in shared memory.
 // The headline shapes are served by the specialised kernels in bqa_fast_*.cu; these kernels are the
 // functional baseline they are validated against and the path for every other (degree, D).
+#pragma once
 #include <cuda_runtime.h>
 
 #include "bqa_core.cuh"
@@ -248,21 +249,12 @@ __global__ void __launch_bounds__(128) k_threshold_project(int half, long long B
 }
 
 // ---- launch helpers --------------------------------------------------------------------------------
-static int node_grid(long long B, int warps_per_block) {
+static inline int node_grid(long long B, int warps_per_block) {
   long long blocks = (B + warps_per_block - 1) / warps_per_block;
   const long long cap = (long long)BQA_GENERIC_MAX_WARPS / warps_per_block;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
-}
-
-size_t generic_ws_elems_per_warp(int d, int D, int Dn) {
-  const int Dm = D > Dn ? D : Dn;
-  size_t W = 2;
-  for (int i = 0; i < d; ++i) W *= Dm;
-  const size_t msgs_part = 2 * W + (size_t)d * 2 * D * D;          // P, E, gram
-  const size_t upd_part = 2 * W + (size_t)2 * D * Dm;              // bufA, bufB, wbuf
-  return (msgs_part > upd_part ? msgs_part : upd_part) + 8;
 }
 
 template <typename R>
@@ -389,7 +381,5 @@ int launch_threshold(int d, int D, long long B, void* T, const int32_t* node_ids
   template int launch_project<R>(int, int, void*, long long, int, cudaStream_t);                                   \
   template int launch_threshold<R>(int, int, long long, void*, const int32_t*, const void*, int32_t*, double,      \
                                    int32_t*, cudaStream_t);
-BQA_INSTANTIATE(float)
-BQA_INSTANTIATE(double)
 
 }  // namespace bqa

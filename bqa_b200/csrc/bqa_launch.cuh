@@ -13,7 +13,15 @@ namespace bqa {
 int set_error(const char* fmt, ...);
 int after_launch(const char* what);      // counts the launch, maps cudaGetLastError to a return code
 
-size_t generic_ws_elems_per_warp(int d, int D, int Dn);
+// complex elements of per-warp scratch the generic node kernels need (P, E, gram | bufA, bufB, wbuf)
+inline size_t generic_ws_elems_per_warp(int d, int D, int Dn) {
+  const int Dm = D > Dn ? D : Dn;
+  size_t W = 2;
+  for (int i = 0; i < d; ++i) W *= Dm;
+  const size_t msgs_part = 2 * W + (size_t)d * 2 * D * D;
+  const size_t upd_part = 2 * W + (size_t)2 * D * Dm;
+  return (msgs_part > upd_part ? msgs_part : upd_part) + 8;
+}
 
 template <typename R>
 int launch_node_msgs(bool ext, int d, int D, long long B, const void* T, const void* msgs_cur, void* msgs_out,

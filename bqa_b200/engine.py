@@ -170,6 +170,16 @@ class Engine:
             self._canon = torch.zeros(need, dtype=self.cdtype, device=self.dev)
 
     @property
+    def ctrl_bytes_per_bp_read(self) -> int:
+        """bytes of one device -> host read of the BP control block (one per chunk of sweeps)"""
+        return int(self._ctrl.numel())
+
+    @property
+    def colmax_bytes(self) -> int:
+        """bytes of the per-step device -> host read behind the bond-dimension decision"""
+        return int(self._colmax.numel() * self._colmax.element_size())
+
+    @property
     def msgs_buffer(self) -> torch.Tensor:
         return self._msgs[self._msgs_cur]
 
@@ -204,9 +214,23 @@ class Engine:
         s = self._lmbd_stride
         return self._to_host(self._lmbds[: self.L * s]).reshape(self.L, s)[:, : self.D].copy()
 
-    def state_to_host(self) -> dict:
-        """Checkpoint of the run-time state (the reference has none)."""
-        return {"D": self.D, "tensors": self.tensors_numpy(), "msgs": self.msgs_numpy(), "lmbds": self.lmbds_numpy()}
+    def state_to_host(self, pinned: bool = False) -> dict:
+        """Checkpoint of the run-time state (the reference has none).  With ``pinned`` the
+        arrays are views of page-locked host buffers (listed under "_pinned"), which ``load_state`` uploads
+        with asynchronous copies."""
+        snap = {"D": self.D, "tensors": self.tensors_numpy(), "msgs": self.msgs_numpy(), "lmbds": self.lmbds_numpy()}
+        if pinned and self.cuda:
+            keep = []
+
+            def pin(a):
+                t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+                keep.append(t)
+                return t.numpy()
+            snap["tensors"] = {d: pin(t) for d, t in snap["tensors"].items()}
+            snap["msgs"] = pin(snap["msgs"])
+            snap["lmbds"] = pin(snap["lmbds"])
+            snap["_pinned"] = keep
+        return snap
 
     def load_state(self, snap: dict) -> None:
         """Uploads a checkpoint / an oracle state: tensors {degree: (B, 2, D..)}, msgs (2L, D, D), lmbds (L, D)."""
@@ -218,15 +242,15 @@ class Engine:
             t = np.ascontiguousarray(np.asarray(snap["tensors"][c.degree]).astype(np_c)).reshape(-1)
             assert t.shape[0] == c.B * 2 * D ** c.degree, "tensor batch has the wrong shape"
             c.cur = 0
-            c.T[0][: t.shape[0]].copy_(torch.from_numpy(t).to(self.dev))
+            c.T[0][: t.shape[0]].copy_(torch.from_numpy(t), non_blocking=True)
         m = np.ascontiguousarray(np.asarray(snap["msgs"]).astype(np_c)).reshape(-1)
         assert m.shape[0] == self.E2 * D * D
         self._msgs_cur = 0
-        self._msgs[0][: m.shape[0]].copy_(torch.from_numpy(m).to(self.dev))
+        self._msgs[0][: m.shape[0]].copy_(torch.from_numpy(m), non_blocking=True)
         lm = np.zeros((self.L, 2 * D), self.np_rdtype)
         lm[:, :D] = np.real(np.asarray(snap["lmbds"]))
         self._lmbd_stride = 2 * D
-        self._lmbds[: lm.size].copy_(torch.from_numpy(lm.reshape(-1)).to(self.dev))
+        self._lmbds[: lm.size].copy_(torch.from_numpy(lm.reshape(-1)))
         self.D = D
 
     # ------------------------------------------------------------------------------------------

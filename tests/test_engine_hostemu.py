@@ -153,3 +153,56 @@ def test_product_loader_refuses_host_emulation(emu, tmp_path, monkeypatch):
     monkeypatch.setattr(_lib, "_cached", None)
     with pytest.raises(RuntimeError, match="not the CUDA build"):
         _lib.load_library()
+
+
+def test_rank_deficient_ker_keeps_relative_accuracy(emu):
+    """Extended messages whose masked ranks differ (4 vs 5 of 8) give a rank-deficient ker with more non-zero
+    columns than its rank; the kept lambdas must still come out to high relative accuracy.  (The Jacobi SVD
+    leaves numerically-zero columns alone; test_random_regular_400_lockstep_with_oracle is the regression test
+    for the case where rotating such a column into the denormal range rescaled the smallest kept lambda.)"""
+    import torch
+    rng = np.random.default_rng(11)
+    n, L = 8, 40
+    spec_f = np.array([0.97, 2.4e-2, 5e-4, 1.3e-5, 7.9e-7, 3.5e-8, 9.5e-9, 3.2e-10])
+    spec_b = np.array([0.97, 2.3e-2, 5e-4, 2.2e-5, 8.3e-6, 2.9e-7, 2.5e-8, 6.4e-10])
+
+    def psd(spec):
+        q, _ = np.linalg.qr(rng.normal(size=(L, n, n)) + 1j * rng.normal(size=(L, n, n)))
+        # graded eigenvectors: close to the identity, like the extended messages of a weakly entangled bond
+        q = np.linalg.qr(np.eye(n) + 0.05 * q)[0]
+        m = (q * (spec / spec.sum())) @ np.swapaxes(q.conj(), 1, 2)
+        return 0.5 * (m + np.swapaxes(m.conj(), 1, 2))
+    ext = np.concatenate([psd(spec_f), psd(spec_b)], 0)
+    lm_ref, _ = O.canonicalizers(ext, 1e-6, np.complex128)
+    e = torch.from_numpy(np.ascontiguousarray(ext).reshape(-1))
+    canon = torch.zeros_like(e)
+    lm = torch.zeros(L * n, dtype=torch.float64)
+    colmax = torch.zeros(n, dtype=torch.float64)
+    emu.canonicalize(_lib.C128, 4, L, e.data_ptr(), canon.data_ptr(), lm.data_ptr(), colmax.data_ptr(), 1e-6, 0)
+    lm = lm.numpy().reshape(L, n)
+    assert (lm_ref.real[:, 3] > 0).all() and (lm_ref.real[:, 4] == 0).all()
+    rel = np.abs(lm[:, :4] - lm_ref.real[:, :4]) / lm_ref.real[:, :4]
+    assert rel.max() < 1e-9
+
+
+def test_random_regular_400_lockstep_with_oracle(emu):
+    """30 steps of the dt = 0.2 schedule on a seeded random 3-regular QUBO, engine and oracle in lock step:
+    identical bond dimensions and sweep counts, Bloch vectors and lambda spectra to 1e-10 after every step."""
+    from bqa_b200.benchmarking import generate_qubo_on_random_regular_graph
+    nodes, edges = generate_qubo_on_random_regular_graph(400, 3, seed=42)
+    cfg = {"nodes": nodes, "edges": edges, "max_bond_dim": 4,
+           "schedule": {"total_time": 6.0, "starting_mixing": 1.0,
+                        "actions": [{"weight": 1.0, "steps_number": 30, "final_mixing": 0.0}]}}
+    ctx = config_to_context(cfg)
+    eng = Engine(ctx, precision="double", _testing_lib=emu)
+    octx = O.compile_config(cfg)
+    ost = O.init_state(octx)
+    for ins in [i for i in ctx.instructions if isinstance(i, dict)]:
+        eng.run_layer(ins["xtime"], ins["ztime"])
+        O.run_layer(octx, ost, ins["xtime"], ins["ztime"])
+        assert eng.D == ost.bond_dim
+        assert eng.stats["bp_sweeps"][-1] == ost.stats["bp_sweeps"][-1]
+        lm = np.sort(eng.lmbds_numpy(), axis=1)[:, ::-1]
+        olm = np.sort(np.real(ost.lmbds), axis=1)[:, ::-1]
+        assert np.abs(lm - olm).max() < 1e-10
+        assert np.abs(eng.bloch_vectors() - O.bloch_vectors(O.density_matrices(octx, ost))).max() < 1e-10

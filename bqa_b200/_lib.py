@@ -25,7 +25,7 @@ SIGNATURES = {
     "bqa_b200_threshold_project": [_i, _i, _i, _ll, _vp, _vp, _vp, _vp, _d, _vp, _vp],
 }
 EXPORTS = list(SIGNATURES) + ["bqa_b200_last_error", "bqa_b200_version", "bqa_b200_launch_count",
-                              "bqa_b200_workspace_bytes"]
+                              "bqa_b200_workspace_bytes", "bqa_b200_set_kernel_mode"]
 
 
 class Library:
@@ -58,6 +58,11 @@ class Library:
 
     def launch_count(self) -> int:
         return int(self._dll.bqa_b200_launch_count())
+
+    def set_kernel_mode(self, mode: int) -> None:
+        """0: specialised kernels where they exist (default); 1: generic kernels only."""
+        if self._dll.bqa_b200_set_kernel_mode(int(mode)) != 0:
+            raise RuntimeError(self._dll.bqa_b200_last_error().decode())
 
     def workspace_bytes(self, prec: int, degree: int, D: int, D_new: int) -> int:
         return int(self._dll.bqa_b200_workspace_bytes(prec, degree, D, D_new))

@@ -14,6 +14,7 @@ namespace bqa {
 
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
+static std::atomic<int> g_kernel_mode{0};       // 0: specialised kernels where they exist, 1: generic kernels only
 
 int set_error(const char* fmt, ...) {
   va_list ap;
@@ -46,6 +47,11 @@ extern "C" {
 const char* bqa_b200_last_error(void) { return g_err; }
 int bqa_b200_version(void) { return 1; }
 long long bqa_b200_launch_count(void) { return g_launches.load(); }
+int bqa_b200_set_kernel_mode(int mode) {
+  if (mode != 0 && mode != 1) return set_error("kernel mode must be 0 (auto) or 1 (generic only), got %d", mode);
+  g_kernel_mode.store(mode);
+  return 0;
+}
 
 size_t bqa_b200_workspace_bytes(int prec, int degree, int D, int D_new) {
   const size_t elem = prec == BQA_C64 ? sizeof(cx<float>) : sizeof(cx<double>);
@@ -58,6 +64,9 @@ int bqa_b200_bp_sweep(int prec, int degree, int D, long long B, const void* T, c
                       size_t workspace_bytes, void* stream) {
   if (int rc = check_shape(prec, degree, D)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  if (g_kernel_mode.load() == 0 && fast_d3D4_available(prec, degree, D))
+    return launch_fast_msgs_d3D4(false, B, T, msgs_cur, msgs_nxt, in_pos, out_pos, nullptr, 0.0, damping, write_undamped,
+                                 bp_eps, it, resid, status, st);
   if (prec == BQA_C64)
     return launch_node_msgs<float>(false, degree, D, B, T, msgs_cur, msgs_nxt, in_pos, out_pos, nullptr, 0.0, damping,
                                    write_undamped, bp_eps, it, resid, status, workspace, workspace_bytes, st);
@@ -70,6 +79,9 @@ int bqa_b200_ext_msgs(int prec, int degree, int D, long long B, const void* T, c
                       void* workspace, size_t workspace_bytes, void* stream) {
   if (int rc = check_shape(prec, degree, D)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  if (g_kernel_mode.load() == 0 && fast_d3D4_available(prec, degree, D))
+    return launch_fast_msgs_d3D4(true, B, T, msgs_cur, ext, in_pos, out_pos, edge_ampls, ztime, 0.0, 0, 0.0, 0, nullptr,
+                                 nullptr, st);
   if (prec == BQA_C64)
     return launch_node_msgs<float>(true, degree, D, B, T, msgs_cur, ext, in_pos, out_pos, edge_ampls, ztime, 0.0, 0,
                                    0.0, 0, nullptr, nullptr, workspace, workspace_bytes, st);

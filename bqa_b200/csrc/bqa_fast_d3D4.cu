@@ -1,0 +1,396 @@
+// bqa_fast_d3D4.cu -- specialised sm_100a kernels for the headline shape: degree-3 nodes, bond dimension 4,
+// complex64 (random 3-regular QUBO at max_bond_dim 4: BASELINE.json configs 4 and 5).
+//
+//   k_msgs_d3D4<false> : one BP sweep            (Tensor.pass_msgs, src/bqa/backends.py:381-408, + get_dist :492-495
+//                                                 + damping :539-540 + the gathers/scatters of state.py:109-112)
+//   k_msgs_d3D4<true>  : ZZ-extended messages    (_get_extended_msgs, state.py:127-139; backends.py:519-526)
+//
+// Work decomposition.  Eight lanes own a node: lane (p, a) holds the slice T[p, a, :, :] (16 complex) in
+// registers, a warp works on 4 consecutive nodes, a CTA of 8 warps is persistent (one per SM) and every warp
+// runs its own two-stage cp.async pipeline: the contiguous 4 KB of node tensors and the 24 gathered 128-byte
+// messages (3 incoming + 3 previous outgoing per node) of the NEXT group stream into shared memory while the
+// current group is contracted out of registers.
+//
+// Arithmetic.  With Hermitian messages (BP messages are Hermitian positive semi-definite by construction)
+//   U_j = T x_j m_j                                   (3 mode products instead of the reference's 6)
+//   out_0[x,y] = sum conj(U_1[x,b,c]) U_2[y,b,c],  out_1[x,y] = sum conj(U_2[a,x,c]) U_0[a,y,c],
+//   out_2[x,y] = sum conj(U_1[a,b,x]) U_0[a,b,y]
+// is the same sum as conj(T) . prod_{j != k} m_j . T, at 384 complex multiply-adds per lane.  Legs 1 and 2
+// are thread-local; leg 0 is spread over the 4 `a` lanes, so U_0 and out_0 read the other lanes' slices from
+// shared memory (broadcast reads of padded 144-byte slices: conflict-free), and the per-lane partial sums of
+// out_1 / out_2 are reduced through shared memory into the 16-byte piece of the message each lane stores.
+#include <cuda_runtime.h>
+
+#include "bqa_core.cuh"
+#include "bqa_launch.cuh"
+
+namespace bqa {
+namespace fast {
+
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+constexpr int kSlice = 144;                       // 128-byte slice + 16 bytes of padding (bank spreading)
+constexpr int kTBytes = 32 * kSlice;              // 4 nodes x 8 slices
+constexpr int kMBytes = 12 * 128;                 // 3 messages x 4 nodes
+constexpr int kStage = kTBytes + 2 * kMBytes;     // T | incoming messages | previous outgoing messages
+constexpr int kWarpBytes = 2 * kStage + kTBytes;  // two stages + reduction scratch
+constexpr int kSmem = kWarps * kWarpBytes;
+
+struct Args {
+  long long B;
+  const float2* T;
+  const float2* msgs_cur;
+  float2* msgs_out;
+  const int32_t* in_pos;
+  const int32_t* out_pos;
+  const float* edge_ampls;
+  float ztime, damping, bp_eps;
+  int write_undamped, it;
+  float* resid;
+  int32_t* status;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// acc += a * b
+__device__ __forceinline__ void fma_c(float2& acc, float2 a, float2 b) {
+  acc.x = fmaf(a.x, b.x, acc.x); acc.x = fmaf(-a.y, b.y, acc.x);
+  acc.y = fmaf(a.x, b.y, acc.y); acc.y = fmaf(a.y, b.x, acc.y);
+}
+// acc += conj(a) * b
+__device__ __forceinline__ void fma_cc(float2& acc, float2 a, float2 b) {
+  acc.x = fmaf(a.x, b.x, acc.x); acc.x = fmaf(a.y, b.y, acc.x);
+  acc.y = fmaf(a.x, b.y, acc.y); acc.y = fmaf(-a.y, b.x, acc.y);
+}
+
+// 16 complex (128 bytes) shared -> registers
+__device__ __forceinline__ void lds_tile(float2 (&r)[16], const unsigned char* p) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 v = *reinterpret_cast<const float4*>(p + 16 * i);
+    r[2 * i] = make_float2(v.x, v.y);
+    r[2 * i + 1] = make_float2(v.z, v.w);
+  }
+}
+__device__ __forceinline__ void sts_tile(unsigned char* p, const float2 (&r)[16]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    *reinterpret_cast<float4*>(p + 16 * i) = make_float4(r[2 * i].x, r[2 * i].y, r[2 * i + 1].x, r[2 * i + 1].y);
+}
+
+// issue the copies of one 4-node group into a stage: T (coalesced 4 KB), 12 incoming and 12 previous
+// outgoing messages (each by the 8 lanes of a quarter warp: one full 128-byte line)
+template <bool EXT>
+__device__ __forceinline__ void issue_group(const Args& a, unsigned char* stage, long long node0, int lane,
+                                            int idx_reg) {
+  const long long last = a.B - 1;
+  const unsigned char* Tg = reinterpret_cast<const unsigned char*>(a.T);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = i * 32 + lane;                 // 16-byte chunk of the 4 KB block
+    const int s = c >> 6;                        // node slot
+    long long node = node0 + s;
+    node = node > last ? last : node;
+    cp_async16(stage + (c >> 3) * kSlice + (c & 7) * 16, Tg + node * 1024 + (c & 63) * 16);
+  }
+  const unsigned char* Mg = reinterpret_cast<const unsigned char*>(a.msgs_cur);
+  const int s = lane >> 3, ch = lane & 7;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const int pin = __shfl_sync(0xffffffffu, idx_reg, j * 4 + s);
+    cp_async16(stage + kTBytes + (j * 4 + s) * 128 + ch * 16, Mg + (size_t)pin * 128 + ch * 16);
+    if (!EXT) {
+      const int pout = __shfl_sync(0xffffffffu, idx_reg, 12 + j * 4 + s);
+      cp_async16(stage + kTBytes + kMBytes + (j * 4 + s) * 128 + ch * 16, Mg + (size_t)pout * 128 + ch * 16);
+    }
+  }
+  cp_async_commit();
+}
+
+// lanes 0..11 hold in_pos[j][node0 + s], lanes 12..23 hold out_pos[j][node0 + s]  (index j * 4 + s)
+__device__ __forceinline__ int load_idx(const Args& a, long long node0, int lane) {
+  int v = 0;
+  if (lane < 24) {
+    const int l = lane < 12 ? lane : lane - 12;
+    long long node = node0 + (l & 3);
+    node = node > a.B - 1 ? a.B - 1 : node;
+    const int32_t* src = lane < 12 ? a.in_pos : a.out_pos;
+    v = __ldg(src + (size_t)(l >> 2) * a.B + node);
+  }
+  return v;
+}
+
+template <bool EXT>
+__global__ void __launch_bounds__(kThreads, 1) k_msgs_d3D4(Args a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  if (!EXT && a.it > 0) {                                   // device-side early exit after convergence
+    if (*((volatile int32_t*)a.status) != 0) return;
+    const float num = a.resid[2 * (a.it - 1)], den = a.resid[2 * (a.it - 1) + 1];
+    if (sqrtf(num / den) < a.bp_eps) {
+      if (threadIdx.x == 0) { a.status[1] = a.it; __threadfence(); a.status[0] = 1; }
+      return;
+    }
+  }
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int s = lane >> 3, t = lane & 7, p = t >> 2, la = t & 3;     // node slot, lane in node, physical, leg-0 index
+  unsigned char* wbase = smem + wib * kWarpBytes;
+  unsigned char* scratch = wbase + 2 * kStage;
+  const long long groups = (a.B + 3) >> 2;
+  const long long nwarps = (long long)gridDim.x * kWarps;
+  long long g = (long long)blockIdx.x * kWarps + wib;
+  float mnum = 0.f, mden = 0.f;
+
+  int idx_cur = 0, idx_nxt = 0;
+  if (g < groups) {
+    idx_cur = load_idx(a, g * 4, lane);
+    issue_group<EXT>(a, wbase, g * 4, lane, idx_cur);
+    if (g + nwarps < groups) idx_nxt = load_idx(a, (g + nwarps) * 4, lane);
+  }
+  int cur = 0;
+  for (; g < groups; g += nwarps, cur ^= 1) {
+    unsigned char* st = wbase + cur * kStage;
+    const bool has_next = g + nwarps < groups;
+    int idx_nn = 0;
+    if (has_next) {
+      issue_group<EXT>(a, wbase + (cur ^ 1) * kStage, (g + nwarps) * 4, lane, idx_nxt);
+      if (g + 2 * nwarps < groups) idx_nn = load_idx(a, (g + 2 * nwarps) * 4, lane);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncwarp();
+
+    const unsigned char* Ts = st + (s * 8 + p * 4) * kSlice;          // the four a-slices of (node, p)
+    const unsigned char* Min = st + kTBytes;
+    float2 U0[16], U1[16], U2[16];
+    {
+      float2 tt[16], m[16];
+      lds_tile(tt, Ts + la * kSlice);
+      // U2[b][c'] = sum_c m2[c'][c] T[b][c]
+      lds_tile(m, Min + (2 * 4 + s) * 128);
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+#pragma unroll
+        for (int c2 = 0; c2 < 4; ++c2) {
+          float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) fma_c(acc, m[c2 * 4 + c], tt[b * 4 + c]);
+          U2[b * 4 + c2] = acc;
+        }
+      // U1[b'][c] = sum_b m1[b'][b] T[b][c]
+      lds_tile(m, Min + (1 * 4 + s) * 128);
+#pragma unroll
+      for (int b2 = 0; b2 < 4; ++b2)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int b = 0; b < 4; ++b) fma_c(acc, m[b2 * 4 + b], tt[b * 4 + c]);
+          U1[b2 * 4 + c] = acc;
+        }
+    }
+    {
+      // U0[a][b][c] = sum_a' m0[a][a'] T[a'][b][c]: row `la` of m0, the four slices broadcast from shared memory
+      const float4 r0 = *reinterpret_cast<const float4*>(Min + (0 * 4 + s) * 128 + la * 32);
+      const float4 r1 = *reinterpret_cast<const float4*>(Min + (0 * 4 + s) * 128 + la * 32 + 16);
+      const float2 m0row[4] = {make_float2(r0.x, r0.y), make_float2(r0.z, r0.w), make_float2(r1.x, r1.y),
+                               make_float2(r1.z, r1.w)};
+#pragma unroll
+      for (int i = 0; i < 16; ++i) U0[i] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int a2 = 0; a2 < 4; ++a2) {
+        float2 tt[16];
+        lds_tile(tt, Ts + a2 * kSlice);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) fma_c(U0[i], m0row[a2], tt[i]);
+      }
+    }
+    __syncwarp();                                           // every lane is done with the T slices
+    unsigned char* Xs = st + (s * 8 + p * 4) * kSlice;      // exchange area: U1 slices in the T layout
+    sts_tile(Xs + la * kSlice, U1);
+
+    float2 e[3][4];                                         // per message k: [g0 piece (2), g1 piece (2)]; BP sums them
+    unsigned char* red = scratch + s * (8 * kSlice);
+    // ---- out_1[x][y] = sum_{a,c} conj(U2[a][x][c]) U0[a][y][c]  (partial over this lane's (p, a)) ----
+    // ---- out_2[x][y] = sum_{a,b} conj(U1[a][b][x]) U0[a][b][y]
+#pragma unroll
+    for (int k = 1; k <= 2; ++k) {
+      float2 acc[16];
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+          float2 v = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (k == 1) fma_cc(v, U2[x * 4 + q], U0[y * 4 + q]);
+            else fma_cc(v, U1[q * 4 + x], U0[q * 4 + y]);
+          }
+          acc[x * 4 + y] = v;
+        }
+      __syncwarp();                                         // previous readers of the scratch are done
+      sts_tile(red + t * kSlice, acc);
+      __syncwarp();
+      float2 g0a = make_float2(0.f, 0.f), g0b = g0a, g1a = g0a, g1b = g0a;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float4 v0 = *reinterpret_cast<const float4*>(red + r * kSlice + t * 16);
+        const float4 v1 = *reinterpret_cast<const float4*>(red + (4 + r) * kSlice + t * 16);
+        g0a.x += v0.x; g0a.y += v0.y; g0b.x += v0.z; g0b.y += v0.w;
+        g1a.x += v1.x; g1a.y += v1.y; g1b.x += v1.z; g1b.y += v1.w;
+      }
+      e[k][0] = g0a; e[k][1] = g0b; e[k][2] = g1a; e[k][3] = g1b;
+    }
+    // ---- out_0[x][y] = sum_{b,c} conj(U1[x][b][c]) U2[y][b][c]: lane (p, y = la) against the exchanged U1 slices
+    {
+      float2 col[4];
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        float2 ux[16];
+        lds_tile(ux, Xs + x * kSlice);
+        float2 v = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) fma_cc(v, ux[i], U2[i]);
+        col[x] = v;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int x = 0; x < 4; ++x) *reinterpret_cast<float2*>(red + p * kSlice + (x * 4 + la) * 8) = col[x];
+      __syncwarp();
+      const float4 v0 = *reinterpret_cast<const float4*>(red + t * 16);
+      const float4 v1 = *reinterpret_cast<const float4*>(red + kSlice + t * 16);
+      e[0][0] = make_float2(v0.x, v0.y); e[0][1] = make_float2(v0.z, v0.w);
+      e[0][2] = make_float2(v1.x, v1.y); e[0][3] = make_float2(v1.z, v1.w);
+    }
+
+    // ---- epilogue: lane t owns elements (x, y0) and (x, y0 + 1) of every message, x = t / 2, y0 = 2 (t % 2)
+    const long long node = g * 4 + s;
+    const bool live = node < a.B;
+    const int x = t >> 1, y0 = (t & 1) * 2;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float2 sa = make_float2(e[k][0].x + e[k][2].x, e[k][0].y + e[k][2].y);
+      const float2 sb = make_float2(e[k][1].x + e[k][3].x, e[k][1].y + e[k][3].y);
+      float2 tr = (x == y0) ? sa : ((x == y0 + 1) ? sb : make_float2(0.f, 0.f));
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        tr.x += __shfl_xor_sync(0xffffffffu, tr.x, o);
+        tr.y += __shfl_xor_sync(0xffffffffu, tr.y, o);
+      }
+      const int slot = __shfl_sync(0xffffffffu, idx_cur, 12 + k * 4 + s);
+      if (!EXT) {
+        const float d = 1.f / (tr.x * tr.x + tr.y * tr.y);
+        const float2 itr = make_float2(tr.x * d, -tr.y * d);
+        const float2 na = cmul(itr, sa), nb = cmul(itr, sb);
+        const float4 ov = *reinterpret_cast<const float4*>(st + kTBytes + kMBytes + (k * 4 + s) * 128 + t * 16);
+        if (live) {
+          float da = (na.x - ov.x) * (na.x - ov.x) + (na.y - ov.y) * (na.y - ov.y);
+          float db = (nb.x - ov.z) * (nb.x - ov.z) + (nb.y - ov.w) * (nb.y - ov.w);
+          mnum = fmaxf(mnum, fmaxf(da, db));
+          da = (na.x + ov.x) * (na.x + ov.x) + (na.y + ov.y) * (na.y + ov.y);
+          db = (nb.x + ov.z) * (nb.x + ov.z) + (nb.y + ov.w) * (nb.y + ov.w);
+          mden = fmaxf(mden, fmaxf(da, db));
+          float4 w;
+          if (a.write_undamped) {
+            w = make_float4(na.x, na.y, nb.x, nb.y);
+          } else {
+            const float al = a.damping, be = 1.f - a.damping;
+            w = make_float4(al * ov.x + be * na.x, al * ov.y + be * na.y, al * ov.z + be * nb.x, al * ov.w + be * nb.y);
+          }
+          *reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(a.msgs_out) + (size_t)slot * 128 + t * 16) = w;
+        }
+      } else {
+        // ext[(s1,x),(s2,y)] = conj(f_s1) f_s2 (g0 + (-1)^(s1+s2) g1)[x][y] / ((|f0|^2 + |f1|^2) trace)
+        long long nn = node > a.B - 1 ? a.B - 1 : node;
+        const float theta = __ldg(a.edge_ampls + (size_t)k * a.B + nn) * a.ztime;
+        cx<float> f0, f1;
+        zz_factors<float>(theta, f0, f1);
+        const float2 ff[2] = {make_float2(f0.re, f0.im), make_float2(f1.re, f1.im)};
+        const float w = (f0.re * f0.re + f0.im * f0.im + f1.re * f1.re + f1.im * f1.im);
+        const float d = 1.f / (w * (tr.x * tr.x + tr.y * tr.y));
+        const float2 itr = make_float2(tr.x * d, -tr.y * d);
+        const float2 da = make_float2(e[k][0].x - e[k][2].x, e[k][0].y - e[k][2].y);
+        const float2 db = make_float2(e[k][1].x - e[k][3].x, e[k][1].y - e[k][3].y);
+        if (live) {
+          unsigned char* dst = reinterpret_cast<unsigned char*>(a.msgs_out) + (size_t)slot * 512;
+#pragma unroll
+          for (int s1 = 0; s1 < 2; ++s1)
+#pragma unroll
+            for (int s2 = 0; s2 < 2; ++s2) {
+              const float2 cf = cmul(itr, cmul(make_float2(ff[s1].x, -ff[s1].y), ff[s2]));
+              const float2 va = cmul(cf, s1 == s2 ? sa : da), vb = cmul(cf, s1 == s2 ? sb : db);
+              *reinterpret_cast<float4*>(dst + ((s1 * 4 + x) * 8 + s2 * 4 + y0) * 8) = make_float4(va.x, va.y, vb.x, vb.y);
+            }
+        }
+      }
+    }
+    idx_cur = idx_nxt;
+    idx_nxt = idx_nn;
+    __syncwarp();                                           // stage `cur` may be overwritten by the next issue
+  }
+  if (!EXT) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mnum = fmaxf(mnum, __shfl_xor_sync(0xffffffffu, mnum, o));
+      mden = fmaxf(mden, __shfl_xor_sync(0xffffffffu, mden, o));
+    }
+    if (lane == 0) {
+      atomicMax(reinterpret_cast<unsigned int*>(a.resid + 2 * a.it), __float_as_uint(mnum));
+      atomicMax(reinterpret_cast<unsigned int*>(a.resid + 2 * a.it + 1), __float_as_uint(mden));
+    }
+  }
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace fast
+
+bool fast_d3D4_available(int prec, int degree, int D) { return prec == 0 && degree == 3 && D == 4; }
+
+int launch_fast_msgs_d3D4(bool ext, long long B, const void* T, const void* msgs_cur, void* msgs_out,
+                          const int32_t* in_pos, const int32_t* out_pos, const void* edge_ampls, double ztime,
+                          double damping, int write_undamped, double bp_eps, int it, void* resid, int32_t* status,
+                          cudaStream_t st) {
+  using namespace fast;
+  if (B == 0) return 0;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e1 = cudaFuncSetAttribute(k_msgs_d3D4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaError_t e2 = cudaFuncSetAttribute(k_msgs_d3D4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (e1 != cudaSuccess || e2 != cudaSuccess)
+      return set_error("cudaFuncSetAttribute(k_msgs_d3D4): %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    configured = true;
+  }
+  Args a{};
+  a.B = B; a.T = (const float2*)T; a.msgs_cur = (const float2*)msgs_cur; a.msgs_out = (float2*)msgs_out;
+  a.in_pos = in_pos; a.out_pos = out_pos; a.edge_ampls = (const float*)edge_ampls;
+  a.ztime = (float)ztime; a.damping = (float)damping; a.bp_eps = (float)bp_eps;
+  a.write_undamped = write_undamped; a.it = it; a.resid = (float*)resid; a.status = status;
+  const long long groups = (B + 3) / 4;
+  long long grid = (groups + kWarps - 1) / kWarps;
+  if (grid > sm_count()) grid = sm_count();
+  if (ext) k_msgs_d3D4<true><<<(int)grid, kThreads, kSmem, st>>>(a);
+  else k_msgs_d3D4<false><<<(int)grid, kThreads, kSmem, st>>>(a);
+  return after_launch(ext ? "ext_msgs(d3D4)" : "bp_sweep(d3D4)");
+}
+
+}  // namespace bqa

@@ -37,6 +37,10 @@ int bqa_b200_version(void);
 /* number of this library's kernel launches since load (bench.py reports it as gpu_launches) */
 long long bqa_b200_launch_count(void);
 
+/* 0 (default): specialised kernels where one exists for (precision, degree, D), generic kernels otherwise;
+ * 1: generic kernels only (used by the tests to check the specialised kernels against the generic ones) */
+int bqa_b200_set_kernel_mode(int mode);
+
 /* bytes of device scratch the node kernels need for a degree class (pass the max over classes) */
 size_t bqa_b200_workspace_bytes(int prec, int degree, int D, int D_new);
 

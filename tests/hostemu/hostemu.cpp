@@ -148,6 +148,7 @@ extern "C" {
 const char* bqa_b200_last_error(void) { return g_err; }
 int bqa_b200_version(void) { return -1; }   // negative: host emulation
 long long bqa_b200_launch_count(void) { return g_calls; }
+int bqa_b200_set_kernel_mode(int) { return 0; }
 size_t bqa_b200_workspace_bytes(int, int, int, int) { return 16; }
 
 int bqa_b200_bp_sweep(int prec, int degree, int D, long long B, const void* T, const void* msgs_cur, void* msgs_nxt,

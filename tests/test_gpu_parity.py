@@ -167,3 +167,61 @@ def test_full_size_properties_100k(lib):
     eng2 = Engine(eng.ctx, precision="single")
     eng2.load_state(snap)
     assert np.abs(eng2.bloch_vectors() - eng.bloch_vectors()).max() == 0.0
+
+
+@pytest.mark.parametrize("B", [1, 4, 1003, 40_001])
+def test_fast_d3D4_kernels_match_generic_and_oracle(lib, B):
+    """Specialised degree-3 / D=4 / complex64 kernels (bqa_fast_d3D4.cu) against the generic kernels and
+    against the oracle's pass_msgs (reference backends.py:406-408) on scattered message slots, a ragged
+    batch (B not a multiple of the 4 nodes a warp handles) and non-zero damping."""
+    import torch
+    from bqa_b200 import _lib
+    from oracle import bqa_oracle as O
+    d, D = 3, 4
+    rng = np.random.default_rng(B)
+    t, msgs, thetas = instances.random_node_batch(B, d, D, seed=7 + B)
+    slots = rng.permutation(d * B + 5)                      # a few unused slots
+    in_pos = slots[: d * B].reshape(d, B).astype(np.int32)
+    out_pos = rng.permutation(d * B + 5)[: d * B].reshape(d, B).astype(np.int32)
+    cur = np.zeros((d * B + 5, D, D), np.complex64)
+    cur[:] = instances.random_psd_msgs(rng, d * B + 5, D)
+    for j in range(d):
+        cur[in_pos[j]] = msgs[j]
+    msgs32 = [cur[in_pos[j]].astype(np.complex128) for j in range(d)]
+    t32 = t.astype(np.complex64)
+    dev = torch.device("cuda:0")
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    T, C, ip, op = up(t32.reshape(-1)), up(cur.reshape(-1)), up(in_pos), up(out_pos)
+    ea = up(np.stack(thetas).astype(np.float32))
+    ws = torch.zeros(lib.workspace_bytes(_lib.C64, d, D, D), dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    out = {}
+    for mode in (1, 0):
+        lib.set_kernel_mode(mode)
+        try:
+            nxt = C.clone()
+            resid = torch.zeros(2, dtype=torch.float32, device=dev)
+            status = torch.zeros(4, dtype=torch.int32, device=dev)
+            lib.bp_sweep(_lib.C64, d, D, B, T.data_ptr(), C.data_ptr(), nxt.data_ptr(), ip.data_ptr(), op.data_ptr(),
+                         0.25, 0, 1e-6, 0, resid.data_ptr(), status.data_ptr(), ws.data_ptr(), ws.numel(), st)
+            ext = torch.zeros((d * B + 5) * 4 * D * D, dtype=torch.complex64, device=dev)
+            lib.ext_msgs(_lib.C64, d, D, B, T.data_ptr(), C.data_ptr(), ext.data_ptr(), ip.data_ptr(), op.data_ptr(),
+                         ea.data_ptr(), 0.7, ws.data_ptr(), ws.numel(), st)
+            out[mode] = (nxt.cpu().numpy().reshape(-1, D, D), resid.cpu().numpy().astype(np.float64),
+                         ext.cpu().numpy().reshape(-1, 2 * D, 2 * D))
+        finally:
+            lib.set_kernel_mode(0)
+    gen, fast = out[1], out[0]
+    assert np.abs(fast[0] - gen[0]).max() < 2e-6
+    assert np.abs(fast[2] - gen[2]).max() < 2e-6
+    assert np.allclose(np.sqrt(fast[1][0] / fast[1][1]), np.sqrt(gen[1][0] / gen[1][1]), rtol=1e-4)
+    # untouched slots keep their content
+    untouched = np.setdiff1d(np.arange(d * B + 5), out_pos.reshape(-1))
+    assert np.array_equal(fast[0][untouched], cur[untouched])
+    # oracle (complex128) on the same complex64 inputs
+    want = O.pass_msgs(t32.astype(np.complex128), msgs32)
+    want_ext = O.pass_msgs(t32.astype(np.complex128), msgs32, [(0.7 * th.astype(np.float32).astype(np.float64)).astype(np.complex128) for th in thetas])   # complex like the reference's edge_ampls (principal roots)
+    for j in range(d):
+        damped = 0.25 * cur[out_pos[j]] + 0.75 * want[j]
+        assert np.abs(fast[0][out_pos[j]] - damped).max() < 2e-6
+        assert np.abs(fast[2][out_pos[j]] - want_ext[j]).max() < 2e-6

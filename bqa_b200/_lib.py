@@ -17,7 +17,7 @@ _vp, _i, _ll, _d, _sz = C.c_void_p, C.c_int, C.c_longlong, C.c_double, C.c_size_
 SIGNATURES = {
     "bqa_b200_bp_sweep": [_i, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp, _d, _i, _d, _i, _vp, _vp, _vp, _sz, _vp],
     "bqa_b200_ext_msgs": [_i, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _d, _vp, _sz, _vp],
-    "bqa_b200_canonicalize": [_i, _i, _ll, _vp, _vp, _vp, _vp, _d, _vp],
+    "bqa_b200_canonicalize": [_i, _i, _ll, _vp, _vp, _vp, _vp, _d, _i, _vp],
     "bqa_b200_apply_update": [_i, _i, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _vp, _sz, _vp],
     "bqa_b200_density": [_i, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp],
     "bqa_b200_argmax_unmeasured": [_i, _ll, _vp, _vp, _vp, _vp, _vp],
@@ -25,7 +25,7 @@ SIGNATURES = {
     "bqa_b200_threshold_project": [_i, _i, _i, _ll, _vp, _vp, _vp, _vp, _d, _vp, _vp],
 }
 EXPORTS = list(SIGNATURES) + ["bqa_b200_last_error", "bqa_b200_version", "bqa_b200_launch_count",
-                              "bqa_b200_workspace_bytes", "bqa_b200_set_kernel_mode"]
+                              "bqa_b200_workspace_bytes", "bqa_b200_set_kernel_mode", "bqa_b200_canon_stats"]
 
 
 class Library:
@@ -63,6 +63,11 @@ class Library:
         """0: specialised kernels where they exist (default); 1: generic kernels only."""
         if self._dll.bqa_b200_set_kernel_mode(int(mode)) != 0:
             raise RuntimeError(self._dll.bqa_b200_last_error().decode())
+
+    def canon_stats(self) -> tuple[int, int]:
+        out = (C.c_ulonglong * 2)()
+        self._dll.bqa_b200_canon_stats(out)
+        return int(out[0]), int(out[1])
 
     def workspace_bytes(self, prec: int, degree: int, D: int, D_new: int) -> int:
         return int(self._dll.bqa_b200_workspace_bytes(prec, degree, D, D_new))

@@ -47,6 +47,12 @@ extern "C" {
 const char* bqa_b200_last_error(void) { return g_err; }
 int bqa_b200_version(void) { return 1; }
 long long bqa_b200_launch_count(void) { return g_launches.load(); }
+/* profiling aid: out[0] = warp-level Jacobi problems solved by the n = 8 canonicalizer kernel since load,
+ * out[1] = Jacobi sweeps summed over them (synchronises the device) */
+int bqa_b200_canon_stats(unsigned long long* out2) {
+  canon8_stats(out2);
+  return 0;
+}
 int bqa_b200_set_kernel_mode(int mode) {
   if (mode != 0 && mode != 1) return set_error("kernel mode must be 0 (auto) or 1 (generic only), got %d", mode);
   g_kernel_mode.store(mode);
@@ -90,9 +96,12 @@ int bqa_b200_ext_msgs(int prec, int degree, int D, long long B, const void* T, c
 }
 
 int bqa_b200_canonicalize(int prec, int D, long long L, const void* ext, void* canon, void* lmbds, void* colmax,
-                          double pinv_eps, void* stream) {
+                          double pinv_eps, int n_cols, void* stream) {
   if (int rc = check_shape(prec, 0, D)) return rc;
+  if (n_cols < 1 || n_cols > 2 * D) return set_error("n_cols %d outside [1, %d]", n_cols, 2 * D);
   cudaStream_t st = (cudaStream_t)stream;
+  if (g_kernel_mode.load() == 0 && prec == BQA_C64 && D == 4)
+    return launch_fast_canon8(L, ext, canon, lmbds, colmax, pinv_eps, n_cols, st);
   if (prec == BQA_C64) return launch_canonicalize<float>(D, L, ext, canon, lmbds, colmax, pinv_eps, st);
   return launch_canonicalize<double>(D, L, ext, canon, lmbds, colmax, pinv_eps, st);
 }

@@ -55,4 +55,10 @@ int launch_fast_msgs_d3D4(bool ext, long long B, const void* T, const void* msgs
                           double damping, int write_undamped, double bp_eps, int it, void* resid, int32_t* status,
                           cudaStream_t st);
 
+// specialised canonicalizer kernel (bqa_fast_canon8.cu): D = 4 (n = 8), complex64
+int launch_fast_canon8(long long L, const void* ext, void* canon, void* lmbds, void* colmax, double pinv_eps,
+                       int ncols, cudaStream_t st);
+
+void canon8_stats(unsigned long long* out2);
+
 }  // namespace bqa

@@ -335,7 +335,8 @@ class Engine:
         self._exchange_ext()
         self._colmax.zero_()
         self.lib.canonicalize(self.prec, D, self.L, self._ext.data_ptr(), self._canon.data_ptr(),
-                              self._lmbds.data_ptr(), self._colmax.data_ptr(), self.pinv_eps, st)
+                              self._lmbds.data_ptr(), self._colmax.data_ptr(), self.pinv_eps,
+                              min(2 * D, self.Dmax), st)
         self._lmbd_stride = 2 * D
         self._reduce_colmax(self._colmax)
         colmax = self._to_host(self._colmax)[: 2 * D].astype(np.float64)        # the one host sync per step

@@ -41,6 +41,10 @@ long long bqa_b200_launch_count(void);
  * 1: generic kernels only (used by the tests to check the specialised kernels against the generic ones) */
 int bqa_b200_set_kernel_mode(int mode);
 
+/* profiling aid: out2[0] = warp-level Jacobi problems solved by the n = 8 canonicalizer kernel since load,
+ * out2[1] = Jacobi sweeps summed over them (synchronises the device) */
+int bqa_b200_canon_stats(unsigned long long* out2);
+
 /* bytes of device scratch the node kernels need for a degree class (pass the max over classes) */
 size_t bqa_b200_workspace_bytes(int prec, int degree, int D, int D_new);
 
@@ -73,9 +77,11 @@ int bqa_b200_ext_msgs(int prec, int degree, int D, long long B, const void* T, c
  * replaces _get_canonicalizers (state.py:171-200): masked SVD of every extended message
  * (backends.py:483-490, 709-727), ker = lu_f lu_b^T, masked SVD of ker, canonicalizers = [ul_b vs ; ul_f us],
  * lmbds = s / |s|.  ext, canon: (2L, 2D, 2D); lmbds: real (L, 2D); colmax: real (2D), zeroed by the
- * caller, receives the column-wise max of lmbds over all edges (truncate_lmbds, backends.py:297-299). */
+ * caller, receives the column-wise max of lmbds over all edges (truncate_lmbds, backends.py:297-299).
+ * n_cols: number of leading canonicalizer columns the caller will use (>= min(2D, max_bond_dim), the largest
+ * bond dimension the truncation can keep, state.py:233-235); columns >= n_cols of canon may be left unwritten. */
 int bqa_b200_canonicalize(int prec, int D, long long L, const void* ext, void* canon, void* lmbds,
-                          void* colmax, double pinv_eps, void* stream);
+                          void* colmax, double pinv_eps, int n_cols, void* stream);
 
 /* ---- K3c + K4: apply the simple update to a degree class ---------------------------------------
  * replaces batch_truncate_all_but + apply_canonicalizers_with_extensions (state.py:235-246,

@@ -149,6 +149,7 @@ const char* bqa_b200_last_error(void) { return g_err; }
 int bqa_b200_version(void) { return -1; }   // negative: host emulation
 long long bqa_b200_launch_count(void) { return g_calls; }
 int bqa_b200_set_kernel_mode(int) { return 0; }
+int bqa_b200_canon_stats(unsigned long long* o) { o[0] = o[1] = 0; return 0; }
 size_t bqa_b200_workspace_bytes(int, int, int, int) { return 16; }
 
 int bqa_b200_bp_sweep(int prec, int degree, int D, long long B, const void* T, const void* msgs_cur, void* msgs_nxt,
@@ -164,7 +165,7 @@ int bqa_b200_ext_msgs(int prec, int degree, int D, long long B, const void* T, c
            bp_or_ext<double>(true, degree, D, B, T, msgs_cur, ext, in_pos, out_pos, edge_ampls, ztime, 0, 0, 0, 0, nullptr, nullptr));
 }
 int bqa_b200_canonicalize(int prec, int D, long long L, const void* ext, void* canon, void* lmbds, void* colmax,
-                          double pinv_eps, void*) {
+                          double pinv_eps, int /*n_cols*/, void*) {
   DISPATCH(canonicalize<float>(D, L, ext, canon, lmbds, colmax, pinv_eps),
            canonicalize<double>(D, L, ext, canon, lmbds, colmax, pinv_eps));
 }

@@ -112,7 +112,7 @@ def test_jacobi_canonicalizers_are_gauge_equivalent_to_lapack(emu):
     canon = torch.zeros_like(e)
     lm = torch.zeros(L * n, dtype=torch.float64)
     colmax = torch.zeros(n, dtype=torch.float64)
-    emu.canonicalize(_lib.C128, D, L, e.data_ptr(), canon.data_ptr(), lm.data_ptr(), colmax.data_ptr(), 1e-9, 0)
+    emu.canonicalize(_lib.C128, D, L, e.data_ptr(), canon.data_ptr(), lm.data_ptr(), colmax.data_ptr(), 1e-9, n, 0)
     lm = lm.numpy().reshape(L, n)
     assert np.abs(lm - lm_ref.real).max() < 1e-10
     assert np.abs(colmax.numpy() - lm_ref.real.max(0)).max() < 1e-10
@@ -178,7 +178,7 @@ def test_rank_deficient_ker_keeps_relative_accuracy(emu):
     canon = torch.zeros_like(e)
     lm = torch.zeros(L * n, dtype=torch.float64)
     colmax = torch.zeros(n, dtype=torch.float64)
-    emu.canonicalize(_lib.C128, 4, L, e.data_ptr(), canon.data_ptr(), lm.data_ptr(), colmax.data_ptr(), 1e-6, 0)
+    emu.canonicalize(_lib.C128, 4, L, e.data_ptr(), canon.data_ptr(), lm.data_ptr(), colmax.data_ptr(), 1e-6, n, 0)
     lm = lm.numpy().reshape(L, n)
     assert (lm_ref.real[:, 3] > 0).all() and (lm_ref.real[:, 4] == 0).all()
     rel = np.abs(lm[:, :4] - lm_ref.real[:, :4]) / lm_ref.real[:, :4]

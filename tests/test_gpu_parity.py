@@ -225,3 +225,54 @@ def test_fast_d3D4_kernels_match_generic_and_oracle(lib, B):
         damped = 0.25 * cur[out_pos[j]] + 0.75 * want[j]
         assert np.abs(fast[0][out_pos[j]] - damped).max() < 2e-6
         assert np.abs(fast[2][out_pos[j]] - want_ext[j]).max() < 2e-6
+
+
+def _graded_ext_msgs(rng, L, n=8):
+    """Hermitian PSD trace-1 matrices with the graded spectra extended messages have in the symmetric gauge."""
+    spec = np.array([0.82, 0.18, 1.4e-3, 3e-4, 4e-5, 9e-6, 2e-6, 3e-7])
+
+    def psd():
+        q = np.linalg.qr(rng.normal(size=(L, n, n)) + 1j * rng.normal(size=(L, n, n)))[0]
+        q = np.linalg.qr(np.eye(n) + 0.05 * q)[0]
+        s = spec * np.exp(rng.normal(scale=0.3, size=(L, n)))
+        m = (q * (s / s.sum(1, keepdims=True))[:, None, :]) @ np.swapaxes(q.conj(), 1, 2)
+        return 0.5 * (m + np.swapaxes(m.conj(), 1, 2))
+    return np.concatenate([psd(), psd()], 0)
+
+
+@pytest.mark.parametrize("L", [1, 5, 3001])
+def test_fast_canon8_matches_oracle(lib, L):
+    """Specialised n = 8 complex64 canonicalizer kernel (bqa_fast_canon8.cu) against the oracle's
+    _get_canonicalizers restatement (reference state.py:171-200) in complex128: lambdas, column maxima and the
+    gauge-invariant bond operator sum_k C_b[a,k] lambda_k C_f[b,k] over the 4 kept columns; the generic
+    complex64 kernel on the same input sets the scale of what complex64 can deliver."""
+    import torch
+    from bqa_b200 import _lib
+    from oracle import bqa_oracle as O
+    rng = np.random.default_rng(100 + L)
+    n, D = 8, 4
+    ext = _graded_ext_msgs(rng, L).astype(np.complex64)
+    lm_ref, canon_ref = O.canonicalizers(ext.astype(np.complex128), 1e-6, np.complex128)
+    lm_ref = lm_ref.real
+    inv_ref = np.einsum("eak,ek,ebk->eab", canon_ref[:L, :, :4], lm_ref[:, :4], canon_ref[L:, :, :4])
+    dev = torch.device("cuda:0")
+    e = torch.from_numpy(ext.reshape(-1)).to(dev)
+    st = torch.cuda.current_stream().cuda_stream
+    err = {}
+    for mode in (1, 0):
+        lib.set_kernel_mode(mode)
+        try:
+            canon = torch.zeros_like(e)
+            lm = torch.zeros(L * n, dtype=torch.float32, device=dev)
+            colmax = torch.zeros(n, dtype=torch.float32, device=dev)
+            lib.canonicalize(_lib.C64, D, L, e.data_ptr(), canon.data_ptr(), lm.data_ptr(), colmax.data_ptr(), 1e-6, 4, st)
+        finally:
+            lib.set_kernel_mode(0)
+        lmh = lm.cpu().numpy().reshape(L, n).astype(np.float64)
+        c = canon.cpu().numpy().reshape(2 * L, n, n).astype(np.complex128)
+        inv = np.einsum("eak,ek,ebk->eab", c[:L, :, :4], lmh[:, :4], c[L:, :, :4])
+        err[mode] = (np.abs(lmh[:, :4] - lm_ref[:, :4]).max(), np.abs(inv - inv_ref).max(),
+                     np.abs(colmax.cpu().numpy() - lmh.max(0)).max())
+    assert err[0][2] == 0.0                                   # column maxima are exactly the maxima of what was written
+    assert err[0][0] < 5e-6                                   # lambdas (L2-normalised, <= 1)
+    assert err[0][1] < max(2.0 * err[1][1], 2e-4)             # no worse than the generic complex64 kernel

@@ -31,7 +31,12 @@ constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int kSlice = 144;                       // 128-byte slice + 16 bytes of padding (bank spreading)
 constexpr int kTBytes = 32 * kSlice;              // 4 nodes x 8 slices
-constexpr int kMBytes = 12 * 128;                 // 3 messages x 4 nodes
+constexpr int kMsg = 144;                         // 128-byte message + 16 bytes of padding
+constexpr int kMBytes = 12 * kMsg;                // 3 messages x 4 nodes
+constexpr int kRedRow = 80;                       // packed Hermitian partial: 4 diagonal + 6 upper entries (complex)
+constexpr int kRedSlot = 8 * kRedRow + 64;        // 8 lanes of a node (+ skew between the two nodes of a half warp)
+constexpr int kOut0 = 4 * kRedSlot;               // scratch offset of the out_0 exchange (4 rows of 288 bytes)
+constexpr int kOut0Row = 288;
 constexpr int kStage = kTBytes + 2 * kMBytes;     // T | incoming messages | previous outgoing messages
 constexpr int kWarpBytes = 2 * kStage + kTBytes;  // two stages + reduction scratch
 constexpr int kSmem = kWarps * kWarpBytes;
@@ -108,13 +113,12 @@ __device__ __forceinline__ void issue_group(const Args& a, unsigned char* stage,
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
     const int pin = __shfl_sync(0xffffffffu, idx_reg, j * 4 + s);
-    cp_async16(stage + kTBytes + (j * 4 + s) * 128 + ch * 16, Mg + (size_t)pin * 128 + ch * 16);
+    cp_async16(stage + kTBytes + (j * 4 + s) * kMsg + ch * 16, Mg + (size_t)pin * 128 + ch * 16);
     if (!EXT) {
       const int pout = __shfl_sync(0xffffffffu, idx_reg, 12 + j * 4 + s);
-      cp_async16(stage + kTBytes + kMBytes + (j * 4 + s) * 128 + ch * 16, Mg + (size_t)pout * 128 + ch * 16);
+      cp_async16(stage + kTBytes + kMBytes + (j * 4 + s) * kMsg + ch * 16, Mg + (size_t)pout * 128 + ch * 16);
     }
   }
-  cp_async_commit();
 }
 
 // lanes 0..11 hold in_pos[j][node0 + s], lanes 12..23 hold out_pos[j][node0 + s]  (index j * 4 + s)
@@ -150,13 +154,28 @@ __global__ void __launch_bounds__(kThreads, 1) k_msgs_d3D4(Args a) {
   long long g = (long long)blockIdx.x * kWarps + wib;
   float mnum = 0.f, mden = 0.f;
 
+  // packed Hermitian partials: entry (x, x) at complex index x, entry (x < y) at 4 + pair(x, y); this lane finally
+  // owns (x, y0) and (x, y0 + 1), x = t / 2, y0 = 2 (t % 2); a lower-triangle entry is the conjugate of its mirror
+  int offA, offB;
+  float sgnA, sgnB;
+  {
+    const int x = t >> 1, y0 = (t & 1) * 2;
+    auto pack = [](int i, int j) { return i == j ? i : 4 + (i == 0 ? j - 1 : (i == 1 ? j + 1 : 5)); };
+    const int ya = y0, yb = y0 + 1;
+    offA = 8 * (x <= ya ? pack(x, ya) : pack(ya, x));
+    offB = 8 * (x <= yb ? pack(x, yb) : pack(yb, x));
+    sgnA = x > ya ? -1.f : 1.f;
+    sgnB = x > yb ? -1.f : 1.f;
+  }
   int idx_cur = 0, idx_nxt = 0;
   if (g < groups) {
     idx_cur = load_idx(a, g * 4, lane);
     issue_group<EXT>(a, wbase, g * 4, lane, idx_cur);
+    cp_async_commit();
     if (g + nwarps < groups) idx_nxt = load_idx(a, (g + nwarps) * 4, lane);
   }
   int cur = 0;
+#pragma unroll 1
   for (; g < groups; g += nwarps, cur ^= 1) {
     unsigned char* st = wbase + cur * kStage;
     const bool has_next = g + nwarps < groups;
@@ -164,12 +183,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_msgs_d3D4(Args a) {
     if (has_next) {
       issue_group<EXT>(a, wbase + (cur ^ 1) * kStage, (g + nwarps) * 4, lane, idx_nxt);
       if (g + 2 * nwarps < groups) idx_nn = load_idx(a, (g + 2 * nwarps) * 4, lane);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
     }
+    cp_async_commit();                                      // always commit (possibly empty): one loop body, one wait
+    cp_async_wait<1>();
     __syncwarp();
 
+    float th[3] = {0.f, 0.f, 0.f};
+    if (EXT) {                                              // coupling angles of this node's 3 legs, fetched early
+      long long nn = g * 4 + s;
+      nn = nn > a.B - 1 ? a.B - 1 : nn;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) th[k] = __ldg(a.edge_ampls + (size_t)k * a.B + nn) * a.ztime;
+    }
     const unsigned char* Ts = st + (s * 8 + p * 4) * kSlice;          // the four a-slices of (node, p)
     const unsigned char* Min = st + kTBytes;
     float2 U0[16], U1[16], U2[16];
@@ -177,7 +202,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_msgs_d3D4(Args a) {
       float2 tt[16], m[16];
       lds_tile(tt, Ts + la * kSlice);
       // U2[b][c'] = sum_c m2[c'][c] T[b][c]
-      lds_tile(m, Min + (2 * 4 + s) * 128);
+      lds_tile(m, Min + (2 * 4 + s) * kMsg);
 #pragma unroll
       for (int b = 0; b < 4; ++b)
 #pragma unroll
@@ -188,7 +213,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_msgs_d3D4(Args a) {
           U2[b * 4 + c2] = acc;
         }
       // U1[b'][c] = sum_b m1[b'][b] T[b][c]
-      lds_tile(m, Min + (1 * 4 + s) * 128);
+      lds_tile(m, Min + (1 * 4 + s) * kMsg);
 #pragma unroll
       for (int b2 = 0; b2 < 4; ++b2)
 #pragma unroll
@@ -201,18 +226,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_msgs_d3D4(Args a) {
     }
     {
       // U0[a][b][c] = sum_a' m0[a][a'] T[a'][b][c]: row `la` of m0, the four slices broadcast from shared memory
-      const float4 r0 = *reinterpret_cast<const float4*>(Min + (0 * 4 + s) * 128 + la * 32);
-      const float4 r1 = *reinterpret_cast<const float4*>(Min + (0 * 4 + s) * 128 + la * 32 + 16);
-      const float2 m0row[4] = {make_float2(r0.x, r0.y), make_float2(r0.z, r0.w), make_float2(r1.x, r1.y),
-                               make_float2(r1.z, r1.w)};
+      const unsigned char* m0row = Min + (0 * 4 + s) * kMsg + la * 32;
 #pragma unroll
       for (int i = 0; i < 16; ++i) U0[i] = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int a2 = 0; a2 < 4; ++a2) {
+#pragma unroll 1
+      for (int a2 = 0; a2 < 4; ++a2) {                      // rolled: code size (instruction cache) matters
         float2 tt[16];
         lds_tile(tt, Ts + a2 * kSlice);
+        const float2 m = *reinterpret_cast<const float2*>(m0row + a2 * 8);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) fma_c(U0[i], m0row[a2], tt[i]);
+        for (int i = 0; i < 16; ++i) fma_c(U0[i], m, tt[i]);
       }
     }
     __syncwarp();                                           // every lane is done with the T slices
@@ -220,55 +243,72 @@ __global__ void __launch_bounds__(kThreads, 1) k_msgs_d3D4(Args a) {
     sts_tile(Xs + la * kSlice, U1);
 
     float2 e[3][4];                                         // per message k: [g0 piece (2), g1 piece (2)]; BP sums them
-    unsigned char* red = scratch + s * (8 * kSlice);
-    // ---- out_1[x][y] = sum_{a,c} conj(U2[a][x][c]) U0[a][y][c]  (partial over this lane's (p, a)) ----
-    // ---- out_2[x][y] = sum_{a,b} conj(U1[a][b][x]) U0[a][b][y]
+    unsigned char* red = scratch + s * kRedSlot;
+    // ---- out_1[x][y] = sum_{a,c} conj(U2[a][x][c]) U0[a][y][c],  out_2[x][y] = sum_{a,b} conj(U1[a][b][x]) U0[a][b][y]
+    // (partial over this lane's (p, a); Hermitian: diagonal real parts and the upper triangle only)
 #pragma unroll
     for (int k = 1; k <= 2; ++k) {
-      float2 acc[16];
+      float2 acc[10];
 #pragma unroll
-      for (int x = 0; x < 4; ++x)
+      for (int x = 0; x < 4; ++x) {
+        float d = 0.f;
 #pragma unroll
-        for (int y = 0; y < 4; ++y) {
-          float2 v = make_float2(0.f, 0.f);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (k == 1) fma_cc(v, U2[x * 4 + q], U0[y * 4 + q]);
-            else fma_cc(v, U1[q * 4 + x], U0[q * 4 + y]);
-          }
-          acc[x * 4 + y] = v;
+        for (int q = 0; q < 4; ++q) {
+          const float2 u = (k == 1) ? U2[x * 4 + q] : U1[q * 4 + x];
+          const float2 v = (k == 1) ? U0[x * 4 + q] : U0[q * 4 + x];
+          d = fmaf(u.x, v.x, d); d = fmaf(u.y, v.y, d);
         }
+        acc[x] = make_float2(d, 0.f);
+      }
+      {
+        int n = 4;
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+          for (int y = x + 1; y < 4; ++y) {
+            float2 v = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (k == 1) fma_cc(v, U2[x * 4 + q], U0[y * 4 + q]);
+              else fma_cc(v, U1[q * 4 + x], U0[q * 4 + y]);
+            }
+            acc[n++] = v;
+          }
+      }
       __syncwarp();                                         // previous readers of the scratch are done
-      sts_tile(red + t * kSlice, acc);
+#pragma unroll
+      for (int i = 0; i < 5; ++i)
+        *reinterpret_cast<float4*>(red + t * kRedRow + 16 * i) =
+            make_float4(acc[2 * i].x, acc[2 * i].y, acc[2 * i + 1].x, acc[2 * i + 1].y);
       __syncwarp();
       float2 g0a = make_float2(0.f, 0.f), g0b = g0a, g1a = g0a, g1b = g0a;
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
-        const float4 v0 = *reinterpret_cast<const float4*>(red + r * kSlice + t * 16);
-        const float4 v1 = *reinterpret_cast<const float4*>(red + (4 + r) * kSlice + t * 16);
-        g0a.x += v0.x; g0a.y += v0.y; g0b.x += v0.z; g0b.y += v0.w;
-        g1a.x += v1.x; g1a.y += v1.y; g1b.x += v1.z; g1b.y += v1.w;
+        const float2 a0 = *reinterpret_cast<const float2*>(red + r * kRedRow + offA);
+        const float2 b0 = *reinterpret_cast<const float2*>(red + r * kRedRow + offB);
+        const float2 a1 = *reinterpret_cast<const float2*>(red + (4 + r) * kRedRow + offA);
+        const float2 b1 = *reinterpret_cast<const float2*>(red + (4 + r) * kRedRow + offB);
+        g0a.x += a0.x; g0a.y += a0.y; g0b.x += b0.x; g0b.y += b0.y;
+        g1a.x += a1.x; g1a.y += a1.y; g1b.x += b1.x; g1b.y += b1.y;
       }
-      e[k][0] = g0a; e[k][1] = g0b; e[k][2] = g1a; e[k][3] = g1b;
+      e[k][0] = make_float2(g0a.x, sgnA * g0a.y); e[k][1] = make_float2(g0b.x, sgnB * g0b.y);
+      e[k][2] = make_float2(g1a.x, sgnA * g1a.y); e[k][3] = make_float2(g1b.x, sgnB * g1b.y);
     }
     // ---- out_0[x][y] = sum_{b,c} conj(U1[x][b][c]) U2[y][b][c]: lane (p, y = la) against the exchanged U1 slices
     {
-      float2 col[4];
-#pragma unroll
-      for (int x = 0; x < 4; ++x) {
+      unsigned char* o0 = scratch + kOut0 + s * 64;         // [x][node][p][y]: a warp-wide store is 256 contiguous bytes
+#pragma unroll 1
+      for (int x = 0; x < 4; ++x) {                         // rolled: code size
         float2 ux[16];
         lds_tile(ux, Xs + x * kSlice);
-        float2 v = make_float2(0.f, 0.f);
+        float2 v0 = make_float2(0.f, 0.f), v1 = v0;         // two chains
 #pragma unroll
-        for (int i = 0; i < 16; ++i) fma_cc(v, ux[i], U2[i]);
-        col[x] = v;
+        for (int i = 0; i < 16; i += 2) { fma_cc(v0, ux[i], U2[i]); fma_cc(v1, ux[i + 1], U2[i + 1]); }
+        *reinterpret_cast<float2*>(o0 + x * kOut0Row + p * 32 + la * 8) = make_float2(v0.x + v1.x, v0.y + v1.y);
       }
       __syncwarp();
-#pragma unroll
-      for (int x = 0; x < 4; ++x) *reinterpret_cast<float2*>(red + p * kSlice + (x * 4 + la) * 8) = col[x];
-      __syncwarp();
-      const float4 v0 = *reinterpret_cast<const float4*>(red + t * 16);
-      const float4 v1 = *reinterpret_cast<const float4*>(red + kSlice + t * 16);
+      const float4 v0 = *reinterpret_cast<const float4*>(o0 + (t >> 1) * kOut0Row + (t & 1) * 16);
+      const float4 v1 = *reinterpret_cast<const float4*>(o0 + (t >> 1) * kOut0Row + 32 + (t & 1) * 16);
       e[0][0] = make_float2(v0.x, v0.y); e[0][1] = make_float2(v0.z, v0.w);
       e[0][2] = make_float2(v1.x, v1.y); e[0][3] = make_float2(v1.z, v1.w);
     }
@@ -292,7 +332,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_msgs_d3D4(Args a) {
         const float d = 1.f / (tr.x * tr.x + tr.y * tr.y);
         const float2 itr = make_float2(tr.x * d, -tr.y * d);
         const float2 na = cmul(itr, sa), nb = cmul(itr, sb);
-        const float4 ov = *reinterpret_cast<const float4*>(st + kTBytes + kMBytes + (k * 4 + s) * 128 + t * 16);
+        const float4 ov = *reinterpret_cast<const float4*>(st + kTBytes + kMBytes + (k * 4 + s) * kMsg + t * 16);
         if (live) {
           float da = (na.x - ov.x) * (na.x - ov.x) + (na.y - ov.y) * (na.y - ov.y);
           float db = (nb.x - ov.z) * (nb.x - ov.z) + (nb.y - ov.w) * (nb.y - ov.w);
@@ -311,10 +351,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_msgs_d3D4(Args a) {
         }
       } else {
         // ext[(s1,x),(s2,y)] = conj(f_s1) f_s2 (g0 + (-1)^(s1+s2) g1)[x][y] / ((|f0|^2 + |f1|^2) trace)
-        long long nn = node > a.B - 1 ? a.B - 1 : node;
-        const float theta = __ldg(a.edge_ampls + (size_t)k * a.B + nn) * a.ztime;
         cx<float> f0, f1;
-        zz_factors<float>(theta, f0, f1);
+        zz_factors<float>(th[k], f0, f1);
         const float2 ff[2] = {make_float2(f0.re, f0.im), make_float2(f1.re, f1.im)};
         const float w = (f0.re * f0.re + f0.im * f0.im + f1.re * f1.re + f1.im * f1.im);
         const float d = 1.f / (w * (tr.x * tr.x + tr.y * tr.y));

@@ -228,8 +228,10 @@ def test_fast_d3D4_kernels_match_generic_and_oracle(lib, B):
 
 
 def _graded_ext_msgs(rng, L, n=8):
-    """Hermitian PSD trace-1 matrices with the graded spectra extended messages have in the symmetric gauge."""
-    spec = np.array([0.82, 0.18, 1.4e-3, 3e-4, 4e-5, 9e-6, 2e-6, 3e-7])
+    """Hermitian PSD trace-1 matrices with the graded spectra extended messages have in the symmetric gauge.
+    The spectrum stays clear of the pinv_eps = 1e-6 mask (kept values >= 3e-6, masked ones <= 1e-7): an
+    eigenvalue within complex64 rounding of the cut would be kept by one precision and dropped by the other."""
+    spec = np.array([0.82, 0.18, 1.4e-3, 3e-4, 4e-5, 9e-6, 2.5e-8, 3e-9])
 
     def psd():
         q = np.linalg.qr(rng.normal(size=(L, n, n)) + 1j * rng.normal(size=(L, n, n)))[0]

@@ -278,3 +278,18 @@ def test_fast_canon8_matches_oracle(lib, L):
     assert err[0][2] == 0.0                                   # column maxima are exactly the maxima of what was written
     assert err[0][0] < 5e-6                                   # lambdas (L2-normalised, <= 1)
     assert err[0][1] < max(2.0 * err[1][1], 2e-4)             # no worse than the generic complex64 kernel
+
+
+def test_partitioned_nccl(lib):
+    """Node-partitioned engine over NCCL on 2 GPUs == single-GPU engine (skipped on a 1-GPU box; the gloo
+    world_size-2/3 tests in tests/test_partitioned.py cover the same logic on CPU)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(here, "multigpu_check.py")],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "multigpu_check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -164,7 +164,7 @@ def run_reference(args) -> None:
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "sweeps_per_step": r["sweeps_per_step"], "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def make_bench_config(n_gpus: int) -> dict:
@@ -296,7 +296,7 @@ def run_ours(args) -> None:
             return e.state_to_host()
         r = cpu_steps_per_s(CPU_SAMPLE_QUBITS, args.cpu_steps, 0, inject=inject)
         line["cpu_baseline"] = {kk: r[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -385,7 +385,25 @@ def measure_e2e(eng, snapshot, layers, torch, dev, bloch_resident) -> dict:
                     "wall clock incl. all copies"}
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line, written to the process's original stdout (see main)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main() -> None:
+    # libraries (NCCL's version banner, warnings) write to fd 1: keep stdout for the JSON line alone
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

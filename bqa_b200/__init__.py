@@ -12,5 +12,6 @@ Importing the package does not need a GPU; constructing an Engine does (there is
 from .config import ConfigSyntaxError, Context, Layout, config_to_context  # noqa: F401
 from .core import run_context, run_qa  # noqa: F401
 from .engine import Engine  # noqa: F401
+from .backend import register_with_bqa  # noqa: F401
 
 __version__ = "0.1.0"

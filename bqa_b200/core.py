@@ -12,9 +12,10 @@ log = logging.getLogger(__name__)
 def run_context(context, precision=None, device=None, engine_cls=Engine, **engine_kwargs) -> list:
     """Interprets the instruction list of a compiled context (ours or bqa's own ``Context``)."""
     engine = engine_cls(context, precision=precision, device=device, **engine_kwargs)
-    n = len(context.instructions)
+    instructions = list(context.instructions)
+    n = len(instructions)
     results = []
-    for i, ins in enumerate(context.instructions):
+    for i, ins in enumerate(instructions):
         log.info(f"Instruction number {i} / {n} started")
         if isinstance(ins, dict):
             engine.run_layer(ins["xtime"], ins["ztime"])        # "type" is ignored like in the reference (core.py:23)

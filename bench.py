@@ -312,9 +312,13 @@ def measure_roofline(eng, lib, layers, torch, dev) -> dict:
             peaks = json.load(f)
     peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks \
         else (6650.0, "fallback (B200_PROFILING.md)")
-    names = ["bp_sweep", "ext_msgs", "canonicalize", "apply_update"]
+    # entry point -> bucket (the partitioned engine calls the *_p2p variants)
+    buckets = {"bp_sweep": "bp_sweep", "bp_sweep_p2p": "bp_sweep", "ext_msgs": "ext_msgs", "ext_msgs_p2p": "ext_msgs",
+               "canonicalize": "canonicalize", "apply_update": "apply_update", "sweep_sync": "sweep_sync",
+               "gauge_msgs": "gauge_msgs"}
+    names = sorted(set(buckets.values()))
     events = {n: [] for n in names}
-    orig = {n: getattr(lib, n) for n in names}
+    orig = {n: getattr(lib, n) for n in buckets}
 
     def wrap(name):
         fn = orig[name]
@@ -324,16 +328,16 @@ def measure_roofline(eng, lib, layers, torch, dev) -> dict:
             e0.record()
             fn(*a)
             e1.record()
-            events[name].append((e0, e1, a))
+            events[buckets[name]].append((e0, e1, a))
         return call
-    for n in names:
+    for n in buckets:
         setattr(lib, n, wrap(n))
     try:
         for ins in layers:
             eng.run_layer(ins["xtime"], ins["ztime"])
         torch.cuda.synchronize(dev)
     finally:
-        for n in names:
+        for n in buckets:
             setattr(lib, n, orig[n])
     nsteps = max(len(layers), 1)
     out = {"kernel_ms_per_step": {}}

@@ -15,6 +15,10 @@ _vp, _i, _ll, _d, _sz = C.c_void_p, C.c_int, C.c_longlong, C.c_double, C.c_size_
 
 # name -> argtypes, exactly as declared in include/bqa_b200.h
 SIGNATURES = {
+    "bqa_b200_bp_sweep_p2p": [_i, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp, _d, _i, _d, _i, _vp, _vp, _vp, _sz, _vp, _vp, _vp],
+    "bqa_b200_ext_msgs_p2p": [_i, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _d, _vp, _sz, _vp, _vp, _vp],
+    "bqa_b200_sweep_sync": [_i, _i, _i, _vp, _i, _vp, C.c_uint, _vp, _vp],
+    "bqa_b200_gauge_msgs": [_i, _i, _i, _ll, _vp, _vp, _vp],
     "bqa_b200_bp_sweep": [_i, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp, _d, _i, _d, _i, _vp, _vp, _vp, _sz, _vp],
     "bqa_b200_ext_msgs": [_i, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _d, _vp, _sz, _vp],
     "bqa_b200_canonicalize": [_i, _i, _ll, _vp, _vp, _vp, _vp, _d, _i, _vp],

@@ -267,6 +267,9 @@ class Layout:
     lmbds_position: np.ndarray
     node_ampls: np.ndarray
     edge_ampls: np.ndarray
+    # partitioned runs over peer memory only (bqa_b200/partitioned.py): where the owner of the receiving node keeps
+    # each outgoing message, (peer << 27 | slot on that peer), -1 if the receiver is owned by this rank
+    remote_msgs_position: np.ndarray = None
 
     @property
     def degree(self) -> int:

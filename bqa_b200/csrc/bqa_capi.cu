@@ -64,35 +64,67 @@ size_t bqa_b200_workspace_bytes(int prec, int degree, int D, int D_new) {
   return generic_ws_elems_per_warp(degree, D, D_new) * elem * BQA_GENERIC_MAX_WARPS;
 }
 
-int bqa_b200_bp_sweep(int prec, int degree, int D, long long B, const void* T, const void* msgs_cur,
-                      void* msgs_nxt, const int32_t* in_pos, const int32_t* out_pos, double damping,
-                      int write_undamped, double bp_eps, int it, void* resid, int32_t* status, void* workspace,
-                      size_t workspace_bytes, void* stream) {
+int bqa_b200_bp_sweep_p2p(int prec, int degree, int D, long long B, const void* T, const void* msgs_cur,
+                          void* msgs_nxt, const int32_t* in_pos, const int32_t* out_pos, double damping,
+                          int write_undamped, double bp_eps, int it, void* resid, int32_t* status, void* workspace,
+                          size_t workspace_bytes, const int32_t* remote_pos, void* const* peers, void* stream) {
   if (int rc = check_shape(prec, degree, D)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   if (g_kernel_mode.load() == 0 && fast_d3D4_available(prec, degree, D))
     return launch_fast_msgs_d3D4(false, B, T, msgs_cur, msgs_nxt, in_pos, out_pos, nullptr, 0.0, damping, write_undamped,
-                                 bp_eps, it, resid, status, st);
+                                 bp_eps, it, resid, status, remote_pos, peers, st);
   if (prec == BQA_C64)
     return launch_node_msgs<float>(false, degree, D, B, T, msgs_cur, msgs_nxt, in_pos, out_pos, nullptr, 0.0, damping,
-                                   write_undamped, bp_eps, it, resid, status, workspace, workspace_bytes, st);
+                                   write_undamped, bp_eps, it, resid, status, workspace, workspace_bytes, remote_pos,
+                                   peers, st);
   return launch_node_msgs<double>(false, degree, D, B, T, msgs_cur, msgs_nxt, in_pos, out_pos, nullptr, 0.0, damping,
-                                  write_undamped, bp_eps, it, resid, status, workspace, workspace_bytes, st);
+                                  write_undamped, bp_eps, it, resid, status, workspace, workspace_bytes, remote_pos,
+                                  peers, st);
+}
+
+int bqa_b200_bp_sweep(int prec, int degree, int D, long long B, const void* T, const void* msgs_cur,
+                      void* msgs_nxt, const int32_t* in_pos, const int32_t* out_pos, double damping,
+                      int write_undamped, double bp_eps, int it, void* resid, int32_t* status, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  return bqa_b200_bp_sweep_p2p(prec, degree, D, B, T, msgs_cur, msgs_nxt, in_pos, out_pos, damping, write_undamped,
+                               bp_eps, it, resid, status, workspace, workspace_bytes, nullptr, nullptr, stream);
+}
+
+int bqa_b200_ext_msgs_p2p(int prec, int degree, int D, long long B, const void* T, const void* msgs_cur, void* ext,
+                          const int32_t* in_pos, const int32_t* out_pos, const void* edge_ampls, double ztime,
+                          void* workspace, size_t workspace_bytes, const int32_t* remote_pos, void* const* peers,
+                          void* stream) {
+  if (int rc = check_shape(prec, degree, D)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (g_kernel_mode.load() == 0 && fast_d3D4_available(prec, degree, D))
+    return launch_fast_msgs_d3D4(true, B, T, msgs_cur, ext, in_pos, out_pos, edge_ampls, ztime, 0.0, 0, 0.0, 0, nullptr,
+                                 nullptr, remote_pos, peers, st);
+  if (prec == BQA_C64)
+    return launch_node_msgs<float>(true, degree, D, B, T, msgs_cur, ext, in_pos, out_pos, edge_ampls, ztime, 0.0, 0,
+                                   0.0, 0, nullptr, nullptr, workspace, workspace_bytes, remote_pos, peers, st);
+  return launch_node_msgs<double>(true, degree, D, B, T, msgs_cur, ext, in_pos, out_pos, edge_ampls, ztime, 0.0, 0,
+                                  0.0, 0, nullptr, nullptr, workspace, workspace_bytes, remote_pos, peers, st);
 }
 
 int bqa_b200_ext_msgs(int prec, int degree, int D, long long B, const void* T, const void* msgs_cur, void* ext,
                       const int32_t* in_pos, const int32_t* out_pos, const void* edge_ampls, double ztime,
                       void* workspace, size_t workspace_bytes, void* stream) {
-  if (int rc = check_shape(prec, degree, D)) return rc;
+  return bqa_b200_ext_msgs_p2p(prec, degree, D, B, T, msgs_cur, ext, in_pos, out_pos, edge_ampls, ztime, workspace,
+                               workspace_bytes, nullptr, nullptr, stream);
+}
+
+int bqa_b200_gauge_msgs(int prec, int D_old, int D_new, long long L, const void* lmbds, void* msgs_out, void* stream) {
+  if (int rc = check_shape(prec, 0, D_old)) return rc;
+  if (D_new < 1 || D_new > 2 * D_old || D_new > BQA_MAX_D) return set_error("new bond dimension %d invalid for D = %d", D_new, D_old);
   cudaStream_t st = (cudaStream_t)stream;
-  if (g_kernel_mode.load() == 0 && fast_d3D4_available(prec, degree, D))
-    return launch_fast_msgs_d3D4(true, B, T, msgs_cur, ext, in_pos, out_pos, edge_ampls, ztime, 0.0, 0, 0.0, 0, nullptr,
-                                 nullptr, st);
-  if (prec == BQA_C64)
-    return launch_node_msgs<float>(true, degree, D, B, T, msgs_cur, ext, in_pos, out_pos, edge_ampls, ztime, 0.0, 0,
-                                   0.0, 0, nullptr, nullptr, workspace, workspace_bytes, st);
-  return launch_node_msgs<double>(true, degree, D, B, T, msgs_cur, ext, in_pos, out_pos, edge_ampls, ztime, 0.0, 0,
-                                  0.0, 0, nullptr, nullptr, workspace, workspace_bytes, st);
+  if (prec == BQA_C64) return launch_gauge_msgs<float>(D_old, D_new, L, lmbds, msgs_out, st);
+  return launch_gauge_msgs<double>(D_old, D_new, L, lmbds, msgs_out, st);
+}
+
+int bqa_b200_sweep_sync(int prec, int rank, int world, void* const* peer_resid, int it, void* const* peer_flags,
+                        unsigned seq, int32_t* status, void* stream) {
+  if (prec != BQA_C64 && prec != BQA_C128) return set_error("unknown precision code %d", prec);
+  return launch_sweep_sync(prec, rank, world, peer_resid, it, peer_flags, seq, status, (cudaStream_t)stream);
 }
 
 int bqa_b200_canonicalize(int prec, int D, long long L, const void* ext, void* canon, void* lmbds, void* colmax,

@@ -184,7 +184,7 @@ BQA_HD void zz_factors(R theta, cx<R>& f0, cx<R>& f1) {
 // alpha * old + (1 - alpha) * new (or the undamped new) into dst (backends.py:761-764).
 template <typename R, typename G>
 BQA_HDN void emit_bp_msg(G g, int D, const cx<R>* g0, const cx<R>* g1, const cx<R>* old, cx<R>* dst, R damping,
-                         int write_undamped, R& mnum, R& mden) {
+                         int write_undamped, R& mnum, R& mden, cx<R>* dst2 = nullptr) {
   cx<R> tr = mk<R>(0, 0);
   for (int x = 0; x < D; ++x) tr = tr + g0[x * D + x] + g1[x * D + x];
   const cx<R> itr = cinv(tr);
@@ -194,14 +194,16 @@ BQA_HDN void emit_bp_msg(G g, int D, const cx<R>* g0, const cx<R>* g1, const cx<
     const R a = norm2(nw - od), b = norm2(nw + od);
     mnum = a > mnum ? a : mnum;
     mden = b > mden ? b : mden;
-    dst[o] = write_undamped ? nw : (damping * od + (R(1) - damping) * nw);
+    const cx<R> w = write_undamped ? nw : (damping * od + (R(1) - damping) * nw);
+    dst[o] = w;
+    if (dst2) dst2[o] = w;                                // halo slot of the peer that owns the receiving node
   }
 }
 
 // ZZ-extended message (2D x 2D) from the Gram parts:
 //   ext[(s,x),(s',y)] = conj(f_s) f_s' (g0[x,y] + (-1)^{s+s'} g1[x,y]) / trace      (state.py:127-139)
 template <typename R, typename G>
-BQA_HDN void emit_ext_msg(G g, int D, const cx<R>* g0, const cx<R>* g1, R theta, cx<R>* dst) {
+BQA_HDN void emit_ext_msg(G g, int D, const cx<R>* g0, const cx<R>* g1, R theta, cx<R>* dst, cx<R>* dst2 = nullptr) {
   const int n = 2 * D;
   cx<R> f[2];
   zz_factors<R>(theta, f[0], f[1]);
@@ -213,7 +215,9 @@ BQA_HDN void emit_ext_msg(G g, int D, const cx<R>* g0, const cx<R>* g1, R theta,
     const int s = r / D, x = r - s * D, sp = c / D, y = c - sp * D;
     const cx<R> a0 = g0[x * D + y], a1 = g1[x * D + y];
     const cx<R> v = (s == sp) ? (a0 + a1) : (a0 - a1);
-    dst[o] = itr * (conj(f[s]) * f[sp] * v);
+    const cx<R> w = itr * (conj(f[s]) * f[sp] * v);
+    dst[o] = w;
+    if (dst2) dst2[o] = w;
   }
 }
 

@@ -53,6 +53,9 @@ struct Args {
   int write_undamped, it;
   float* resid;
   int32_t* status;
+  // multi-GPU over peer memory (see NodeArgs in bqa_generic.cuh)
+  const int32_t* remote_pos;
+  unsigned char* peers[BQA_MAX_PEERS];
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -134,6 +137,16 @@ __device__ __forceinline__ int load_idx(const Args& a, long long node0, int lane
   return v;
 }
 
+// lanes 0..11 hold remote_pos[j][node0 + s] (index j * 4 + s); -1 everywhere on one GPU
+__device__ __forceinline__ int load_rpos(const Args& a, long long node0, int lane) {
+  int v = -1;
+  if (a.remote_pos != nullptr && lane < 12) {
+    long long node = node0 + (lane & 3);
+    if (node < a.B) v = __ldg(a.remote_pos + (size_t)(lane >> 2) * a.B + node);
+  }
+  return v;
+}
+
 template <bool EXT>
 __global__ void __launch_bounds__(kThreads, 1) k_msgs_d3D4(Args a) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -167,22 +180,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_msgs_d3D4(Args a) {
     sgnA = x > ya ? -1.f : 1.f;
     sgnB = x > yb ? -1.f : 1.f;
   }
-  int idx_cur = 0, idx_nxt = 0;
+  int idx_cur = 0, idx_nxt = 0, rp_cur = -1, rp_nxt = -1;
   if (g < groups) {
     idx_cur = load_idx(a, g * 4, lane);
+    rp_cur = load_rpos(a, g * 4, lane);
     issue_group<EXT>(a, wbase, g * 4, lane, idx_cur);
     cp_async_commit();
-    if (g + nwarps < groups) idx_nxt = load_idx(a, (g + nwarps) * 4, lane);
+    if (g + nwarps < groups) { idx_nxt = load_idx(a, (g + nwarps) * 4, lane); rp_nxt = load_rpos(a, (g + nwarps) * 4, lane); }
   }
   int cur = 0;
 #pragma unroll 1
   for (; g < groups; g += nwarps, cur ^= 1) {
     unsigned char* st = wbase + cur * kStage;
     const bool has_next = g + nwarps < groups;
-    int idx_nn = 0;
+    int idx_nn = 0, rp_nn = -1;
     if (has_next) {
       issue_group<EXT>(a, wbase + (cur ^ 1) * kStage, (g + nwarps) * 4, lane, idx_nxt);
-      if (g + 2 * nwarps < groups) idx_nn = load_idx(a, (g + 2 * nwarps) * 4, lane);
+      if (g + 2 * nwarps < groups) { idx_nn = load_idx(a, (g + 2 * nwarps) * 4, lane); rp_nn = load_rpos(a, (g + 2 * nwarps) * 4, lane); }
     }
     cp_async_commit();                                      // always commit (possibly empty): one loop body, one wait
     cp_async_wait<1>();
@@ -328,6 +342,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_msgs_d3D4(Args a) {
         tr.y += __shfl_xor_sync(0xffffffffu, tr.y, o);
       }
       const int slot = __shfl_sync(0xffffffffu, idx_cur, 12 + k * 4 + s);
+      const int rp = __shfl_sync(0xffffffffu, rp_cur, k * 4 + s);
+      unsigned char* far = rp < 0 ? nullptr : a.peers[rp >> 27] + (size_t)(rp & ((1 << 27) - 1)) * (EXT ? 512 : 128);
       if (!EXT) {
         const float d = 1.f / (tr.x * tr.x + tr.y * tr.y);
         const float2 itr = make_float2(tr.x * d, -tr.y * d);
@@ -348,6 +364,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_msgs_d3D4(Args a) {
             w = make_float4(al * ov.x + be * na.x, al * ov.y + be * na.y, al * ov.z + be * nb.x, al * ov.w + be * nb.y);
           }
           *reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(a.msgs_out) + (size_t)slot * 128 + t * 16) = w;
+          if (far) *reinterpret_cast<float4*>(far + t * 16) = w;      // halo slot on the peer that owns the receiver
         }
       } else {
         // ext[(s1,x),(s2,y)] = conj(f_s1) f_s2 (g0 + (-1)^(s1+s2) g1)[x][y] / ((|f0|^2 + |f1|^2) trace)
@@ -367,13 +384,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_msgs_d3D4(Args a) {
             for (int s2 = 0; s2 < 2; ++s2) {
               const float2 cf = cmul(itr, cmul(make_float2(ff[s1].x, -ff[s1].y), ff[s2]));
               const float2 va = cmul(cf, s1 == s2 ? sa : da), vb = cmul(cf, s1 == s2 ? sb : db);
-              *reinterpret_cast<float4*>(dst + ((s1 * 4 + x) * 8 + s2 * 4 + y0) * 8) = make_float4(va.x, va.y, vb.x, vb.y);
+              const float4 w4 = make_float4(va.x, va.y, vb.x, vb.y);
+              *reinterpret_cast<float4*>(dst + ((s1 * 4 + x) * 8 + s2 * 4 + y0) * 8) = w4;
+              if (far) *reinterpret_cast<float4*>(far + ((s1 * 4 + x) * 8 + s2 * 4 + y0) * 8) = w4;
             }
         }
       }
     }
     idx_cur = idx_nxt;
     idx_nxt = idx_nn;
+    rp_cur = rp_nxt;
+    rp_nxt = rp_nn;
     __syncwarp();                                           // stage `cur` may be overwritten by the next issue
   }
   if (!EXT) {
@@ -407,7 +428,7 @@ bool fast_d3D4_available(int prec, int degree, int D) { return prec == 0 && degr
 int launch_fast_msgs_d3D4(bool ext, long long B, const void* T, const void* msgs_cur, void* msgs_out,
                           const int32_t* in_pos, const int32_t* out_pos, const void* edge_ampls, double ztime,
                           double damping, int write_undamped, double bp_eps, int it, void* resid, int32_t* status,
-                          cudaStream_t st) {
+                          const int32_t* remote_pos, void* const* peers, cudaStream_t st) {
   using namespace fast;
   if (B == 0) return 0;
   static bool configured = false;
@@ -423,6 +444,8 @@ int launch_fast_msgs_d3D4(bool ext, long long B, const void* T, const void* msgs
   a.in_pos = in_pos; a.out_pos = out_pos; a.edge_ampls = (const float*)edge_ampls;
   a.ztime = (float)ztime; a.damping = (float)damping; a.bp_eps = (float)bp_eps;
   a.write_undamped = write_undamped; a.it = it; a.resid = (float*)resid; a.status = status;
+  a.remote_pos = peers ? remote_pos : nullptr;
+  for (int q = 0; q < BQA_MAX_PEERS; ++q) a.peers[q] = peers ? (unsigned char*)peers[q] : nullptr;
   const long long groups = (B + 3) / 4;
   long long grid = (groups + kWarps - 1) / kWarps;
   if (grid > sm_count()) grid = sm_count();

@@ -60,6 +60,10 @@ struct NodeArgs {
   int32_t* status;
   cx<R>* ws;
   size_t ws_per_warp;       // elements
+  // multi-GPU over peer memory: remote_pos (d, B), -1 or (peer << 27 | slot in that peer's array); peers[q] = base
+  // of rank q's destination array mapped into this process
+  const int32_t* remote_pos;
+  unsigned char* peers[BQA_MAX_PEERS];
 };
 
 // ---- BP sweep / extended messages ---------------------------------------------------------------
@@ -84,11 +88,14 @@ __global__ void __launch_bounds__(128) k_node_msgs(NodeArgs<R> a) {
       const cx<R>* g0 = gram + (size_t)k * 2 * DD;
       const cx<R>* g1 = g0 + DD;
       const size_t slot = (size_t)a.out_pos[(size_t)k * a.B + node];
+      const int rp = a.remote_pos ? a.remote_pos[(size_t)k * a.B + node] : -1;
+      cx<R>* far = rp < 0 ? nullptr
+                          : reinterpret_cast<cx<R>*>(a.peers[rp >> 27]) + (size_t)(rp & ((1 << 27) - 1)) * (EXT ? 4 * DD : DD);
       if (!EXT)
         emit_bp_msg<R>(g, D, g0, g1, a.msgs_cur + slot * DD, a.msgs_out + slot * DD, a.damping, a.write_undamped,
-                       mnum, mden);
+                       mnum, mden, far);
       else
-        emit_ext_msg<R>(g, D, g0, g1, a.edge_ampls[(size_t)k * a.B + node] * a.ztime, a.msgs_out + slot * 4 * DD);
+        emit_ext_msg<R>(g, D, g0, g1, a.edge_ampls[(size_t)k * a.B + node] * a.ztime, a.msgs_out + slot * 4 * DD, far);
     }
     g.sync();
   }
@@ -268,7 +275,7 @@ template <typename R>
 int launch_node_msgs(bool ext, int d, int D, long long B, const void* T, const void* msgs_cur, void* msgs_out,
                      const int32_t* in_pos, const int32_t* out_pos, const void* edge_ampls, double ztime,
                      double damping, int write_undamped, double bp_eps, int it, void* resid, int32_t* status,
-                     void* ws, size_t ws_bytes, cudaStream_t st) {
+                     void* ws, size_t ws_bytes, const int32_t* remote_pos, void* const* peers, cudaStream_t st) {
   if (B == 0) return 0;
   if (int rc = check_ws<R>(d, D, D, ws_bytes)) return rc;
   NodeArgs<R> a{};
@@ -278,6 +285,8 @@ int launch_node_msgs(bool ext, int d, int D, long long B, const void* T, const v
   a.ztime = (R)ztime; a.damping = (R)damping; a.write_undamped = write_undamped; a.bp_eps = (R)bp_eps;
   a.it = it; a.resid = (R*)resid; a.status = status;
   a.ws = (cx<R>*)ws; a.ws_per_warp = generic_ws_elems_per_warp(d, D, D);
+  a.remote_pos = peers ? remote_pos : nullptr;
+  for (int q = 0; q < BQA_MAX_PEERS; ++q) a.peers[q] = peers ? (unsigned char*)peers[q] : nullptr;
   const int grid = node_grid(B, 4);
   if (ext) k_node_msgs<R, true><<<grid, 128, 0, st>>>(a);
   else k_node_msgs<R, false><<<grid, 128, 0, st>>>(a);
@@ -370,7 +379,7 @@ int launch_threshold(int d, int D, long long B, void* T, const int32_t* node_ids
 #define BQA_INSTANTIATE(R)                                                                                         \
   template int launch_node_msgs<R>(bool, int, int, long long, const void*, const void*, void*, const int32_t*,     \
                                    const int32_t*, const void*, double, double, int, double, int, void*, int32_t*, \
-                                   void*, size_t, cudaStream_t);                                                   \
+                                   void*, size_t, const int32_t*, void* const*, cudaStream_t);                                                   \
   template int launch_canonicalize<R>(int, long long, const void*, void*, void*, void*, double, cudaStream_t);     \
   template int launch_apply_update<R>(int, int, int, long long, const void*, void*, const void*, const void*,      \
                                       void*, const int32_t*, const int32_t*, const int32_t*, const void*,          \

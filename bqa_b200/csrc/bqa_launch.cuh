@@ -7,6 +7,7 @@
 #include <cstdint>
 
 #define BQA_GENERIC_MAX_WARPS (148 * 32)
+#define BQA_MAX_PEERS 8
 
 namespace bqa {
 
@@ -27,7 +28,7 @@ template <typename R>
 int launch_node_msgs(bool ext, int d, int D, long long B, const void* T, const void* msgs_cur, void* msgs_out,
                      const int32_t* in_pos, const int32_t* out_pos, const void* edge_ampls, double ztime,
                      double damping, int write_undamped, double bp_eps, int it, void* resid, int32_t* status,
-                     void* ws, size_t ws_bytes, cudaStream_t st);
+                     void* ws, size_t ws_bytes, const int32_t* remote_pos, void* const* peers, cudaStream_t st);
 template <typename R>
 int launch_canonicalize(int D, long long L, const void* ext, void* canon, void* lmbds, void* colmax,
                         double pinv_eps, cudaStream_t st);
@@ -53,7 +54,13 @@ bool fast_d3D4_available(int prec, int degree, int D);
 int launch_fast_msgs_d3D4(bool ext, long long B, const void* T, const void* msgs_cur, void* msgs_out,
                           const int32_t* in_pos, const int32_t* out_pos, const void* edge_ampls, double ztime,
                           double damping, int write_undamped, double bp_eps, int it, void* resid, int32_t* status,
-                          cudaStream_t st);
+                          const int32_t* remote_pos, void* const* peers, cudaStream_t st);
+// symmetric-gauge messages of every slot, msgs[p] = diag(lambda[p mod L][:Dn]) / trace      (state.py:56-57)
+template <typename R>
+int launch_gauge_msgs(int D_old, int Dn, long long L, const void* lmbds, void* msgs_out, cudaStream_t st);
+// cross-GPU sweep epilogue over peer memory: residual max to every peer + barrier (bqa_sync.cu)
+int launch_sweep_sync(int prec, int rank, int world, void* const* peer_resid, int it, void* const* peer_flags,
+                      unsigned seq, int32_t* status, cudaStream_t st);
 
 // specialised canonicalizer kernel (bqa_fast_canon8.cu): D = 4 (n = 8), complex64
 int launch_fast_canon8(long long L, const void* ext, void* canon, void* lmbds, void* colmax, double pinv_eps,

@@ -1,0 +1,107 @@
+// bqa_sync.cu -- the two small kernels of the peer-memory (NVLink P2P) multi-GPU path.
+//
+//   k_gauge_msgs  : msgs[p] = diag(lambda[p mod L][:Dn]) / trace for EVERY slot (reference state.py:56-57).  On one
+//                   GPU the apply-update kernel writes these per node; a partitioned rank also needs the halo
+//                   slots, whose lambdas it holds (cut edges are canonicalised on both owners), so it fills all
+//                   slots locally instead of exchanging them.
+//   k_sweep_sync  : after a BP sweep whose kernels stored the boundary messages straight into the peers' halo
+//                   slots: push this rank's residual maxima to every peer (system-scope atomic max over NVLink:
+//                   get_dist is a ratio of two GLOBAL maxima, backends.py:492-495) and run a flag barrier, so the
+//                   next sweep starts only when every peer's stores and maxima have landed.  it < 0: barrier only.
+#include <cuda_runtime.h>
+
+#include "bqa_core.cuh"
+#include "bqa_launch.cuh"
+
+namespace bqa {
+
+template <typename R>
+__global__ void __launch_bounds__(256) k_gauge_msgs(int stride, int Dn, long long n_slots, long long L, const R* lmbds,
+                                                    cx<R>* msgs) {
+  const int DD = Dn * Dn;
+  const long long total = n_slots * DD;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / DD;
+    const int o = (int)(i - p * DD), r = o / Dn, c = o - r * Dn;
+    const R* lam = lmbds + (size_t)(p % L) * stride;
+    R v = 0;
+    if (r == c) {
+      R tr = 0;
+      for (int k = 0; k < Dn; ++k) tr += lam[k];
+      v = lam[c] / tr;
+    }
+    msgs[i] = mk<R>(v, R(0));
+  }
+}
+
+template <typename R>
+int launch_gauge_msgs(int D_old, int Dn, long long L, const void* lmbds, void* msgs_out, cudaStream_t st) {
+  if (L == 0) return 0;
+  const long long total = 2 * L * Dn * Dn;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_gauge_msgs<R><<<(int)blocks, 256, 0, st>>>(2 * D_old, Dn, 2 * L, L, (const R*)lmbds, (cx<R>*)msgs_out);
+  return after_launch("gauge_msgs");
+}
+template int launch_gauge_msgs<float>(int, int, long long, const void*, void*, cudaStream_t);
+template int launch_gauge_msgs<double>(int, int, long long, const void*, void*, cudaStream_t);
+
+struct SyncArgs {
+  int rank, world, it, dbl;
+  unsigned seq;
+  void* resid[BQA_MAX_PEERS];              // base of every rank's residual array (peer mapped)
+  unsigned* flags[BQA_MAX_PEERS];          // every rank's flag array: flags[q][src] is written by rank src
+  int32_t* status;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(32) k_sweep_sync(SyncArgs a) {
+  const int q = threadIdx.x;
+  if (q < a.world && q != a.rank) {
+    if (a.it >= 0) {                                        // non-negative reals order like their bit patterns
+      if (a.dbl) {
+        const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(a.resid[a.rank]) + 2 * a.it;
+        unsigned long long* theirs = reinterpret_cast<unsigned long long*>(a.resid[q]) + 2 * a.it;
+        atomicMax_system(theirs, mine[0]);
+        atomicMax_system(theirs + 1, mine[1]);
+      } else {
+        const unsigned* mine = reinterpret_cast<const unsigned*>(a.resid[a.rank]) + 2 * a.it;
+        unsigned* theirs = reinterpret_cast<unsigned*>(a.resid[q]) + 2 * a.it;
+        atomicMax_system(theirs, mine[0]);
+        atomicMax_system(theirs + 1, mine[1]);
+      }
+    }
+    __threadfence_system();
+    st_release_sys(a.flags[q] + a.rank, a.seq);             // "rank has finished sweep seq" on peer q
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_sys(a.flags[a.rank] + q) - a.seq) < 0) {
+      if (clock64() - t0 > 20000000000LL) {                 // ~10 s: a peer died; flag the error instead of hanging
+        a.status[3] = 1;
+        break;
+      }
+    }
+  }
+}
+
+int launch_sweep_sync(int prec, int rank, int world, void* const* peer_resid, int it, void* const* peer_flags,
+                      unsigned seq, int32_t* status, cudaStream_t st) {
+  if (world < 1 || world > BQA_MAX_PEERS || rank < 0 || rank >= world)
+    return set_error("sweep_sync: rank %d / world %d outside [1, %d]", rank, world, BQA_MAX_PEERS);
+  if (world == 1) return 0;
+  SyncArgs a{};
+  a.rank = rank; a.world = world; a.it = it; a.dbl = prec == 1; a.seq = seq; a.status = status;
+  for (int q = 0; q < world; ++q) { a.resid[q] = peer_resid ? peer_resid[q] : nullptr; a.flags[q] = (unsigned*)peer_flags[q]; }
+  if (it >= 0 && !peer_resid) return set_error("sweep_sync: residual arrays missing");
+  k_sweep_sync<<<1, 32, 0, st>>>(a);
+  return after_launch("sweep_sync");
+}
+
+}  // namespace bqa

@@ -57,6 +57,7 @@ class _DegreeClass:
     in_pos: torch.Tensor
     out_pos: torch.Tensor
     lmbd_pos: torch.Tensor
+    remote_pos: torch.Tensor     # peer-memory path only: (peer << 27 | slot on that peer) or -1, like out_pos
     node_ampls: torch.Tensor
     edge_ampls: torch.Tensor
     T: list            # two flat complex buffers (ping-pong across bond-dimension changes)
@@ -125,11 +126,13 @@ class Engine:
                 node_ids=torch.from_numpy(ids.astype(np.int32)).to(self.dev),
                 in_pos=i32(lay.input_msgs_position), out_pos=i32(lay.output_msgs_position),
                 lmbd_pos=i32(lay.lmbds_position),
+                remote_pos=i32(getattr(lay, "remote_msgs_position", None)) if getattr(lay, "remote_msgs_position", None) is not None
+                else torch.full((max(degree, 1), B), -1, dtype=torch.int32, device=self.dev),
                 node_ampls=real(lay.node_ampls, (B,)), edge_ampls=real(lay.edge_ampls, (degree, B)),
                 T=[torch.zeros(elems, dtype=self.cdtype, device=self.dev) for _ in range(2)],
                 node_ids_host=ids))
         Dm = self.Dmax
-        self._msgs = [torch.zeros(self.E2 * Dm * Dm, dtype=self.cdtype, device=self.dev) for _ in range(2)]
+        self._msgs = [self._alloc_shared(self.E2 * Dm * Dm, self.cdtype, f"msgs{i}") for i in range(2)]
         self._msgs_cur = 0
         self._ext = None         # allocated on first simple update (size depends on the largest D reached)
         self._canon = None
@@ -138,7 +141,7 @@ class Engine:
         self._colmax = torch.zeros(2 * Dm, dtype=self.rdtype, device=self.dev)
         # BP control block, read back with one copy per chunk of sweeps: [resid (max_iters, 2) reals | status int32 x4]
         rbytes = ((max(self.max_iters, 1) * 2 * (4 if self.precision == "single" else 8)) + 15) // 16 * 16
-        self._ctrl = torch.zeros(rbytes + 16, dtype=torch.uint8, device=self.dev)
+        self._ctrl = self._alloc_shared(rbytes + 16, torch.uint8, "ctrl")
         self._ctrl_rbytes = rbytes
         self._resid = self._ctrl[:rbytes].view(self.rdtype)
         self._status = self._ctrl[rbytes:].view(torch.int32)
@@ -163,10 +166,16 @@ class Engine:
         if self._ws.numel() < need:
             self._ws = torch.zeros(need, dtype=torch.uint8, device=self.dev)
 
+    def _alloc_shared(self, numel: int, dtype, tag: str) -> torch.Tensor:
+        """Buffers other GPUs write into on the peer-memory path (messages, extended messages, BP control
+        block); plain device memory here, symmetric memory in PartitionedEngine."""
+        return torch.zeros(numel, dtype=dtype, device=self.dev)
+
     def _ensure_edge_buffers(self, D: int) -> None:
         need = self.E2 * 4 * D * D
         if self._ext is None or self._ext.numel() < need:
-            self._ext = torch.zeros(need, dtype=self.cdtype, device=self.dev)
+            self._ext = self._alloc_shared(need, self.cdtype, "ext")
+        if self._canon is None or self._canon.numel() < need:
             self._canon = torch.zeros(need, dtype=self.cdtype, device=self.dev)
 
     @property
@@ -261,23 +270,37 @@ class Engine:
         cur = self._msgs[(self._msgs_cur + it) % 2]
         nxt = self._msgs[(self._msgs_cur + it + 1) % 2]
         st = self._stream()
+        peers = self._peer_targets("msgs", (self._msgs_cur + it + 1) % 2)
         for c in self.classes:
             if c.degree == 0:
                 continue
-            self.lib.bp_sweep(self.prec, c.degree, D, c.B, c.T[c.cur].data_ptr(), cur.data_ptr(), nxt.data_ptr(),
-                              c.in_pos.data_ptr(), c.out_pos.data_ptr(), self.damping, int(write_undamped),
-                              self.bp_eps, it, self._resid.data_ptr(), self._status.data_ptr(),
-                              self._ws.data_ptr(), self._ws.numel(), st)
+            args = (self.prec, c.degree, D, c.B, c.T[c.cur].data_ptr(), cur.data_ptr(), nxt.data_ptr(),
+                    c.in_pos.data_ptr(), c.out_pos.data_ptr(), self.damping, int(write_undamped),
+                    self.bp_eps, it, self._resid.data_ptr(), self._status.data_ptr(),
+                    self._ws.data_ptr(), self._ws.numel())
+            if peers is None:
+                self.lib.bp_sweep(*args, st)
+            else:
+                self.lib.bp_sweep_p2p(*args, c.remote_pos.data_ptr(), peers, st)
         self._after_sweep(it, nxt)
 
     def _after_sweep(self, it: int, nxt: torch.Tensor) -> None:
         """Hook for the partitioned engine: halo exchange + residual all-reduce (no-op on one GPU)."""
+
+    def _peer_targets(self, what: str, parity: int = 0):
+        """Peer-memory path of the partitioned engine: host array of the peers' base pointers of the array the
+        kernel is about to write (``None`` = everything stays on this GPU)."""
+        return None
+
+    def _before_bp(self) -> None:
+        """Hook for the partitioned engine (orders the control-block reset against the peers' residual pushes)."""
 
     def run_bp(self) -> int:
         max_it = self.max_iters
         assert max_it > 0, "max_bp_iter_number must be positive"      # reference: assert best_msgs is not None
         self._ensure_ws(self.D, self.D)
         self._ctrl.zero_()
+        self._before_bp()
         eps = self.np_rdtype(self.bp_eps)
         it = 0
         done = False
@@ -290,6 +313,8 @@ class Engine:
             ctrl = self._to_host(self._ctrl)                 # one D2H + sync per chunk of sweeps
             resid = ctrl[: self._ctrl_rbytes].view(self.np_rdtype).reshape(-1, 2)
             status = ctrl[self._ctrl_rbytes:].view(np.int32)
+            if status[3]:
+                raise RuntimeError("a peer GPU never reached the sweep barrier (bqa_b200_sweep_sync timed out)")
             if status[0]:                                    # a later sweep saw convergence on the device
                 done, sweeps = True, int(status[1])
             else:                                            # the last enqueued sweep is tested here
@@ -326,12 +351,17 @@ class Engine:
         self._ensure_ws(D, min(2 * D, self.Dmax))
         self._ensure_edge_buffers(D)
         cur = self.msgs_buffer
+        peers = self._peer_targets("ext")
         for c in self.classes:
             if c.degree == 0:
                 continue
-            self.lib.ext_msgs(self.prec, c.degree, D, c.B, c.T[c.cur].data_ptr(), cur.data_ptr(),
-                              self._ext.data_ptr(), c.in_pos.data_ptr(), c.out_pos.data_ptr(),
-                              c.edge_ampls.data_ptr(), float(ztime), self._ws.data_ptr(), self._ws.numel(), st)
+            args = (self.prec, c.degree, D, c.B, c.T[c.cur].data_ptr(), cur.data_ptr(),
+                    self._ext.data_ptr(), c.in_pos.data_ptr(), c.out_pos.data_ptr(),
+                    c.edge_ampls.data_ptr(), float(ztime), self._ws.data_ptr(), self._ws.numel())
+            if peers is None:
+                self.lib.ext_msgs(*args, st)
+            else:
+                self.lib.ext_msgs_p2p(*args, c.remote_pos.data_ptr(), peers, st)
         self._exchange_ext()
         self._colmax.zero_()
         self.lib.canonicalize(self.prec, D, self.L, self._ext.data_ptr(), self._canon.data_ptr(),

@@ -19,7 +19,9 @@ Collectives go through torch.distributed (NCCL over NVLink on GPUs; gloo in the 
 """
 from __future__ import annotations
 
+import ctypes as C
 import logging
+import os
 from dataclasses import dataclass, replace
 
 import numpy as np
@@ -202,6 +204,7 @@ class ExchangePlan:
     recv_slots: dict                  # peer -> local halo slots filled by that peer (same global-position order)
     n_local_edges: int
     n_cut_edges: int
+    max_local_edges: int = 0          # over all ranks (symmetric buffers are sized for it)
 
 
 def build_local_context(ctx: Context, part: np.ndarray, rank: int, world: int):
@@ -219,6 +222,28 @@ def build_local_context(ctx: Context, part: np.ndarray, rank: int, world: int):
         pos = np.asarray(pos, np.int64)
         return g2l[pos % L] + (pos // L) * Lr
 
+    # slot numbering of every rank (for the peer-memory path: a boundary message is stored straight into the
+    # halo slot of the rank that owns its receiver)
+    g2l_all, L_all = [], []
+    for q in range(world):
+        mq = (pl == q) | (pr == q)
+        gq = np.full(L, -1, np.int64)
+        gq[mq] = np.arange(int(mq.sum()))
+        g2l_all.append(gq)
+        L_all.append(int(mq.sum()))
+
+    def remote(pos):                                         # global position of an outgoing message -> remote code
+        pos = np.asarray(pos, np.int64)
+        e, back = pos % L, pos // L
+        recv_owner = np.where(back == 0, pr[e], pl[e])       # forward = lhs -> rhs, backward = rhs -> lhs
+        code = np.full(pos.shape, -1, np.int64)
+        for q in range(world):
+            if q == rank:
+                continue
+            m = recv_owner == q
+            code[m] = (q << 27) | (g2l_all[q][e[m]] + back[m] * L_all[q])
+        return code
+
     owned = np.flatnonzero(part == rank)
     gid2lid = np.full(part.shape[0], -1, np.int64)
     gid2lid[owned] = np.arange(owned.size)
@@ -235,7 +260,8 @@ def build_local_context(ctx: Context, part: np.ndarray, rank: int, world: int):
             input_msgs_position=slot(sel(lay.input_msgs_position)),
             output_msgs_position=slot(sel(lay.output_msgs_position)),
             lmbds_position=g2l[np.asarray(sel(lay.lmbds_position), np.int64)],
-            node_ampls=np.real(_np(lay.node_ampls))[m], edge_ampls=np.real(sel(lay.edge_ampls)))
+            node_ampls=np.real(_np(lay.node_ampls))[m], edge_ampls=np.real(sel(lay.edge_ampls)),
+            remote_msgs_position=remote(sel(lay.output_msgs_position)))
     # boundary messages: forward position e is lhs -> rhs, backward position e + L is rhs -> lhs
     cut = np.flatnonzero(local_edge & (pl != pr))
     send, recv = {}, {}
@@ -246,7 +272,8 @@ def build_local_context(ctx: Context, part: np.ndarray, rank: int, world: int):
             peer, s_pos, r_pos = int(pl[e]), e + L, e
         send.setdefault(peer, []).append(s_pos)
         recv.setdefault(peer, []).append(r_pos)
-    plan = ExchangePlan(rank=rank, world=world, owned=owned,
+    assert max(L_all) < (1 << 26), "too many local edges for the 27-bit remote slot code"
+    plan = ExchangePlan(rank=rank, world=world, owned=owned, max_local_edges=max(L_all),
                         send_slots={q: slot(np.sort(np.array(v))) for q, v in send.items()},
                         recv_slots={q: slot(np.sort(np.array(v))) for q, v in recv.items()},
                         n_local_edges=Lr, n_cut_edges=int(cut.size))
@@ -260,10 +287,18 @@ def build_local_context(ctx: Context, part: np.ndarray, rank: int, world: int):
 # engine
 # ---------------------------------------------------------------------------------------------------
 class PartitionedEngine(Engine):
-    """Same interface as Engine; ``bloch_vectors`` / ``measure`` return global results on every rank."""
+    """Same interface as Engine; ``bloch_vectors`` / ``measure`` return global results on every rank.
+
+    Two transports for the boundary messages:
+      * peer memory (default on CUDA + NCCL): message / extended-message / control buffers live in symmetric
+        memory, the sweep kernels store boundary messages straight into the owner's halo slots over NVLink and
+        ``bqa_b200_sweep_sync`` pushes the residual maxima and runs the barrier -- two kernel launches per sweep,
+        no pack / unpack, no collective call in the sweep loop;
+      * ``torch.distributed`` P2P ops + all-reduce (``p2p=False``; the only transport under gloo / in the CPU tests).
+    """
 
     def __init__(self, context, precision=None, device=None, group=None, part=None, partition_seed: int = 0,
-                 _testing_lib=None):
+                 p2p: bool | None = None, _testing_lib=None):
         if not dist.is_initialized():
             raise RuntimeError("PartitionedEngine needs an initialised torch.distributed process group")
         self.group = group
@@ -276,6 +311,12 @@ class PartitionedEngine(Engine):
             partition_nodes(self.N_global, E, self.world, seed=partition_seed)
         local, plan = build_local_context(context, self.part, self.rank, self.world)
         self.plan = plan
+        if p2p is None:
+            p2p = (_testing_lib is None and dist.get_backend(group) == "nccl" and self.world <= 8
+                   and os.environ.get("BQA_B200_P2P", "1") != "0")
+        self.p2p = bool(p2p) and self.world > 1
+        self._symm = {}                                       # tag -> (tensor, handle)
+        self._seq = 0
         super().__init__(local, precision=precision, device=device, _testing_lib=_testing_lib)
         self.rng = np.random.default_rng(int(context.seed))              # same stream on every rank
         dev = self.dev
@@ -284,8 +325,46 @@ class PartitionedEngine(Engine):
         self._recv_idx = {q: torch.from_numpy(plan.recv_slots[q]).to(dev) for q in self._peers}
         self._owned_dev = torch.from_numpy(plan.owned).to(dev)
         self.comm_bytes = 0
+        if self.p2p:
+            self._ensure_edge_buffers(self.Dmax)              # symmetric allocations are collective: do them all now
+            self._flags = self._alloc_shared(64, torch.uint8, "flags")
+            ptrs = lambda tag: (C.c_void_p * 8)(*([int(x) for x in self._symm[tag][1].buffer_ptrs] + [0] * (8 - self.world)))
+            self._peer_ptrs = {("msgs", 0): ptrs("msgs0"), ("msgs", 1): ptrs("msgs1"), ("ext", 0): ptrs("ext"),
+                               "ctrl": ptrs("ctrl"), "flags": ptrs("flags")}
+            dist.barrier(group=self.group)
         log.info(f"rank {self.rank}/{self.world}: {plan.owned.size} nodes, {plan.n_local_edges} local edges, "
-                 f"{plan.n_cut_edges} cut")
+                 f"{plan.n_cut_edges} cut, transport {'peer memory' if self.p2p else 'torch.distributed'}")
+
+    # -- symmetric memory ------------------------------------------------------------------------------
+    def _alloc_shared(self, numel: int, dtype, tag: str) -> torch.Tensor:
+        if not self.p2p:
+            return super()._alloc_shared(numel, dtype, tag)
+        import torch.distributed._symmetric_memory as symm_mem
+        esize = torch.empty(0, dtype=dtype).element_size()
+        if tag.startswith("msgs"):                            # same size on every rank: the largest local slot count
+            numel = 2 * self.plan.max_local_edges * self.Dmax * self.Dmax
+        elif tag == "ext":
+            numel = 2 * self.plan.max_local_edges * 4 * self.Dmax * self.Dmax
+        nbytes = (numel * esize + 511) // 512 * 512
+        raw = symm_mem.empty(nbytes, dtype=torch.uint8, device=self.dev)
+        raw.zero_()
+        pg = self.group if self.group is not None else dist.group.WORLD
+        handle = symm_mem.rendezvous(raw, pg)
+        self._symm[tag] = (raw, handle)
+        return raw[: numel * esize].view(dtype)
+
+    def _peer_targets(self, what: str, parity: int = 0):
+        return self._peer_ptrs[(what, parity)] if self.p2p else None
+
+    def _sync(self, it: int) -> None:
+        """Residual push (it >= 0) + barrier over peer memory: one tiny kernel."""
+        self._seq += 1
+        self.lib.sweep_sync(self.prec, self.rank, self.world, self._peer_ptrs["ctrl"], it, self._peer_ptrs["flags"],
+                            self._seq, self._status.data_ptr(), self._stream())
+
+    def _before_bp(self) -> None:
+        if self.p2p:
+            self._sync(-1)            # nobody pushes residuals of the new run before everybody has reset its block
 
     # -- boundary exchange of a (slots, elems) complex array held flat in `buf` ------------------------
     def _exchange(self, buf: torch.Tensor, elems: int) -> None:
@@ -311,17 +390,26 @@ class PartitionedEngine(Engine):
 
     # -- hooks of the single-GPU engine ------------------------------------------------------------------
     def _after_sweep(self, it: int, nxt: torch.Tensor) -> None:
+        if self.p2p:
+            self._sync(it)
+            return
         self._exchange(nxt, self.D * self.D)
         dist.all_reduce(self._resid[2 * it: 2 * it + 2], op=dist.ReduceOp.MAX, group=self.group)
 
     def _exchange_ext(self) -> None:
+        if self.p2p:
+            self._sync(-1)
+            return
         self._exchange(self._ext, 4 * self.D * self.D)
 
     def _reduce_colmax(self, colmax: torch.Tensor) -> None:
         dist.all_reduce(colmax, op=dist.ReduceOp.MAX, group=self.group)
 
     def _after_update(self) -> None:
-        self._exchange(self.msgs_buffer, self.D * self.D)
+        # halo slots of the re-initialised messages: lambdas of cut edges are held by both owners, so every slot is
+        # filled locally (state.py:56-57) instead of being exchanged
+        self.lib.gauge_msgs(self.prec, self._lmbd_stride // 2, self.D, self.L, self._lmbds.data_ptr(),
+                            self.msgs_buffer.data_ptr(), self._stream())
 
     # -- results ---------------------------------------------------------------------------------------
     def _gather_rows(self, local: torch.Tensor, width: int) -> torch.Tensor:

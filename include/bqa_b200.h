@@ -65,6 +65,32 @@ int bqa_b200_bp_sweep(int prec, int degree, int D, long long B, const void* T, c
                       int write_undamped, double bp_eps, int it, void* resid, int32_t* status,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- multi-GPU over peer memory (NVLink P2P) -----------------------------------------------------
+ * The reference is single-process; these entry points are the B200 scaling path.
+ * remote_pos: int32 (d, B) like out_pos; -1 = the message stays local, otherwise (peer << 27 | slot) = where the
+ * owner of the receiving node keeps it.  peers: HOST array of BQA_B200_MAX_PEERS device pointers, peers[q] = base
+ * of rank q's destination array (msgs_nxt of the same sweep parity / ext) mapped into this process.  The kernel
+ * stores such a message twice: locally at out_pos and into the peer's halo slot.  Both NULL = one GPU. */
+#define BQA_B200_MAX_PEERS 8
+int bqa_b200_bp_sweep_p2p(int prec, int degree, int D, long long B, const void* T, const void* msgs_cur,
+                          void* msgs_nxt, const int32_t* in_pos, const int32_t* out_pos, double damping,
+                          int write_undamped, double bp_eps, int it, void* resid, int32_t* status,
+                          void* workspace, size_t workspace_bytes, const int32_t* remote_pos, void* const* peers,
+                          void* stream);
+int bqa_b200_ext_msgs_p2p(int prec, int degree, int D, long long B, const void* T, const void* msgs_cur,
+                          void* ext, const int32_t* in_pos, const int32_t* out_pos, const void* edge_ampls,
+                          double ztime, void* workspace, size_t workspace_bytes, const int32_t* remote_pos,
+                          void* const* peers, void* stream);
+/* after the sweep kernels of sweep `it`: atomic-max this rank's resid[it] pair into every peer's resid array
+ * (get_dist is a ratio of two GLOBAL maxima, backends.py:492-495) and wait on a flag barrier until every peer
+ * has done the same -- their boundary stores have then landed.  it < 0: barrier only.  peer_resid / peer_flags:
+ * HOST arrays of `world` device pointers (own arrays at index `rank`); flags: uint32[BQA_B200_MAX_PEERS] per rank,
+ * zero-initialised; seq: 1, 2, 3, ... per call.  A peer that never arrives sets status[3] after ~10 s. */
+int bqa_b200_sweep_sync(int prec, int rank, int world, void* const* peer_resid, int it, void* const* peer_flags,
+                        unsigned seq, int32_t* status, void* stream);
+/* msgs_out[p] = diag(lmbds[p mod L][:D_new]) / trace for every slot p < 2L (state.py:56-57); lmbds: real (L, 2 D_old) */
+int bqa_b200_gauge_msgs(int prec, int D_old, int D_new, long long L, const void* lmbds, void* msgs_out, void* stream);
+
 /* ---- K3a: ZZ-extended messages of a degree class -----------------------------------------------
  * replaces _get_extended_msgs (state.py:127-139): pass_msgs with evolution_times, i.e. the open leg is
  * extended D -> 2D by the ZZ half gate (backends.py:519-526) with theta = edge_ampl * ztime.

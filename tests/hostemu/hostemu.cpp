@@ -142,6 +142,13 @@ static void threshold(int d, int D, long long B, void* T_, const int32_t* node_i
   }
 }
 
+template <typename R>
+static void gauge_msgs(int Dold, int Dn, long long L, const void* lm_, void* msgs_) {
+  GroupSerial g;
+  for (long long p = 0; p < 2 * L; ++p)
+    emit_gauge_msg<R>(g, Dn, (const R*)lm_ + (size_t)(p % L) * 2 * Dold, (cx<R>*)msgs_ + (size_t)p * Dn * Dn);
+}
+
 #define DISPATCH(call_f, call_d) do { ++g_calls; if (prec == BQA_C64) { call_f; } else { call_d; } return 0; } while (0)
 
 extern "C" {
@@ -150,6 +157,15 @@ int bqa_b200_version(void) { return -1; }   // negative: host emulation
 long long bqa_b200_launch_count(void) { return g_calls; }
 int bqa_b200_set_kernel_mode(int) { return 0; }
 int bqa_b200_canon_stats(unsigned long long* o) { o[0] = o[1] = 0; return 0; }
+int bqa_b200_gauge_msgs(int prec, int D_old, int D_new, long long L, const void* lmbds, void* msgs_out, void*) {
+  DISPATCH(gauge_msgs<float>(D_old, D_new, L, lmbds, msgs_out), gauge_msgs<double>(D_old, D_new, L, lmbds, msgs_out));
+}
+static int no_p2p() { snprintf(g_err, sizeof(g_err), "peer-memory entry points need the CUDA build"); return 1; }
+int bqa_b200_bp_sweep_p2p(int, int, int, long long, const void*, const void*, void*, const int32_t*, const int32_t*, double,
+                          int, double, int, void*, int32_t*, void*, size_t, const int32_t*, void* const*, void*) { return no_p2p(); }
+int bqa_b200_ext_msgs_p2p(int, int, int, long long, const void*, const void*, void*, const int32_t*, const int32_t*,
+                          const void*, double, void*, size_t, const int32_t*, void* const*, void*) { return no_p2p(); }
+int bqa_b200_sweep_sync(int, int, int, void* const*, int, void* const*, unsigned, int32_t*, void*) { return no_p2p(); }
 size_t bqa_b200_workspace_bytes(int, int, int, int) { return 16; }
 
 int bqa_b200_bp_sweep(int prec, int degree, int D, long long B, const void* T, const void* msgs_cur, void* msgs_nxt,

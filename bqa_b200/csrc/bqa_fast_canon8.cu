@@ -52,51 +52,89 @@ __device__ __forceinline__ float rsqrt_nr(float x) {
   return y * (1.5f - 0.5f * x * y * y);
 }
 
-// Branch-free rotation of columns (P, Q): an inactive pair (converged, or a numerically-zero column) gets the
-// identity through selects, so the four pairs of a round stay independent straight-line code.
-template <int P, int Q>
-__device__ __forceinline__ void rotate(float2 (&A)[8], float2 (&V)[8], float (&w)[8], float gr, float gi, float nul,
-                                       float tol2, bool& rotated) {
-  const float al = w[P], be = w[Q];
+// Rotation parameters of one column pair, computed from the all-reduced inner product (gr, gi) and the column norms.
+// Branch-free: an inactive pair (converged, or a numerically-zero column) gets the identity through selects.
+struct Rot {
+  float c, s, phx, phy, dw;      // cos, sin, unimodular phase conj(g)/|g|, norm transfer t |g|
+};
+__device__ __forceinline__ Rot rot_params(float al, float be, float gr, float gi, float nul, float tol2) {
   const float g2 = gr * gr + gi * gi;
-  const bool act = !(al <= nul || be <= nul || g2 <= tol2 * al * be);          // uniform over the 8 lanes of an edge
-  rotated |= act;
+  const bool act = !(al <= nul || be <= nul || g2 <= tol2 * al * be);
   const float ig = rsqrt_nr(g2);                  // 1 / |g|   (inf / nan when inactive: discarded below)
   const float ag = g2 * ig;
   const float zeta = 0.5f * (be - al) * ig;
   const float z2 = 1.f + zeta * zeta;
   const float t0 = __fdividef(1.f, fabsf(zeta) + z2 * rsqrt_nr(z2));   // accuracy of t only affects how well g is zeroed
   const float t = act ? copysignf(t0, zeta) : 0.f;
-  const float c = rsqrt_nr(1.f + t * t), s = c * t;
-  const float2 ph = act ? make_float2(gr * ig, -gi * ig) : make_float2(1.f, 0.f);
-  float2 ap = A[P], aq = cmulf(ph, A[Q]);
-  A[P] = make_float2(c * ap.x - s * aq.x, c * ap.y - s * aq.y);
-  A[Q] = make_float2(s * ap.x + c * aq.x, s * ap.y + c * aq.y);
-  ap = V[P]; aq = cmulf(ph, V[Q]);
-  V[P] = make_float2(c * ap.x - s * aq.x, c * ap.y - s * aq.y);
-  V[Q] = make_float2(s * ap.x + c * aq.x, s * ap.y + c * aq.y);
-  const float dw = act ? t * ag : 0.f;
-  w[P] = al - dw;
-  w[Q] = be + dw;
+  Rot r;
+  r.c = rsqrt_nr(1.f + t * t);
+  r.s = r.c * t;
+  r.phx = act ? gr * ig : 1.f;
+  r.phy = act ? -gi * ig : 0.f;
+  r.dw = act ? t * ag : 0.f;
+  return r;
 }
 
+template <int P, int Q>
+__device__ __forceinline__ void apply_rot(float2 (&A)[8], float2 (&V)[8], float (&w)[8], const Rot& r) {
+  const float2 ph = make_float2(r.phx, r.phy);
+  float2 ap = A[P], aq = cmulf(ph, A[Q]);
+  A[P] = make_float2(r.c * ap.x - r.s * aq.x, r.c * ap.y - r.s * aq.y);
+  A[Q] = make_float2(r.s * ap.x + r.c * aq.x, r.s * ap.y + r.c * aq.y);
+  ap = V[P]; aq = cmulf(ph, V[Q]);
+  V[P] = make_float2(r.c * ap.x - r.s * aq.x, r.c * ap.y - r.s * aq.y);
+  V[Q] = make_float2(r.s * ap.x + r.c * aq.x, r.s * ap.y + r.c * aq.y);
+  w[P] -= r.dw;
+  w[Q] += r.dw;
+}
+
+// One round = four disjoint pairs (P0,Q0) .. (P3,Q3).  The 8 partial inner-product components (re, im of 4 pairs)
+// are reduce-scattered over the 8 lanes of the edge (7 shuffles; lane r ends up with component r), the two lanes
+// of pair k = r / 2 swap components and compute THAT pair's rotation only, and the four parameter sets are then
+// broadcast (5 shuffles each) -- instead of every lane all-reducing 8 values and deriving all four rotations.
 template <int P0, int Q0, int P1, int Q1, int P2, int Q2, int P3, int Q3>
 __device__ __forceinline__ void jacobi_round(float2 (&A)[8], float2 (&V)[8], float (&w)[8], float nul, float tol2,
-                                             bool& rotated) {
-  // conj(a_p) a_q of this lane's row for the four pairs, all-reduced over the 8 lanes
+                                             bool& rotated, int r) {
   float g[8];
   g[0] = A[P0].x * A[Q0].x + A[P0].y * A[Q0].y; g[1] = A[P0].x * A[Q0].y - A[P0].y * A[Q0].x;
   g[2] = A[P1].x * A[Q1].x + A[P1].y * A[Q1].y; g[3] = A[P1].x * A[Q1].y - A[P1].y * A[Q1].x;
   g[4] = A[P2].x * A[Q2].x + A[P2].y * A[Q2].y; g[5] = A[P2].x * A[Q2].y - A[P2].y * A[Q2].x;
   g[6] = A[P3].x * A[Q3].x + A[P3].y * A[Q3].y; g[7] = A[P3].x * A[Q3].y - A[P3].y * A[Q3].x;
+  const bool b2 = r & 4, b1 = r & 2, b0 = r & 1;
+  float h[4];
 #pragma unroll
-  for (int o = 1; o < 8; o <<= 1)
+  for (int i = 0; i < 4; ++i) {
+    const float send = b2 ? g[i] : g[4 + i], keep = b2 ? g[4 + i] : g[i];
+    h[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  float k2[2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) g[i] += __shfl_xor_sync(0xffffffffu, g[i], o);
-  rotate<P0, Q0>(A, V, w, g[0], g[1], nul, tol2, rotated);
-  rotate<P1, Q1>(A, V, w, g[2], g[3], nul, tol2, rotated);
-  rotate<P2, Q2>(A, V, w, g[4], g[5], nul, tol2, rotated);
-  rotate<P3, Q3>(A, V, w, g[6], g[7], nul, tol2, rotated);
+  for (int i = 0; i < 2; ++i) {
+    const float send = b1 ? h[i] : h[2 + i], keep = b1 ? h[2 + i] : h[i];
+    k2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  const float mine = (b0 ? k2[1] : k2[0]) + __shfl_xor_sync(0xffffffffu, b0 ? k2[0] : k2[1], 1);   // component r
+  const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
+  const float gr = b0 ? other : mine, gi = b0 ? mine : other;
+  // column norms of this lane's pair k = r / 2
+  const float al = b2 ? (b1 ? w[P3] : w[P2]) : (b1 ? w[P1] : w[P0]);
+  const float be = b2 ? (b1 ? w[Q3] : w[Q2]) : (b1 ? w[Q1] : w[Q0]);
+  const Rot mineR = rot_params(al, be, gr, gi, nul, tol2);
+  rotated |= mineR.s != 0.f;
+  const int base = (threadIdx.x & 31) & ~7;
+  Rot R[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    R[k].c = __shfl_sync(0xffffffffu, mineR.c, base + 2 * k);
+    R[k].s = __shfl_sync(0xffffffffu, mineR.s, base + 2 * k);
+    R[k].phx = __shfl_sync(0xffffffffu, mineR.phx, base + 2 * k);
+    R[k].phy = __shfl_sync(0xffffffffu, mineR.phy, base + 2 * k);
+    R[k].dw = __shfl_sync(0xffffffffu, mineR.dw, base + 2 * k);
+  }
+  apply_rot<P0, Q0>(A, V, w, R[0]);
+  apply_rot<P1, Q1>(A, V, w, R[1]);
+  apply_rot<P2, Q2>(A, V, w, R[2]);
+  apply_rot<P3, Q3>(A, V, w, R[3]);
 }
 
 // one-sided Jacobi SVD: on exit A = U diag(sigma) (row of this lane), V = right singular vectors (row of this
@@ -118,7 +156,7 @@ __device__ __forceinline__ void jacobi8(float2 (&A)[8], float2 (&V)[8], float (&
     bool rotated = false;
 #pragma unroll 1
     for (int round = 0; round < 7; ++round) {
-      jacobi_round<0, 7, 1, 6, 2, 5, 3, 4>(A, V, w, nul, tol2, rotated);
+      jacobi_round<0, 7, 1, 6, 2, 5, 3, 4>(A, V, w, nul, tol2, rotated, r);
       const float2 a7 = A[7], v7 = V[7];
       const float w7 = w[7];
 #pragma unroll

@@ -22,23 +22,25 @@
 #include <cuda_runtime.h>
 
 #include "bqa_core.cuh"
+#include "bqa_fast_common.cuh"
 #include "bqa_launch.cuh"
 
 namespace bqa {
 namespace fast {
 
-constexpr int kWarps = 8;
+constexpr int kWarps = 12;
 constexpr int kThreads = kWarps * 32;
 constexpr int kSlice = 144;                       // 128-byte slice + 16 bytes of padding (bank spreading)
 constexpr int kTBytes = 32 * kSlice;              // 4 nodes x 8 slices
-constexpr int kMsg = 144;                         // 128-byte message + 16 bytes of padding
+constexpr int kMsg = 128;                         // one 128-byte message (no padding: 12 warps must fit in 227 KB)
 constexpr int kMBytes = 12 * kMsg;                // 3 messages x 4 nodes
 constexpr int kRedRow = 80;                       // packed Hermitian partial: 4 diagonal + 6 upper entries (complex)
 constexpr int kRedSlot = 8 * kRedRow + 64;        // 8 lanes of a node (+ skew between the two nodes of a half warp)
 constexpr int kOut0 = 4 * kRedSlot;               // scratch offset of the out_0 exchange (4 rows of 288 bytes)
 constexpr int kOut0Row = 288;
 constexpr int kStage = kTBytes + 2 * kMBytes;     // T | incoming messages | previous outgoing messages
-constexpr int kWarpBytes = 2 * kStage + kTBytes;  // two stages + reduction scratch
+constexpr int kScratch = kOut0 + 4 * kOut0Row;     // packed partials of out_1 / out_2 + the out_0 exchange
+constexpr int kWarpBytes = 2 * kStage + kScratch; // two stages + reduction scratch
 constexpr int kSmem = kWarps * kWarpBytes;
 
 struct Args {
@@ -57,44 +59,6 @@ struct Args {
   const int32_t* remote_pos;
   unsigned char* peers[BQA_MAX_PEERS];
 };
-
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
-}
-
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-// acc += a * b
-__device__ __forceinline__ void fma_c(float2& acc, float2 a, float2 b) {
-  acc.x = fmaf(a.x, b.x, acc.x); acc.x = fmaf(-a.y, b.y, acc.x);
-  acc.y = fmaf(a.x, b.y, acc.y); acc.y = fmaf(a.y, b.x, acc.y);
-}
-// acc += conj(a) * b
-__device__ __forceinline__ void fma_cc(float2& acc, float2 a, float2 b) {
-  acc.x = fmaf(a.x, b.x, acc.x); acc.x = fmaf(a.y, b.y, acc.x);
-  acc.y = fmaf(a.x, b.y, acc.y); acc.y = fmaf(-a.y, b.x, acc.y);
-}
-
-// 16 complex (128 bytes) shared -> registers
-__device__ __forceinline__ void lds_tile(float2 (&r)[16], const unsigned char* p) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float4 v = *reinterpret_cast<const float4*>(p + 16 * i);
-    r[2 * i] = make_float2(v.x, v.y);
-    r[2 * i + 1] = make_float2(v.z, v.w);
-  }
-}
-__device__ __forceinline__ void sts_tile(unsigned char* p, const float2 (&r)[16]) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    *reinterpret_cast<float4*>(p + 16 * i) = make_float4(r[2 * i].x, r[2 * i].y, r[2 * i + 1].x, r[2 * i + 1].y);
-}
 
 // issue the copies of one 4-node group into a stage: T (coalesced 4 KB), 12 incoming and 12 previous
 // outgoing messages (each by the 8 lanes of a quarter warp: one full 128-byte line)

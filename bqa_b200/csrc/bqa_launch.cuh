@@ -58,6 +58,15 @@ int launch_fast_msgs_d3D4(bool ext, long long B, const void* T, const void* msgs
 // symmetric-gauge messages of every slot, msgs[p] = diag(lambda[p mod L][:Dn]) / trace      (state.py:56-57)
 template <typename R>
 int launch_gauge_msgs(int D_old, int Dn, long long L, const void* lmbds, void* msgs_out, cudaStream_t st);
+// msgs_out[out_pos[i]] = diag(lambda[lmbd_pos[i]][:Dn]) / trace for a list of (slot, lambda row) pairs
+template <typename R>
+int launch_gauge_slots(int D_old, int Dn, long long n, const int32_t* out_pos, const int32_t* lmbd_pos, const void* lmbds,
+                       void* msgs_out, cudaStream_t st);
+// specialised simple-update application (bqa_fast_apply.cu): degree 3, D = 4 -> 4, complex64
+bool fast_apply_available(int prec, int degree, int D, int Dn);
+int launch_fast_apply_d3D4(long long B, const void* T_in, void* T_out, const void* canon, const void* lmbds,
+                           const int32_t* in_pos, const int32_t* lmbd_pos, const void* node_ampls,
+                           const void* edge_ampls, double ztime, double xtime, cudaStream_t st);
 // cross-GPU sweep epilogue over peer memory: residual max to every peer + barrier (bqa_sync.cu)
 int launch_sweep_sync(int prec, int rank, int world, void* const* peer_resid, int it, void* const* peer_flags,
                       unsigned seq, int32_t* status, cudaStream_t st);

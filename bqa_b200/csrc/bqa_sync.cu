@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(256) k_gauge_msgs(int stride, int Dn, long lon
     if (r == c) {
       R tr = 0;
       for (int k = 0; k < Dn; ++k) tr += lam[k];
-      v = lam[c] / tr;
+      v = lam[c] * (R(1) / tr);                             // same arithmetic as emit_gauge_msg (bqa_core.cuh)
     }
     msgs[i] = mk<R>(v, R(0));
   }
@@ -45,6 +45,37 @@ int launch_gauge_msgs(int D_old, int Dn, long long L, const void* lmbds, void* m
 }
 template int launch_gauge_msgs<float>(int, int, long long, const void*, void*, cudaStream_t);
 template int launch_gauge_msgs<double>(int, int, long long, const void*, void*, cudaStream_t);
+
+template <typename R>
+__global__ void __launch_bounds__(256) k_gauge_slots(int stride, int Dn, long long n, const int32_t* out_pos,
+                                                     const int32_t* lmbd_pos, const R* lmbds, cx<R>* msgs) {
+  const int DD = Dn * Dn;
+  const long long total = n * DD;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long q = i / DD;
+    const int o = (int)(i - q * DD), r = o / Dn, c = o - r * Dn;
+    const R* lam = lmbds + (size_t)lmbd_pos[q] * stride;
+    R v = 0;
+    if (r == c) {
+      R tr = 0;
+      for (int k = 0; k < Dn; ++k) tr += lam[k];
+      v = lam[c] * (R(1) / tr);
+    }
+    msgs[(size_t)out_pos[q] * DD + o] = mk<R>(v, R(0));
+  }
+}
+
+template <typename R>
+int launch_gauge_slots(int D_old, int Dn, long long n, const int32_t* out_pos, const int32_t* lmbd_pos, const void* lmbds,
+                       void* msgs_out, cudaStream_t st) {
+  if (n == 0) return 0;
+  long long blocks = (n * Dn * Dn + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_gauge_slots<R><<<(int)blocks, 256, 0, st>>>(2 * D_old, Dn, n, out_pos, lmbd_pos, (const R*)lmbds, (cx<R>*)msgs_out);
+  return after_launch("gauge_slots");
+}
+template int launch_gauge_slots<float>(int, int, long long, const int32_t*, const int32_t*, const void*, void*, cudaStream_t);
+template int launch_gauge_slots<double>(int, int, long long, const int32_t*, const int32_t*, const void*, void*, cudaStream_t);
 
 struct SyncArgs {
   int rank, world, it, dbl;

@@ -245,22 +245,27 @@ def _graded_ext_msgs(rng, L, n=8):
 @pytest.mark.parametrize("L", [1, 5, 3001])
 def test_fast_canon8_matches_oracle(lib, L):
     """Specialised n = 8 complex64 canonicalizer kernel (bqa_fast_canon8.cu) against the oracle's
-    _get_canonicalizers restatement (reference state.py:171-200) in complex128: lambdas, column maxima and the
-    gauge-invariant bond operator sum_k C_b[a,k] lambda_k C_f[b,k] over the 4 kept columns; the generic
-    complex64 kernel on the same input sets the scale of what complex64 can deliver."""
+    _get_canonicalizers restatement (reference state.py:171-200) in complex128.  Gauge-invariant checks: the lambdas,
+    their column maxima, and the defining property of the canonicalizers -- with the oracle's square-root factors
+    lu_f, lu_b of the masked messages (backends.py:483-490) and ker = lu_f lu_b^T (state.py:186-187),
+    (lu_f C_f)^H ker conj(lu_b C_b) = diag(S) on the kept columns, i.e. lu_f C_f and lu_b C_b are the singular
+    vectors of ker (well conditioned: the 1/sqrt(eigenvalue) factors inside C cancel against lu)."""
     import torch
     from bqa_b200 import _lib
     from oracle import bqa_oracle as O
     rng = np.random.default_rng(100 + L)
     n, D = 8, 4
     ext = _graded_ext_msgs(rng, L).astype(np.complex64)
-    lm_ref, canon_ref = O.canonicalizers(ext.astype(np.complex128), 1e-6, np.complex128)
+    ext64 = ext.astype(np.complex128)
+    lm_ref, _ = O.canonicalizers(ext64, 1e-6, np.complex128)
     lm_ref = lm_ref.real
-    inv_ref = np.einsum("eak,ek,ebk->eab", canon_ref[:L, :, :4], lm_ref[:, :4], canon_ref[L:, :, :4])
+    u, lam, uh = O.masked_svd(ext64, 1e-6, np.complex128)
+    lu = np.sqrt(lam)[..., :, None] * uh
+    ker = lu[:L] @ np.swapaxes(lu[L:], 1, 2)
+    s_ref = np.linalg.svd(ker, compute_uv=False)[:, :4]
     dev = torch.device("cuda:0")
     e = torch.from_numpy(ext.reshape(-1)).to(dev)
     st = torch.cuda.current_stream().cuda_stream
-    err = {}
     for mode in (1, 0):
         lib.set_kernel_mode(mode)
         try:
@@ -272,12 +277,11 @@ def test_fast_canon8_matches_oracle(lib, L):
             lib.set_kernel_mode(0)
         lmh = lm.cpu().numpy().reshape(L, n).astype(np.float64)
         c = canon.cpu().numpy().reshape(2 * L, n, n).astype(np.complex128)
-        inv = np.einsum("eak,ek,ebk->eab", c[:L, :, :4], lmh[:, :4], c[L:, :, :4])
-        err[mode] = (np.abs(lmh[:, :4] - lm_ref[:, :4]).max(), np.abs(inv - inv_ref).max(),
-                     np.abs(colmax.cpu().numpy() - lmh.max(0)).max())
-    assert err[0][2] == 0.0                                   # column maxima are exactly the maxima of what was written
-    assert err[0][0] < 5e-6                                   # lambdas (L2-normalised, <= 1)
-    assert err[0][1] < max(2.0 * err[1][1], 2e-4)             # no worse than the generic complex64 kernel
+        af, ab = lu[:L] @ c[L:, :, :4], lu[L:] @ c[:L, :, :4]
+        G = np.swapaxes(af.conj(), 1, 2) @ ker @ ab.conj()
+        assert np.abs(colmax.cpu().numpy() - lmh.max(0)).max() == 0.0      # exactly the maxima of what was written
+        assert np.abs(lmh[:, :4] - lm_ref[:, :4]).max() < 5e-6                # lambdas (L2-normalised, <= 1)
+        assert np.abs(np.abs(G) - s_ref[:, :, None] * np.eye(4)).max() < 2e-5, mode
 
 
 def test_partitioned_nccl(lib):
@@ -293,3 +297,44 @@ def test_partitioned_nccl(lib):
                         "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(here, "multigpu_check.py")],
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "multigpu_check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("B", [1, 6, 2003])
+def test_fast_apply_update_matches_generic(lib, B):
+    """Specialised degree-3 / D = 4 -> 4 / complex64 simple-update application (bqa_fast_apply.cu) against the
+    generic kernel (itself checked against the oracle end to end) on random canonicalizers, lambdas and scattered
+    slots, incl. a ragged batch; the re-initialised messages must be identical."""
+    import torch
+    from bqa_b200 import _lib
+    d, D = 3, 4
+    rng = np.random.default_rng(50 + B)
+    L = (3 * B + 1) // 2 + 3
+    t, _, thetas = instances.random_node_batch(B, d, D, seed=B)
+    canon = (rng.normal(size=(2 * L, 8, 8)) + 1j * rng.normal(size=(2 * L, 8, 8))).astype(np.complex64)
+    lm = np.sort(rng.uniform(0.01, 1.0, size=(L, 8)), axis=1)[:, ::-1].astype(np.float32).copy()
+    in_pos = rng.permutation(2 * L)[: d * B].reshape(d, B).astype(np.int32)
+    out_pos = ((in_pos + L) % (2 * L)).astype(np.int32)
+    lpos = (in_pos % L).astype(np.int32)
+    dev = torch.device("cuda:0")
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    T, Cn, Lm = up(t.astype(np.complex64).reshape(-1)), up(canon.reshape(-1)), up(lm.reshape(-1))
+    ip, op, lp = up(in_pos), up(out_pos), up(lpos)
+    na = up(rng.uniform(-1, 1, size=B).astype(np.float32))
+    ea = up(np.stack(thetas).astype(np.float32))
+    ws = torch.zeros(lib.workspace_bytes(_lib.C64, d, D, D), dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    out = {}
+    for mode in (1, 0):
+        lib.set_kernel_mode(mode)
+        try:
+            Tout = torch.zeros_like(T)
+            msgs = torch.zeros(2 * L * D * D, dtype=torch.complex64, device=dev)
+            lib.apply_update(_lib.C64, d, D, D, B, T.data_ptr(), Tout.data_ptr(), Cn.data_ptr(), Lm.data_ptr(),
+                             msgs.data_ptr(), ip.data_ptr(), op.data_ptr(), lp.data_ptr(), na.data_ptr(), ea.data_ptr(),
+                             0.13, 0.07, ws.data_ptr(), ws.numel(), st)
+            out[mode] = (Tout.cpu().numpy().reshape(B, -1), msgs.cpu().numpy())
+        finally:
+            lib.set_kernel_mode(0)
+    assert np.abs(np.linalg.norm(out[0][0], axis=1) - 1).max() < 1e-5
+    assert np.abs(out[0][0] - out[1][0]).max() < 2e-6
+    assert np.array_equal(out[0][1], out[1][1])

@@ -372,7 +372,7 @@ def measure_roofline(eng, lib, layers, torch, dev) -> dict:
 def measure_e2e(eng, snapshot, layers, torch, dev, bloch_resident) -> dict:
     """Same K steps driven from HOST buffers through the public engine API: load_state (pinned host -> HBM),
     K x run_layer (each reads its bond-dimension decision and BP residuals back), bloch_vectors (HBM -> host)."""
-    h2d = sum(int(t.numel() * t.element_size()) for t in snapshot["_pinned"])
+    h2d = sum(int(t.numel() * t.element_size()) for t in snapshot["_pinned"].values())
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
     eng.load_state(snapshot)

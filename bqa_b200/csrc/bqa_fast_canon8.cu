@@ -57,9 +57,13 @@ __device__ __forceinline__ float rsqrt_nr(float x) {
 struct Rot {
   float c, s, phx, phy, dw;      // cos, sin, unimodular phase conj(g)/|g|, norm transfer t |g|
 };
-__device__ __forceinline__ Rot rot_params(float al, float be, float gr, float gi, float nul, float tol2) {
+// `again` is raised when the pair was still far from orthogonal (|g| > 1e-4 |a_p| |a_q|).  Jacobi converges
+// quadratically, so a sweep whose largest cosine was below 1e-4 leaves cosines of order 1e-8, far under the
+// 6.7e-7 tolerance: the sweep loop stops after it instead of spending a whole sweep on confirming convergence.
+__device__ __forceinline__ Rot rot_params(float al, float be, float gr, float gi, float nul, float tol2, bool& again) {
   const float g2 = gr * gr + gi * gi;
   const bool act = !(al <= nul || be <= nul || g2 <= tol2 * al * be);
+  again |= act && g2 > 1e-8f * al * be;
   const float ig = rsqrt_nr(g2);                  // 1 / |g|   (inf / nan when inactive: discarded below)
   const float ag = g2 * ig;
   const float zeta = 0.5f * (be - al) * ig;
@@ -119,8 +123,7 @@ __device__ __forceinline__ void jacobi_round(float2 (&A)[8], float2 (&V)[8], flo
   // column norms of this lane's pair k = r / 2
   const float al = b2 ? (b1 ? w[P3] : w[P2]) : (b1 ? w[P1] : w[P0]);
   const float be = b2 ? (b1 ? w[Q3] : w[Q2]) : (b1 ? w[Q1] : w[Q0]);
-  const Rot mineR = rot_params(al, be, gr, gi, nul, tol2);
-  rotated |= mineR.s != 0.f;
+  const Rot mineR = rot_params(al, be, gr, gi, nul, tol2, rotated);
   const int base = (threadIdx.x & 31) & ~7;
   Rot R[4];
 #pragma unroll

@@ -229,16 +229,16 @@ class Engine:
         with asynchronous copies."""
         snap = {"D": self.D, "tensors": self.tensors_numpy(), "msgs": self.msgs_numpy(), "lmbds": self.lmbds_numpy()}
         if pinned and self.cuda:
-            keep = []
+            keep = {}
 
-            def pin(a):
+            def pin(key, a):
                 t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-                keep.append(t)
+                keep[key] = t
                 return t.numpy()
-            snap["tensors"] = {d: pin(t) for d, t in snap["tensors"].items()}
-            snap["msgs"] = pin(snap["msgs"])
-            snap["lmbds"] = pin(snap["lmbds"])
-            snap["_pinned"] = keep
+            snap["tensors"] = {d: pin(("tensors", d), t) for d, t in snap["tensors"].items()}
+            snap["msgs"] = pin("msgs", snap["msgs"])
+            snap["lmbds"] = pin("lmbds", snap["lmbds"])
+            snap["_pinned"] = keep          # page-locked torch tensors behind the numpy views above
         return snap
 
     def load_state(self, snap: dict) -> None:
@@ -247,15 +247,23 @@ class Engine:
         if not 1 <= D <= self.Dmax:
             raise ValueError(f"bond dimension {D} outside [1, {self.Dmax}]")
         np_c = np.complex64 if self.precision == "single" else np.complex128
+        pinned = snap.get("_pinned", {})
+
+        def host(key, arr):
+            """flat host tensor in the working dtype; the page-locked original when there is one (asynchronous copy)"""
+            t = pinned.get(key)
+            if t is not None and t.dtype == self.cdtype:
+                return t.view(-1)
+            return torch.from_numpy(np.ascontiguousarray(np.asarray(arr), dtype=np_c).reshape(-1))
         for c in self.classes:
-            t = np.ascontiguousarray(np.asarray(snap["tensors"][c.degree]).astype(np_c)).reshape(-1)
+            t = host(("tensors", c.degree), snap["tensors"][c.degree])
             assert t.shape[0] == c.B * 2 * D ** c.degree, "tensor batch has the wrong shape"
             c.cur = 0
-            c.T[0][: t.shape[0]].copy_(torch.from_numpy(t), non_blocking=True)
-        m = np.ascontiguousarray(np.asarray(snap["msgs"]).astype(np_c)).reshape(-1)
+            c.T[0][: t.shape[0]].copy_(t, non_blocking=True)
+        m = host("msgs", snap["msgs"])
         assert m.shape[0] == self.E2 * D * D
         self._msgs_cur = 0
-        self._msgs[0][: m.shape[0]].copy_(torch.from_numpy(m), non_blocking=True)
+        self._msgs[0][: m.shape[0]].copy_(m, non_blocking=True)
         lm = np.zeros((self.L, 2 * D), self.np_rdtype)
         lm[:, :D] = np.real(np.asarray(snap["lmbds"]))
         self._lmbd_stride = 2 * D

@@ -338,3 +338,54 @@ def test_fast_apply_update_matches_generic(lib, B):
     assert np.abs(np.linalg.norm(out[0][0], axis=1) - 1).max() < 1e-5
     assert np.abs(out[0][0] - out[1][0]).max() < 2e-6
     assert np.array_equal(out[0][1], out[1][1])
+
+
+# ---- BASELINE.json configs[0..2] as parity cases ------------------------------------
+def _oracle_vs_gpu(cfg, lib, bloch_tol, check_outcomes=True):
+    from oracle import bqa_oracle as O
+    want, octx, ost = O.run_qa(cfg, return_state=True)
+    want = dict(want)
+    res, eng = _run(cfg, "double")
+    assert eng.stats["bond_dims"] == ost.stats["bond_dims"]
+    assert np.abs(np.array(res["bloch_vectors"]) - np.array(want["bloch_vectors"])).max() < bloch_tol
+    if check_outcomes and "measurement_outcomes" in want:
+        assert res["measurement_outcomes"] == want["measurement_outcomes"]
+    return res, eng, ost
+
+
+def test_config2_grid_20x20_double_vs_oracle(lib):
+    """BASELINE configs[1]: 2D square-grid Ising anneal in the shape of reference examples/2d_greed.py:11-30
+    (400 qubits, degrees 2/3/4, max_bond_dim 4, total_time 10; 40 of its 100 steps to bound the oracle's run time),
+    validated against the numpy-backend restatement in double precision."""
+    from bqa_b200.benchmarking import generate_qubo_on_2d_grid
+    nodes, edges = generate_qubo_on_2d_grid(20, 20, seed=42)
+    cfg = {"nodes": nodes, "edges": edges, "max_bond_dim": 4,
+           "schedule": {"total_time": 4.0, "starting_mixing": 1.0,
+                        "actions": [{"weight": 1.0, "steps_number": 40, "final_mixing": 0.6}, "get_bloch_vectors"]}}
+    _oracle_vs_gpu(cfg, lib, 1e-7)     # (the O(N^2) python sampler of the oracle is exercised on the smaller configs)
+
+
+def test_config3_heavy_hex_127_double_vs_oracle(lib):
+    """BASELINE configs[2]: the full-size IBM heavy-hex anneal of reference examples/full_size_ibm_heavy_hex.py:12-100
+    (127 qubits, +-1 amplitudes, max_bond_dim 8, total_time 10, 10 steps, then measure), double precision.
+    +-1 amplitudes give exactly degenerate spectra: this is the case the no-FMA complex128 build exists for."""
+    from bqa_b200.benchmarking import heavy_hex_127
+    nodes, edges = heavy_hex_127(seed=42)
+    cfg = {"nodes": nodes, "edges": edges, "max_bond_dim": 8,
+           "schedule": {"total_time": 10.0, "starting_mixing": 1.0,
+                        "actions": [{"weight": 1.0, "steps_number": 10, "final_mixing": 0.0}, "get_bloch_vectors", "measure"]}}
+    _oracle_vs_gpu(cfg, lib, 1e-6)
+
+
+def test_config1_maxcut_shape_double_vs_oracle(lib):
+    """BASELINE configs[0] shape (benchmarks_against_mqlib/random_3_regular_maxcut_1000.py:10-44: zero fields, unit
+    couplings, max_bond_dim 16, damping 0.5, eps 1e-5, 250 BP iterations, dt 0.2) on 200 qubits for the first 120
+    steps -- the bond dimension passes through 1, 2, 3 on the way; degenerate spectra again."""
+    from bqa_b200.benchmarking import generate_qubo_on_random_regular_graph
+    nodes, edges = generate_qubo_on_random_regular_graph(200, 3, seed=42, node_ampl_func=lambda *_: 0.0,
+                                                         edge_ampl_func=lambda *_: 1.0)
+    cfg = {"nodes": nodes, "edges": edges, "max_bond_dim": 16, "measurement_threshold": 0.99, "damping": 0.5,
+           "bp_eps": 1e-5, "pinv_eps": 1e-5, "max_bp_iter_number": 250,
+           "schedule": {"total_time": 24.0, "starting_mixing": 1.0,
+                        "actions": [{"weight": 1.0, "steps_number": 120, "final_mixing": 0.88}, "get_bloch_vectors"]}}
+    _oracle_vs_gpu(cfg, lib, 1e-6)

@@ -68,10 +68,10 @@ class Library:
         if self._dll.bqa_b200_set_kernel_mode(int(mode)) != 0:
             raise RuntimeError(self._dll.bqa_b200_last_error().decode())
 
-    def canon_stats(self) -> tuple[int, int]:
-        out = (C.c_ulonglong * 2)()
+    def canon_stats(self) -> tuple[int, int, int]:
+        out = (C.c_ulonglong * 3)()
         self._dll.bqa_b200_canon_stats(out)
-        return int(out[0]), int(out[1])
+        return int(out[0]), int(out[1]), int(out[2])
 
     def workspace_bytes(self, prec: int, degree: int, D: int, D_new: int) -> int:
         return int(self._dll.bqa_b200_workspace_bytes(prec, degree, D, D_new))

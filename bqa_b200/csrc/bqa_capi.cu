@@ -47,10 +47,9 @@ extern "C" {
 const char* bqa_b200_last_error(void) { return g_err; }
 int bqa_b200_version(void) { return 1; }
 long long bqa_b200_launch_count(void) { return g_launches.load(); }
-/* profiling aid: out[0] = warp-level Jacobi problems solved by the n = 8 canonicalizer kernel since load,
- * out[1] = Jacobi sweeps summed over them (synchronises the device) */
-int bqa_b200_canon_stats(unsigned long long* out2) {
-  canon8_stats(out2);
+/* profiling aid, see include/bqa_b200.h */
+int bqa_b200_canon_stats(unsigned long long* out3) {
+  canon8_stats(out3);
   return 0;
 }
 int bqa_b200_set_kernel_mode(int mode) {

@@ -27,8 +27,9 @@ constexpr int kMat = 8 * kRow;             // one 8 x 8 complex tile
 constexpr int kEdgeBytes = 2 * kMat + 128; // two tiles + eigenvalues of m_f, m_b (16 floats) + sorted sigma (8) + permutation (8 ints)
 constexpr int kWarpBytes = 4 * kEdgeBytes;
 
-// statistics: [0] Jacobi problems solved (per warp: 4 matrices at a time), [1] sweeps summed over them
-__device__ unsigned long long g_stats[2];
+// statistics: [0] Jacobi problems solved (per warp: 4 matrices at a time), [1] sweeps summed over them,
+// [2] of which spent on the SVD of ker (the other two problems per edge are the message eigendecompositions)
+__device__ unsigned long long g_stats[3];
 
 __device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -57,13 +58,13 @@ __device__ __forceinline__ float rsqrt_nr(float x) {
 struct Rot {
   float c, s, phx, phy, dw;      // cos, sin, unimodular phase conj(g)/|g|, norm transfer t |g|
 };
-// `again` is raised when the pair was still far from orthogonal (|g| > 1e-4 |a_p| |a_q|).  Jacobi converges
-// quadratically, so a sweep whose largest cosine was below 1e-4 leaves cosines of order 1e-8, far under the
-// 6.7e-7 tolerance: the sweep loop stops after it instead of spending a whole sweep on confirming convergence.
-__device__ __forceinline__ Rot rot_params(float al, float be, float gr, float gi, float nul, float tol2, bool& again) {
+// `rotated` is raised when the pair needed a rotation.  The sweep loop runs until a whole sweep needs none, for every
+// edge of the warp: extra sweeps on an already converged edge are exact identities, so an edge's result does not
+// depend on which other edges share its warp (single-GPU and partitioned runs stay bit-identical).
+__device__ __forceinline__ Rot rot_params(float al, float be, float gr, float gi, float nul, float tol2, bool& rotated) {
   const float g2 = gr * gr + gi * gi;
   const bool act = !(al <= nul || be <= nul || g2 <= tol2 * al * be);
-  again |= act && g2 > 1e-8f * al * be;
+  rotated |= act;
   const float ig = rsqrt_nr(g2);                  // 1 / |g|   (inf / nan when inactive: discarded below)
   const float ag = g2 * ig;
   const float zeta = 0.5f * (be - al) * ig;
@@ -201,7 +202,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_canon8(long long L, const float
   const long long groups = (L + 3) >> 2;
   const long long nwarps = (long long)gridDim.x * kWarps;
   float cm = 0.f;                                           // running max of lambda[:, r] over this lane's edges
-  int n_sweeps = 0, n_jac = 0;
+  int n_sweeps = 0, n_jac = 0, n_ker = 0;
   for (long long g = (long long)blockIdx.x * kWarps + wib; g < groups; g += nwarps) {
     long long e = g * 4 + eg;
     const bool live = e < L;
@@ -243,7 +244,9 @@ __global__ void __launch_bounds__(kWarps * 32) k_canon8(long long L, const float
           A[j].x *= sc; A[j].y *= sc;
         }
       }
+      const int before = n_sweeps;
       jacobi8(A, W, sk, r, n_sweeps);
+      if (m == 2) n_ker += n_sweeps - before;
       if (m < 2) {
         float mine = sk[0];
 #pragma unroll
@@ -337,13 +340,14 @@ __global__ void __launch_bounds__(kWarps * 32) k_canon8(long long L, const float
   if (lane == 0) {
     atomicAdd(&g_stats[0], (unsigned long long)n_jac);
     atomicAdd(&g_stats[1], (unsigned long long)n_sweeps);
+    atomicAdd(&g_stats[2], (unsigned long long)n_ker);
   }
 }
 
 }  // namespace canon8
 
-void canon8_stats(unsigned long long* out2) {
-  cudaMemcpyFromSymbol(out2, canon8::g_stats, sizeof(unsigned long long) * 2);
+void canon8_stats(unsigned long long* out3) {
+  cudaMemcpyFromSymbol(out3, canon8::g_stats, sizeof(unsigned long long) * 3);
 }
 
 int launch_fast_canon8(long long L, const void* ext, void* canon, void* lmbds, void* colmax, double pinv_eps,

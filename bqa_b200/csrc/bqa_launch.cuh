@@ -75,6 +75,6 @@ int launch_sweep_sync(int prec, int rank, int world, void* const* peer_resid, in
 int launch_fast_canon8(long long L, const void* ext, void* canon, void* lmbds, void* colmax, double pinv_eps,
                        int ncols, cudaStream_t st);
 
-void canon8_stats(unsigned long long* out2);
+void canon8_stats(unsigned long long* out3);
 
 }  // namespace bqa

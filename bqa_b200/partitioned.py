@@ -315,6 +315,14 @@ class PartitionedEngine(Engine):
             p2p = (_testing_lib is None and dist.get_backend(group) == "nccl" and self.world <= 8
                    and os.environ.get("BQA_B200_P2P", "1") != "0")
         self.p2p = bool(p2p) and self.world > 1
+        if self.p2p:                                          # every pair of GPUs must be peer-accessible; all ranks agree
+            dev_idx = torch.device(device).index if device is not None else torch.cuda.current_device()
+            ok = all(d == dev_idx or torch.cuda.can_device_access_peer(dev_idx, d) for d in range(torch.cuda.device_count()))
+            flag = torch.tensor([1 if ok else 0], device=torch.device("cuda", dev_idx))
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if not int(flag.item()):
+                log.warning("peer access between the GPUs is not available: boundary messages go through torch.distributed")
+                self.p2p = False
         self._symm = {}                                       # tag -> (tensor, handle)
         self._seq = 0
         super().__init__(local, precision=precision, device=device, _testing_lib=_testing_lib)

@@ -41,9 +41,10 @@ long long bqa_b200_launch_count(void);
  * 1: generic kernels only (used by the tests to check the specialised kernels against the generic ones) */
 int bqa_b200_set_kernel_mode(int mode);
 
-/* profiling aid: out2[0] = warp-level Jacobi problems solved by the n = 8 canonicalizer kernel since load,
- * out2[1] = Jacobi sweeps summed over them (synchronises the device) */
-int bqa_b200_canon_stats(unsigned long long* out2);
+/* profiling aid: out3[0] = warp-level Jacobi problems (4 matrices each) solved by the n = 8 canonicalizer kernel
+ * since load, out3[1] = Jacobi sweeps summed over them, out3[2] = the part of out3[1] spent on the SVD of ker
+ * (synchronises the device) */
+int bqa_b200_canon_stats(unsigned long long* out3);
 
 /* bytes of device scratch the node kernels need for a degree class (pass the max over classes) */
 size_t bqa_b200_workspace_bytes(int prec, int degree, int D, int D_new);

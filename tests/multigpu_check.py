@@ -39,7 +39,7 @@ def main():
                         "actions": [{"weight": 1.0, "steps_number": 30, "final_mixing": 0.0}]}}
     ctx = config_to_context(cfg)
     ok = True
-    for precision, tol in (("double", 1e-9), ("single", 5e-3)):
+    for precision, tol in (("double", 1e-9), ("single", 1e-6)):   # designed to be bit-identical; the tolerances are slack
         pe = PartitionedEngine(ctx, precision=precision, device=dev)
         got = run(pe, ctx)
         if rank == 0:
@@ -50,7 +50,7 @@ def main():
             sweeps = np.abs(np.array(pe.stats["bp_sweeps"]) - np.array(se.stats["bp_sweeps"])).max()
             print(f"{precision}: world {dist.get_world_size()} max |bloch - single GPU| = {err:.3e}, bond dims equal: {same}, "
                   f"max sweep-count difference {sweeps}, boundary bytes sent by rank 0: {pe.comm_bytes}", flush=True)
-            ok = ok and err < tol and same and sweeps <= (0 if precision == "double" else 1)
+            ok = ok and err < tol and same and sweeps == 0
         dist.barrier()
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)

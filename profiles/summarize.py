@@ -72,7 +72,9 @@ def kernel(src, dst, pattern=""):
                 v, u = float(r[hdr.index(k)]), units[hdr.index(k)]
                 return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
             t = {"dram_bytes_per_launch": mb("dram__bytes_read.sum") + mb("dram__bytes_write.sum"),
-                 "source": os.path.basename(src), "kernel": r[name_i], "launch_us": float(r[hdr.index("gpu__time_duration.sum")])}
+                 "source": os.path.basename(src), "kernel": r[name_i],
+                 "launch_us": float(r[hdr.index("gpu__time_duration.sum")]) *
+                 {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}[units[hdr.index("gpu__time_duration.sum")]]}
             with open(os.path.join(os.path.dirname(dst), "bp_sweep_traffic.json"), "w") as f:
                 json.dump(t, f, indent=1)
     print(open(dst).read()[:3000])

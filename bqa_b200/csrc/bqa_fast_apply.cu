@@ -238,11 +238,13 @@ int launch_fast_apply_d3D4(long long B, const void* T_in, void* T_out, const voi
                            const void* edge_ampls, double ztime, double xtime, cudaStream_t st) {
   using namespace fast_apply;
   if (B == 0) return 0;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {};           // the attribute is per device
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  if (cur_dev < 0 || cur_dev >= 64 || !configured[cur_dev]) {
     cudaError_t e = cudaFuncSetAttribute(k_apply_d3D4, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(k_apply_d3D4): %s", cudaGetErrorString(e));
-    configured = true;
+    if (cur_dev >= 0 && cur_dev < 64) configured[cur_dev] = true;
   }
   Args a{};
   a.B = B; a.T = (const float2*)T_in; a.Tout = (float2*)T_out; a.canon = (const float2*)canon; a.lmbds = (const float*)lmbds;

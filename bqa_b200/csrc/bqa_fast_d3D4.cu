@@ -374,15 +374,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_msgs_d3D4(Args a) {
   }
 }
 
-static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
+static int sm_count() {                     // of the current device (a process may drive several)
+  int dev = 0, n = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  return n > 0 ? n : 148;
 }
 
 }  // namespace fast
@@ -395,13 +391,15 @@ int launch_fast_msgs_d3D4(bool ext, long long B, const void* T, const void* msgs
                           const int32_t* remote_pos, void* const* peers, cudaStream_t st) {
   using namespace fast;
   if (B == 0) return 0;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {};           // the attribute is per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
     cudaError_t e1 = cudaFuncSetAttribute(k_msgs_d3D4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     cudaError_t e2 = cudaFuncSetAttribute(k_msgs_d3D4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e1 != cudaSuccess || e2 != cudaSuccess)
       return set_error("cudaFuncSetAttribute(k_msgs_d3D4): %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
-    configured = true;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   Args a{};
   a.B = B; a.T = (const float2*)T; a.msgs_cur = (const float2*)msgs_cur; a.msgs_out = (float2*)msgs_out;

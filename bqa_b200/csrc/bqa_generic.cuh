@@ -304,12 +304,9 @@ int launch_canonicalize(int D, long long L, const void* ext, void* canon, void* 
   if (wpb > 8) wpb = 8;
   if (wpb < 1) return set_error("canonicalize: bond dimension %d needs %zu bytes of shared memory per edge", D, per_warp);
   const size_t smem = per_warp * wpb;
-  static size_t configured[2] = {0, 0};
-  const int pi = sizeof(R) == 4 ? 0 : 1;
-  if (smem > configured[pi]) {
+  if (smem > 48 * 1024) {                      // per device and per size: set on every call (microseconds per step)
     cudaError_t e = cudaFuncSetAttribute(k_canonicalize<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(canonicalize): %s", cudaGetErrorString(e));
-    configured[pi] = smem;
   }
   long long blocks = (L + wpb - 1) / wpb;
   const long long cap = (long long)148 * 8;

@@ -6,13 +6,16 @@
 //   ker = U S W^H                                    masked SVD                   (state.py:189)
 //   C_f = V_f L_f^-1/2 U (slot e + L),  C_b = V_b L_b^-1/2 conj(W) (slot e),  lambda = S / |S|   (state.py:196-200)
 //
-// Eight lanes own an edge: lane r holds ROW r of the working matrix and of the accumulated rotations, so a
-// one-sided (Hestenes) Jacobi rotation of columns (p, q) is thread-local once the column inner product has
-// been all-reduced over the 8 lanes with xor shuffles.  Rotations are scheduled round-robin (7 rounds of 4
-// disjoint pairs per sweep): the four inner products of a round are reduced together, which gives every
-// lane four independent dependency chains.  Column norms are carried along (alpha' = alpha - t |g|,
-// beta' = beta + t |g|) and recomputed exactly once per sweep.  A warp holds 4 edges; matrices move between
-// the "row per lane" and "column per lane" views through a padded shared-memory tile.
+// Four lanes own an edge: lane q holds ROWS q and q + 4 of the working matrix and of the accumulated rotations, so
+// a one-sided (Hestenes) Jacobi rotation of columns (p, q) is thread-local once the column inner product has been
+// reduced over the 4 lanes.  Rotations are scheduled round-robin (7 rounds of 4 disjoint pairs per sweep).  Per
+// round the 8 inner-product components (re, im of 4 pairs) are reduce-scattered with xor shuffles so that lane q
+// ends up with BOTH components of pair q, derives that pair's rotation alone, and the four parameter sets are
+// broadcast -- no lane repeats another lane's parameter arithmetic.  Column norms are carried along
+// (alpha' = alpha - t |g|, beta' = beta + t |g|) and recomputed exactly once per sweep.  A warp holds 8 edges;
+// matrices move between the "rows per lane" and "column per lane" views through padded shared-memory tiles.
+// Code size is kept inside the 32 KB instruction cache: ONE round body, executed 7 times per sweep with the columns
+// rotated through the registers, and ONE Jacobi instance looped over the three matrices of an edge.
 #include <cuda_runtime.h>
 
 #include "bqa_core.cuh"
@@ -22,29 +25,30 @@ namespace bqa {
 namespace canon8 {
 
 constexpr int kWarps = 4;
+constexpr int kEdges = 8;                  // edges per warp (4 lanes each)
 constexpr int kRow = 80;                   // 64-byte row of 8 complex + 16 bytes of padding
 constexpr int kMat = 8 * kRow;             // one 8 x 8 complex tile
 constexpr int kEdgeBytes = 2 * kMat + 128; // two tiles + eigenvalues of m_f, m_b (16 floats) + sorted sigma (8) + permutation (8 ints)
-constexpr int kWarpBytes = 4 * kEdgeBytes;
+constexpr int kWarpBytes = kEdges * kEdgeBytes;
 
-// statistics: [0] Jacobi problems solved (per warp: 4 matrices at a time), [1] sweeps summed over them,
+// statistics: [0] Jacobi problems solved (per warp: 8 matrices at a time), [1] sweeps summed over them,
 // [2] of which spent on the SVD of ker (the other two problems per edge are the message eigendecompositions)
 __device__ unsigned long long g_stats[3];
 
 __device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
-__device__ __forceinline__ float red8(float v) {
+__device__ __forceinline__ float red4(float v) {
   v += __shfl_xor_sync(0xffffffffu, v, 1);
   v += __shfl_xor_sync(0xffffffffu, v, 2);
-  v += __shfl_xor_sync(0xffffffffu, v, 4);
   return v;
 }
 
-// squared column norms of the 8 x 8 matrix whose row lives in this lane
-__device__ __forceinline__ void col_norms(const float2 (&A)[8], float (&w)[8]) {
+// squared column norms of the 8 x 8 matrix whose rows q, q + 4 live in this lane
+__device__ __forceinline__ void col_norms(const float2 (&A0)[8], const float2 (&A1)[8], float (&w)[8]) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) w[j] = red8(A[j].x * A[j].x + A[j].y * A[j].y);
+  for (int j = 0; j < 8; ++j)
+    w[j] = red4((A0[j].x * A0[j].x + A0[j].y * A0[j].y) + (A1[j].x * A1[j].x + A1[j].y * A1[j].y));
 }
 
 // rsqrt with one Newton step (MUFU.RSQ is good to ~2 ulp; rotations must stay orthonormal to rounding)
@@ -53,7 +57,7 @@ __device__ __forceinline__ float rsqrt_nr(float x) {
   return y * (1.5f - 0.5f * x * y * y);
 }
 
-// Rotation parameters of one column pair, computed from the all-reduced inner product (gr, gi) and the column norms.
+// Rotation parameters of one column pair, computed from the reduced inner product (gr, gi) and the column norms.
 // Branch-free: an inactive pair (converged, or a numerically-zero column) gets the identity through selects.
 struct Rot {
   float c, s, phx, phy, dw;      // cos, sin, unimodular phase conj(g)/|g|, norm transfer t |g|
@@ -81,78 +85,80 @@ __device__ __forceinline__ Rot rot_params(float al, float be, float gr, float gi
 }
 
 template <int P, int Q>
-__device__ __forceinline__ void apply_rot(float2 (&A)[8], float2 (&V)[8], float (&w)[8], const Rot& r) {
-  const float2 ph = make_float2(r.phx, r.phy);
-  float2 ap = A[P], aq = cmulf(ph, A[Q]);
+__device__ __forceinline__ void rot_row(float2 (&A)[8], const Rot& r) {
+  const float2 ap = A[P], aq = cmulf(make_float2(r.phx, r.phy), A[Q]);
   A[P] = make_float2(r.c * ap.x - r.s * aq.x, r.c * ap.y - r.s * aq.y);
   A[Q] = make_float2(r.s * ap.x + r.c * aq.x, r.s * ap.y + r.c * aq.y);
-  ap = V[P]; aq = cmulf(ph, V[Q]);
-  V[P] = make_float2(r.c * ap.x - r.s * aq.x, r.c * ap.y - r.s * aq.y);
-  V[Q] = make_float2(r.s * ap.x + r.c * aq.x, r.s * ap.y + r.c * aq.y);
+}
+template <int P, int Q>
+__device__ __forceinline__ void apply_rot(float2 (&A0)[8], float2 (&A1)[8], float2 (&V0)[8], float2 (&V1)[8],
+                                          float (&w)[8], const Rot& r) {
+  rot_row<P, Q>(A0, r);
+  rot_row<P, Q>(A1, r);
+  rot_row<P, Q>(V0, r);
+  rot_row<P, Q>(V1, r);
   w[P] -= r.dw;
   w[Q] += r.dw;
 }
 
-// One round = four disjoint pairs (P0,Q0) .. (P3,Q3).  The 8 partial inner-product components (re, im of 4 pairs)
-// are reduce-scattered over the 8 lanes of the edge (7 shuffles; lane r ends up with component r), the two lanes
-// of pair k = r / 2 swap components and compute THAT pair's rotation only, and the four parameter sets are then
-// broadcast (5 shuffles each) -- instead of every lane all-reducing 8 values and deriving all four rotations.
+// conj(a_p) a_q summed over the two rows of this lane
+#define BQA_GAMMA(P, Q, RE, IM)                                                                      \
+  RE = (A0[P].x * A0[Q].x + A0[P].y * A0[Q].y) + (A1[P].x * A1[Q].x + A1[P].y * A1[Q].y);             \
+  IM = (A0[P].x * A0[Q].y - A0[P].y * A0[Q].x) + (A1[P].x * A1[Q].y - A1[P].y * A1[Q].x);
+
+// One round = four disjoint pairs (P0,Q0) .. (P3,Q3), pair k handled by lane k of the edge.
 template <int P0, int Q0, int P1, int Q1, int P2, int Q2, int P3, int Q3>
-__device__ __forceinline__ void jacobi_round(float2 (&A)[8], float2 (&V)[8], float (&w)[8], float nul, float tol2,
-                                             bool& rotated, int r) {
+__device__ __forceinline__ void jacobi_round(float2 (&A0)[8], float2 (&A1)[8], float2 (&V0)[8], float2 (&V1)[8],
+                                             float (&w)[8], float nul, float tol2, bool& rotated, int q) {
   float g[8];
-  g[0] = A[P0].x * A[Q0].x + A[P0].y * A[Q0].y; g[1] = A[P0].x * A[Q0].y - A[P0].y * A[Q0].x;
-  g[2] = A[P1].x * A[Q1].x + A[P1].y * A[Q1].y; g[3] = A[P1].x * A[Q1].y - A[P1].y * A[Q1].x;
-  g[4] = A[P2].x * A[Q2].x + A[P2].y * A[Q2].y; g[5] = A[P2].x * A[Q2].y - A[P2].y * A[Q2].x;
-  g[6] = A[P3].x * A[Q3].x + A[P3].y * A[Q3].y; g[7] = A[P3].x * A[Q3].y - A[P3].y * A[Q3].x;
-  const bool b2 = r & 4, b1 = r & 2, b0 = r & 1;
+  BQA_GAMMA(P0, Q0, g[0], g[1])
+  BQA_GAMMA(P1, Q1, g[2], g[3])
+  BQA_GAMMA(P2, Q2, g[4], g[5])
+  BQA_GAMMA(P3, Q3, g[6], g[7])
+  const bool b1 = q & 2, b0 = q & 1;
   float h[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float send = b2 ? g[i] : g[4 + i], keep = b2 ? g[4 + i] : g[i];
-    h[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  for (int i = 0; i < 4; ++i) {                             // reduce-scatter over the 4 lanes: 6 shuffles
+    const float send = b1 ? g[i] : g[4 + i], keep = b1 ? g[4 + i] : g[i];
+    h[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
   }
-  float k2[2];
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const float send = b1 ? h[i] : h[2 + i], keep = b1 ? h[2 + i] : h[i];
-    k2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  }
-  const float mine = (b0 ? k2[1] : k2[0]) + __shfl_xor_sync(0xffffffffu, b0 ? k2[0] : k2[1], 1);   // component r
-  const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
-  const float gr = b0 ? other : mine, gi = b0 ? mine : other;
-  // column norms of this lane's pair k = r / 2
-  const float al = b2 ? (b1 ? w[P3] : w[P2]) : (b1 ? w[P1] : w[P0]);
-  const float be = b2 ? (b1 ? w[Q3] : w[Q2]) : (b1 ? w[Q1] : w[Q0]);
-  const Rot mineR = rot_params(al, be, gr, gi, nul, tol2, rotated);
-  const int base = (threadIdx.x & 31) & ~7;
+  const float gr = (b0 ? h[2] : h[0]) + __shfl_xor_sync(0xffffffffu, b0 ? h[0] : h[2], 1);
+  const float gi = (b0 ? h[3] : h[1]) + __shfl_xor_sync(0xffffffffu, b0 ? h[1] : h[3], 1);
+  // lane q now holds the inner product of pair q; its column norms:
+  const float al = b1 ? (b0 ? w[P3] : w[P2]) : (b0 ? w[P1] : w[P0]);
+  const float be = b1 ? (b0 ? w[Q3] : w[Q2]) : (b0 ? w[Q1] : w[Q0]);
+  const Rot mine = rot_params(al, be, gr, gi, nul, tol2, rotated);
+  const int base = (threadIdx.x & 31) & ~3;
   Rot R[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    R[k].c = __shfl_sync(0xffffffffu, mineR.c, base + 2 * k);
-    R[k].s = __shfl_sync(0xffffffffu, mineR.s, base + 2 * k);
-    R[k].phx = __shfl_sync(0xffffffffu, mineR.phx, base + 2 * k);
-    R[k].phy = __shfl_sync(0xffffffffu, mineR.phy, base + 2 * k);
-    R[k].dw = __shfl_sync(0xffffffffu, mineR.dw, base + 2 * k);
+    R[k].c = __shfl_sync(0xffffffffu, mine.c, base + k);
+    R[k].s = __shfl_sync(0xffffffffu, mine.s, base + k);
+    R[k].phx = __shfl_sync(0xffffffffu, mine.phx, base + k);
+    R[k].phy = __shfl_sync(0xffffffffu, mine.phy, base + k);
+    R[k].dw = __shfl_sync(0xffffffffu, mine.dw, base + k);
   }
-  apply_rot<P0, Q0>(A, V, w, R[0]);
-  apply_rot<P1, Q1>(A, V, w, R[1]);
-  apply_rot<P2, Q2>(A, V, w, R[2]);
-  apply_rot<P3, Q3>(A, V, w, R[3]);
+  apply_rot<P0, Q0>(A0, A1, V0, V1, w, R[0]);
+  apply_rot<P1, Q1>(A0, A1, V0, V1, w, R[1]);
+  apply_rot<P2, Q2>(A0, A1, V0, V1, w, R[2]);
+  apply_rot<P3, Q3>(A0, A1, V0, V1, w, R[3]);
 }
 
-// one-sided Jacobi SVD: on exit A = U diag(sigma) (row of this lane), V = right singular vectors (row of this
-// lane), w = sigma^2 per column (all lanes).  Code size matters here (the instruction cache is 32 KB and the
-// warps of an SM sit at different points of the kernel): a sweep is ONE round body executed 7 times, with the
-// columns 1..7 rotated through the registers between rounds (circle method: pairs (0,7) (1,6) (2,5) (3,4) by
-// position); after 7 rounds every pair has met once and the columns are back in place.
-__device__ __forceinline__ void jacobi8(float2 (&A)[8], float2 (&V)[8], float (&w)[8], int r, int& sweeps) {
+// one-sided Jacobi SVD: on exit A = U diag(sigma) (rows q, q + 4 of this lane), V = right singular vectors (same
+// rows), w = sigma^2 per column (all lanes).  A sweep is ONE round body executed 7 times, with the columns 1..7
+// rotated through the registers between rounds (circle method: pairs (0,7) (1,6) (2,5) (3,4) by position); after
+// 7 rounds every pair has met once and the columns are back in place.
+__device__ __forceinline__ void jacobi8(float2 (&A0)[8], float2 (&A1)[8], float2 (&V0)[8], float2 (&V1)[8],
+                                        float (&w)[8], int q, int& sweeps) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) V[j] = make_float2(j == r ? 1.f : 0.f, 0.f);
+  for (int j = 0; j < 8; ++j) {
+    V0[j] = make_float2(j == q ? 1.f : 0.f, 0.f);
+    V1[j] = make_float2(j == q + 4 ? 1.f : 0.f, 0.f);
+  }
   const float eps = 1.1920929e-07f;
   const float tol = eps * 2.f * 2.8284271f;                 // eps * 2 * sqrt(n), like the generic kernel
   const float tol2 = tol * tol;
-  col_norms(A, w);
+  col_norms(A0, A1, w);
   const float fro2 = ((w[0] + w[1]) + (w[2] + w[3])) + ((w[4] + w[5]) + (w[6] + w[7]));
   const float nul = eps * eps * fro2;                       // columns below eps |A|_F are numerically zero
 #pragma unroll 1
@@ -160,14 +166,14 @@ __device__ __forceinline__ void jacobi8(float2 (&A)[8], float2 (&V)[8], float (&
     bool rotated = false;
 #pragma unroll 1
     for (int round = 0; round < 7; ++round) {
-      jacobi_round<0, 7, 1, 6, 2, 5, 3, 4>(A, V, w, nul, tol2, rotated, r);
-      const float2 a7 = A[7], v7 = V[7];
+      jacobi_round<0, 7, 1, 6, 2, 5, 3, 4>(A0, A1, V0, V1, w, nul, tol2, rotated, q);
+      const float2 a7 = A0[7], b7 = A1[7], v7 = V0[7], u7 = V1[7];
       const float w7 = w[7];
 #pragma unroll
-      for (int j = 7; j > 1; --j) { A[j] = A[j - 1]; V[j] = V[j - 1]; w[j] = w[j - 1]; }
-      A[1] = a7; V[1] = v7; w[1] = w7;
+      for (int j = 7; j > 1; --j) { A0[j] = A0[j - 1]; A1[j] = A1[j - 1]; V0[j] = V0[j - 1]; V1[j] = V1[j - 1]; w[j] = w[j - 1]; }
+      A0[1] = a7; A1[1] = b7; V0[1] = v7; V1[1] = u7; w[1] = w7;
     }
-    col_norms(A, w);                                        // exact norms once per sweep
+    col_norms(A0, A1, w);                                   // exact norms once per sweep
     ++sweeps;
     if (!__any_sync(0xffffffffu, rotated)) break;
   }
@@ -182,161 +188,190 @@ __device__ __forceinline__ void load_row(float2 (&A)[8], const float2* src) {
     A[2 * i + 1] = make_float2(v.z, v.w);
   }
 }
+__device__ __forceinline__ void lds_row(float2 (&A)[8], const unsigned char* src) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 v = *reinterpret_cast<const float4*>(src + 16 * i);
+    A[2 * i] = make_float2(v.x, v.y);
+    A[2 * i + 1] = make_float2(v.z, v.w);
+  }
+}
 __device__ __forceinline__ void sts_row(unsigned char* dst, const float2 (&A)[8]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i)
     *reinterpret_cast<float4*>(dst + 16 * i) = make_float4(A[2 * i].x, A[2 * i].y, A[2 * i + 1].x, A[2 * i + 1].y);
 }
+// element `idx` (0..3 or 4..7 selected by `hi`) of an 8-vector that every lane holds in registers
+__device__ __forceinline__ float pick(const float (&w)[8], int q, bool hi) {
+  const float a = hi ? w[4] : w[0], b = hi ? w[5] : w[1], c = hi ? w[6] : w[2], d = hi ? w[7] : w[3];
+  return (q & 2) ? ((q & 1) ? d : c) : ((q & 1) ? b : a);
+}
 
-__global__ void __launch_bounds__(kWarps * 32) k_canon8(long long L, const float2* __restrict__ ext,
+__global__ void __launch_bounds__(kWarps * 32, 3) k_canon8(long long L, const float2* __restrict__ ext,
                                                         float2* __restrict__ canon, float* __restrict__ lmbds,
                                                         float* __restrict__ colmax, float pinv_eps, int ncols) {
   __shared__ __align__(16) unsigned char smem[kWarps * kWarpBytes];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int eg = lane >> 3, r = lane & 7;                   // edge slot in the warp, row owned by this lane
+  const int eg = lane >> 2, q = lane & 3;                   // edge slot in the warp; this lane owns rows q and q + 4
+  const int r0 = q, r1 = q + 4;
   unsigned char* tile0 = smem + wib * kWarpBytes + eg * kEdgeBytes;
   unsigned char* tile1 = tile0 + kMat;
   float* seig = reinterpret_cast<float*>(tile0 + 2 * kMat);            // eigenvalues of m_f (8) and m_b (8)
   float* ssig = seig + 16;
   int* scol = reinterpret_cast<int*>(ssig + 8);
-  const long long groups = (L + 3) >> 2;
+  const long long groups = (L + kEdges - 1) / kEdges;
   const long long nwarps = (long long)gridDim.x * kWarps;
-  float cm = 0.f;                                           // running max of lambda[:, r] over this lane's edges
+  float cm0 = 0.f, cm1 = 0.f;                               // running max of lambda[:, q] and lambda[:, q + 4]
   int n_sweeps = 0, n_jac = 0, n_ker = 0;
   for (long long g = (long long)blockIdx.x * kWarps + wib; g < groups; g += nwarps) {
-    long long e = g * 4 + eg;
+    long long e = g * kEdges + eg;
     const bool live = e < L;
     e = live ? e : L - 1;
-    float2 A[8], W[8];
+    float2 A0[8], A1[8], W0[8], W1[8];
     float sk[8];
     // m = 0: eigenvectors of m_f -> tile0, m = 1: eigenvectors of m_b -> tile1, m = 2: SVD of ker
 #pragma unroll 1
     for (int m = 0; m < 3; ++m) {
       if (m < 2) {
-        load_row(A, ext + (size_t)(e + (m ? L : 0)) * 64 + r * 8);
+        const float2* src = ext + (size_t)(e + (m ? L : 0)) * 64;
+        load_row(A0, src + r0 * 8);
+        load_row(A1, src + r1 * 8);
       } else {
-        // ker[i][j] = sqrt(sf_i sb_j) sum_k conj(Vf[k][i]) conj(Vb[k][j]) with masked eigenvalues: lane i takes
-        // column i of Vf and whole rows of Vb from the tiles
-        const float ef = seig[r];
-        const float rsf = ef > pinv_eps ? sqrtf(ef) : 0.f;
+        // ker[i][j] = sqrt(sf_i sb_j) sum_k conj(Vf[k][i]) conj(Vb[k][j]) with masked eigenvalues: this lane builds
+        // rows i = q, q + 4 from columns q, q + 4 of Vf and whole rows of Vb in the tiles
+        const float ef0 = seig[r0], ef1 = seig[r1];
+        const float rsf0 = ef0 > pinv_eps ? sqrtf(ef0) : 0.f, rsf1 = ef1 > pinv_eps ? sqrtf(ef1) : 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) A[j] = make_float2(0.f, 0.f);
+        for (int j = 0; j < 8; ++j) { A0[j] = make_float2(0.f, 0.f); A1[j] = make_float2(0.f, 0.f); }
 #pragma unroll 2
         for (int k = 0; k < 8; ++k) {
-          const float2 vf = *reinterpret_cast<const float2*>(tile0 + k * kRow + r * 8);
+          const float2 vf0 = *reinterpret_cast<const float2*>(tile0 + k * kRow + r0 * 8);
+          const float2 vf1 = *reinterpret_cast<const float2*>(tile0 + k * kRow + r1 * 8);
           float2 row[8];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 v = *reinterpret_cast<const float4*>(tile1 + k * kRow + 16 * i);
-            row[2 * i] = make_float2(v.x, v.y);
-            row[2 * i + 1] = make_float2(v.z, v.w);
-          }
+          lds_row(row, tile1 + k * kRow);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {                     // conj(vf) conj(vb) = conj(vf vb)
-            A[j].x += vf.x * row[j].x - vf.y * row[j].y;
-            A[j].y -= vf.x * row[j].y + vf.y * row[j].x;
+            A0[j].x += vf0.x * row[j].x - vf0.y * row[j].y;
+            A0[j].y -= vf0.x * row[j].y + vf0.y * row[j].x;
+            A1[j].x += vf1.x * row[j].x - vf1.y * row[j].y;
+            A1[j].y -= vf1.x * row[j].y + vf1.y * row[j].x;
           }
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float eb = seig[8 + j];
-          const float sc = rsf * (eb > pinv_eps ? sqrtf(eb) : 0.f);
-          A[j].x *= sc; A[j].y *= sc;
+          const float sb = eb > pinv_eps ? sqrtf(eb) : 0.f;
+          A0[j].x *= rsf0 * sb; A0[j].y *= rsf0 * sb;
+          A1[j].x *= rsf1 * sb; A1[j].y *= rsf1 * sb;
         }
       }
       const int before = n_sweeps;
-      jacobi8(A, W, sk, r, n_sweeps);
+      jacobi8(A0, A1, W0, W1, sk, q, n_sweeps);
       if (m == 2) n_ker += n_sweeps - before;
       if (m < 2) {
-        float mine = sk[0];
-#pragma unroll
-        for (int j = 1; j < 8; ++j) mine = (r == j) ? sk[j] : mine;
         unsigned char* tile = m ? tile1 : tile0;
         __syncwarp();
-        sts_row(tile + r * kRow, W);
-        seig[m * 8 + r] = sqrtf(mine);                      // eigenvalue = singular value of the PSD message
+        sts_row(tile + r0 * kRow, W0);
+        sts_row(tile + r1 * kRow, W1);
+        seig[m * 8 + r0] = sqrtf(pick(sk, q, false));       // eigenvalue = singular value of the PSD message
+        seig[m * 8 + r1] = sqrtf(pick(sk, q, true));
         __syncwarp();
       }
     }
     n_jac += 3;
     // this lane's rows of V_f L_f^-1/2 and V_b L_b^-1/2 (masked like pinv_raw, backends.py:719-727)
-    float2 Vf[8], Vb[8];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4 a = *reinterpret_cast<const float4*>(tile0 + r * kRow + 16 * i);
-      const float4 b = *reinterpret_cast<const float4*>(tile1 + r * kRow + 16 * i);
-      Vf[2 * i] = make_float2(a.x, a.y); Vf[2 * i + 1] = make_float2(a.z, a.w);
-      Vb[2 * i] = make_float2(b.x, b.y); Vb[2 * i + 1] = make_float2(b.z, b.w);
-    }
+    float2 Vf0[8], Vf1[8], Vb0[8], Vb1[8];
+    lds_row(Vf0, tile0 + r0 * kRow);
+    lds_row(Vf1, tile0 + r1 * kRow);
+    lds_row(Vb0, tile1 + r0 * kRow);
+    lds_row(Vb1, tile1 + r1 * kRow);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float ef = seig[j], eb = seig[8 + j];
       const float isf = (ef > pinv_eps && sqrtf(ef) > 1.1920929e-07f) ? rsqrtf(ef) : 0.f;
       const float isb = (eb > pinv_eps && sqrtf(eb) > 1.1920929e-07f) ? rsqrtf(eb) : 0.f;
-      Vf[j].x *= isf; Vf[j].y *= isf;
-      Vb[j].x *= isb; Vb[j].y *= isb;
+      Vf0[j].x *= isf; Vf0[j].y *= isf; Vf1[j].x *= isf; Vf1[j].y *= isf;
+      Vb0[j].x *= isb; Vb0[j].y *= isb; Vb1[j].x *= isb; Vb1[j].y *= isb;
     }
     // sort the singular values (descending, stable) and publish A = U S and W through the tiles
-    float mine = sk[0];
+    const float mine0 = pick(sk, q, false), mine1 = pick(sk, q, true);
+    int rank0 = 0, rank1 = 0;
 #pragma unroll
-    for (int j = 1; j < 8; ++j) mine = (r == j) ? sk[j] : mine;
-    int rank = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) rank += (sk[j] > mine || (sk[j] == mine && j < r)) ? 1 : 0;
+    for (int j = 0; j < 8; ++j) {
+      rank0 += (sk[j] > mine0 || (sk[j] == mine0 && j < r0)) ? 1 : 0;
+      rank1 += (sk[j] > mine1 || (sk[j] == mine1 && j < r1)) ? 1 : 0;
+    }
     __syncwarp();
-    ssig[rank] = sqrtf(mine);
-    scol[rank] = r;
-    sts_row(tile0 + r * kRow, A);
-    sts_row(tile1 + r * kRow, W);
+    ssig[rank0] = sqrtf(mine0); scol[rank0] = r0;
+    ssig[rank1] = sqrtf(mine1); scol[rank1] = r1;
+    sts_row(tile0 + r0 * kRow, A0);
+    sts_row(tile0 + r1 * kRow, A1);
+    sts_row(tile1 + r0 * kRow, W0);
+    sts_row(tile1 + r1 * kRow, W1);
     __syncwarp();
     // lambda = masked S / |masked S|
-    float nrm2 = 0.f, my_s = 0.f;
+    float nrm2 = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float s = ssig[j];
       const float sm = s > pinv_eps ? s : 0.f;
       nrm2 += sm * sm;
-      my_s = (r == j) ? sm : my_s;
     }
-    const float lam = my_s / sqrtf(nrm2);
+    const float inrm = 1.f / sqrtf(nrm2);
+    const float s0 = ssig[r0], s1 = ssig[r1];
+    const float lam0 = (s0 > pinv_eps ? s0 : 0.f) * inrm, lam1 = (s1 > pinv_eps ? s1 : 0.f) * inrm;
     if (live) {
-      lmbds[(size_t)e * 8 + r] = lam;
-      cm = fmaxf(cm, lam);
+      lmbds[(size_t)e * 8 + r0] = lam0;
+      lmbds[(size_t)e * 8 + r1] = lam1;
+      cm0 = fmaxf(cm0, lam0);
+      cm1 = fmaxf(cm1, lam1);
     }
     // C_f[r][c] = sum_i Vf[r][i] isf_i U[i][col_c],  U[i][col] = A[i][col] / S_col   (slot e + L)
     // C_b[r][c] = sum_j Vb[r][j] isb_j conj(W[j][col_c])                               (slot e)
     for (int c = 0; c < ncols; c += 2) {
-      float2 cf[2], cb[2];
+      float2 cf0[2], cf1[2], cb0[2], cb1[2];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int cc = c + h < 8 ? c + h : 7;
         const int col = scol[cc];
         const float s = ssig[cc];
-        float2 f = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
+        float2 f0 = make_float2(0.f, 0.f), f1 = f0, b0 = f0, b1 = f0;
         if (s > pinv_eps) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float2 u = *reinterpret_cast<const float2*>(tile0 + i * kRow + col * 8);
             const float2 w = *reinterpret_cast<const float2*>(tile1 + i * kRow + col * 8);
-            f.x += Vf[i].x * u.x - Vf[i].y * u.y; f.y += Vf[i].x * u.y + Vf[i].y * u.x;
-            b.x += Vb[i].x * w.x + Vb[i].y * w.y; b.y += Vb[i].y * w.x - Vb[i].x * w.y;     // times conj(w)
+            f0.x += Vf0[i].x * u.x - Vf0[i].y * u.y; f0.y += Vf0[i].x * u.y + Vf0[i].y * u.x;
+            f1.x += Vf1[i].x * u.x - Vf1[i].y * u.y; f1.y += Vf1[i].x * u.y + Vf1[i].y * u.x;
+            b0.x += Vb0[i].x * w.x + Vb0[i].y * w.y; b0.y += Vb0[i].y * w.x - Vb0[i].x * w.y;     // times conj(w)
+            b1.x += Vb1[i].x * w.x + Vb1[i].y * w.y; b1.y += Vb1[i].y * w.x - Vb1[i].x * w.y;
           }
           const float is = 1.f / s;
-          f.x *= is; f.y *= is;
+          f0.x *= is; f0.y *= is; f1.x *= is; f1.y *= is;
         }
-        cf[h] = f; cb[h] = b;
+        cf0[h] = f0; cf1[h] = f1; cb0[h] = b0; cb1[h] = b1;
       }
       if (live) {
-        *reinterpret_cast<float4*>(canon + (size_t)(e + L) * 64 + r * 8 + c) = make_float4(cf[0].x, cf[0].y, cf[1].x, cf[1].y);
-        *reinterpret_cast<float4*>(canon + (size_t)e * 64 + r * 8 + c) = make_float4(cb[0].x, cb[0].y, cb[1].x, cb[1].y);
+        float2* cf = canon + (size_t)(e + L) * 64 + c;
+        float2* cb = canon + (size_t)e * 64 + c;
+        *reinterpret_cast<float4*>(cf + r0 * 8) = make_float4(cf0[0].x, cf0[0].y, cf0[1].x, cf0[1].y);
+        *reinterpret_cast<float4*>(cf + r1 * 8) = make_float4(cf1[0].x, cf1[0].y, cf1[1].x, cf1[1].y);
+        *reinterpret_cast<float4*>(cb + r0 * 8) = make_float4(cb0[0].x, cb0[0].y, cb0[1].x, cb0[1].y);
+        *reinterpret_cast<float4*>(cb + r1 * 8) = make_float4(cb1[0].x, cb1[0].y, cb1[1].x, cb1[1].y);
       }
     }
     __syncwarp();
   }
   // column-wise max of lambda over all edges (truncate_lmbds, backends.py:297-299)
-  cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 8));
-  cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 16));
-  if (lane < 8) atomicMax(reinterpret_cast<unsigned int*>(colmax + lane), __float_as_uint(cm));
+#pragma unroll
+  for (int o = 4; o < 32; o <<= 1) {
+    cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, o));
+    cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, o));
+  }
+  if (lane < 4) {
+    atomicMax(reinterpret_cast<unsigned int*>(colmax + lane), __float_as_uint(cm0));
+    atomicMax(reinterpret_cast<unsigned int*>(colmax + lane + 4), __float_as_uint(cm1));
+  }
   if (lane == 0) {
     atomicAdd(&g_stats[0], (unsigned long long)n_jac);
     atomicAdd(&g_stats[1], (unsigned long long)n_sweeps);
@@ -356,7 +391,7 @@ int launch_fast_canon8(long long L, const void* ext, void* canon, void* lmbds, v
   if (L == 0) return 0;
   if (ncols < 1 || ncols > 8) return set_error("canonicalize: %d canonicalizer columns requested for n = 8", ncols);
   ncols = (ncols + 1) & ~1;
-  const long long groups = (L + 3) / 4;
+  const long long groups = (L + kEdges - 1) / kEdges;
   long long grid = (groups + kWarps - 1) / kWarps;
   const long long cap = 148LL * 16;
   if (grid > cap) grid = cap;

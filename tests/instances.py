@@ -115,3 +115,27 @@ def random_node_batch(B: int, d: int, D: int, seed: int):
     msgs = [random_psd_msgs(rng, B, D) for _ in range(d)]
     thetas = [rng.uniform(-1.0, 1.0, size=B) for _ in range(d)]
     return t, msgs, thetas
+
+
+def cfg_isolated_qubit():
+    """A path 0-1-2 plus the isolated qubit 3 (degree 0).  The reference compiles such a config
+    (tests/test_config_to_context.py:68-75) but asserts in get_density_matrices; here the
+    isolated qubit simply follows its single-qubit Rz/Rx evolution."""
+    return {"nodes": {0: 0.3, 1: -0.2, 2: 0.5, 3: 0.7}, "edges": {(0, 1): 0.8, (1, 2): -0.4}, "max_bond_dim": 4,
+            "schedule": _anneal(1.0, 5, ["get_bloch_vectors", "measure"])}
+
+
+def isolated_qubit_bloch(cfg, node=3):
+    """|-> evolved by Rx(xt) Rz(h zt) per step (reference gate conventions, exact_sim.py:36-63)."""
+    import math
+    from bqa_b200.config import config_to_context
+    h = cfg["nodes"][node]
+    psi = np.array([1.0, -1.0], complex) / np.sqrt(2.0)
+    for ins in config_to_context(cfg).instructions:
+        if isinstance(ins, dict):
+            phi, xt = h * ins["ztime"], ins["xtime"]
+            rz = np.diag([np.exp(-1j * phi), np.exp(1j * phi)])
+            rx = np.array([[math.cos(xt), -1j * math.sin(xt)], [-1j * math.sin(xt), math.cos(xt)]])
+            psi = rx @ rz @ psi
+    rho = np.outer(psi, psi.conj())
+    return np.array([(rho[0, 1] + rho[1, 0]).real, (rho[1, 0] - rho[0, 1]).imag, (rho[0, 0] - rho[1, 1]).real])

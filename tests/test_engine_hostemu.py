@@ -206,3 +206,12 @@ def test_random_regular_400_lockstep_with_oracle(emu):
         olm = np.sort(np.real(ost.lmbds), axis=1)[:, ::-1]
         assert np.abs(lm - olm).max() < 1e-10
         assert np.abs(eng.bloch_vectors() - O.bloch_vectors(O.density_matrices(octx, ost))).max() < 1e-10
+
+
+def test_isolated_qubit_follows_single_qubit_evolution(emu):
+    """Degree-0 class (edge case the reference compiles but cannot run): exact single-qubit result, and the sampler
+    terminates with an outcome for every qubit."""
+    cfg = instances.cfg_isolated_qubit()
+    res, _ = _run(cfg, emu, "double")
+    assert np.abs(np.array(res["bloch_vectors"])[3] - instances.isolated_qubit_bloch(cfg)).max() < 1e-12
+    assert sorted(set(res["measurement_outcomes"])) <= [-1, 1] and len(res["measurement_outcomes"]) == 4

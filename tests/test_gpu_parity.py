@@ -389,3 +389,19 @@ def test_config1_maxcut_shape_double_vs_oracle(lib):
            "schedule": {"total_time": 24.0, "starting_mixing": 1.0,
                         "actions": [{"weight": 1.0, "steps_number": 120, "final_mixing": 0.88}, "get_bloch_vectors"]}}
     _oracle_vs_gpu(cfg, lib, 1e-6)
+
+
+@pytest.mark.parametrize("precision,tol", [("double", 1e-12), ("single", 1e-5)])
+def test_isolated_qubit_gpu(lib, precision, tol):
+    """Degree-0 class on the GPU: the isolated qubit follows its exact single-qubit evolution; the other qubits
+    equal the oracle run on the connected part."""
+    from oracle import bqa_oracle as O
+    cfg = instances.cfg_isolated_qubit()
+    res, _ = _run(cfg, precision)
+    b = np.array(res["bloch_vectors"])
+    assert np.abs(b[3] - instances.isolated_qubit_bloch(cfg)).max() < tol
+    connected = {**cfg, "nodes": {k: v for k, v in cfg["nodes"].items() if k != 3},
+                 "schedule": {**cfg["schedule"], "actions": cfg["schedule"]["actions"][:2]}}
+    want = np.array(dict(O.run_qa(connected))["bloch_vectors"])
+    assert np.abs(b[:3] - want).max() < (1e-9 if precision == "double" else 5e-4)
+    assert len(res["measurement_outcomes"]) == 4

@@ -207,7 +207,7 @@ __device__ __forceinline__ float pick(const float (&w)[8], int q, bool hi) {
   return (q & 2) ? ((q & 1) ? d : c) : ((q & 1) ? b : a);
 }
 
-__global__ void __launch_bounds__(kWarps * 32, 3) k_canon8(long long L, const float2* __restrict__ ext,
+__global__ void __launch_bounds__(kWarps * 32, 4) k_canon8(long long L, const float2* __restrict__ ext,
                                                         float2* __restrict__ canon, float* __restrict__ lmbds,
                                                         float* __restrict__ colmax, float pinv_eps, int ncols) {
   __shared__ __align__(16) unsigned char smem[kWarps * kWarpBytes];

@@ -19,6 +19,8 @@ SIGNATURES = {
     "bqa_b200_ext_msgs_p2p": [_i, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _d, _vp, _sz, _vp, _vp, _vp],
     "bqa_b200_sweep_sync": [_i, _i, _i, _vp, _i, _vp, C.c_uint, _vp, _vp],
     "bqa_b200_gauge_msgs": [_i, _i, _i, _ll, _vp, _vp, _vp],
+    "bqa_b200_bp_run": [_i, _i, _i, _ll, _vp, _vp, _vp, _i, _vp, _vp, _d, _d, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp,
+                        C.c_uint, _vp],
     "bqa_b200_bp_sweep": [_i, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp, _d, _i, _d, _i, _vp, _vp, _vp, _sz, _vp],
     "bqa_b200_ext_msgs": [_i, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _d, _vp, _sz, _vp],
     "bqa_b200_canonicalize": [_i, _i, _ll, _vp, _vp, _vp, _vp, _d, _i, _vp],
@@ -52,8 +54,11 @@ class Library:
     def _checked(self, name, fn):
         def call(*args):
             rc = fn(*args)
+            if rc == 2 and name == "bqa_b200_bp_run":
+                return False                  # no single-launch kernel for this shape: not an error
             if rc != 0:
                 raise RuntimeError(f"{name}: {self._dll.bqa_b200_last_error().decode()}")
+            return True
         call.__name__ = name
         return call
 

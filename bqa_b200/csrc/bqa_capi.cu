@@ -112,6 +112,22 @@ int bqa_b200_ext_msgs(int prec, int degree, int D, long long B, const void* T, c
                                workspace_bytes, nullptr, nullptr, stream);
 }
 
+int bqa_b200_bp_run(int prec, int degree, int D, long long B, const void* T, void* msgs0, void* msgs1, int parity,
+                    const int32_t* in_pos, const int32_t* out_pos, double damping, double bp_eps, int max_iters,
+                    void* resid, int32_t* status, const int32_t* remote_pos, void* const* peers0, void* const* peers1,
+                    int rank, int world, void* const* peer_resid, void* const* peer_flags, unsigned seq_base,
+                    void* stream) {
+  if (int rc = check_shape(prec, degree, D)) return rc;
+  if (max_iters < 1) return set_error("max_iters must be positive, got %d", max_iters);
+  if (g_kernel_mode.load() != 0 || !fast_d3D4_available(prec, degree, D)) {
+    set_error("bp_run: no single-launch kernel for precision %d, degree %d, D = %d", prec, degree, D);
+    return 2;                                              /* not an error: the caller enqueues bqa_b200_bp_sweep calls */
+  }
+  return launch_fast_bp_run_d3D4(B, T, msgs0, msgs1, parity, in_pos, out_pos, damping, bp_eps, max_iters, resid, status,
+                                 remote_pos, peers0, peers1, rank, world, peer_resid, peer_flags, seq_base,
+                                 (cudaStream_t)stream);
+}
+
 int bqa_b200_gauge_msgs(int prec, int D_old, int D_new, long long L, const void* lmbds, void* msgs_out, void* stream) {
   if (int rc = check_shape(prec, 0, D_old)) return rc;
   if (D_new < 1 || D_new > 2 * D_old || D_new > BQA_MAX_D) return set_error("new bond dimension %d invalid for D = %d", D_new, D_old);

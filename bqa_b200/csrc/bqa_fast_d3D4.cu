@@ -111,17 +111,9 @@ __device__ __forceinline__ int load_rpos(const Args& a, long long node0, int lan
   return v;
 }
 
+// One sweep (or one extended-message pass) over the degree class by this CTA's warps.
 template <bool EXT>
-__global__ void __launch_bounds__(kThreads, 1) k_msgs_d3D4(Args a) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  if (!EXT && a.it > 0) {                                   // device-side early exit after convergence
-    if (*((volatile int32_t*)a.status) != 0) return;
-    const float num = a.resid[2 * (a.it - 1)], den = a.resid[2 * (a.it - 1) + 1];
-    if (sqrtf(num / den) < a.bp_eps) {
-      if (threadIdx.x == 0) { a.status[1] = a.it; __threadfence(); a.status[0] = 1; }
-      return;
-    }
-  }
+__device__ __forceinline__ void sweep(const Args& a, unsigned char* smem) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int s = lane >> 3, t = lane & 7, p = t >> 2, la = t & 3;     // node slot, lane in node, physical, leg-0 index
   unsigned char* wbase = smem + wib * kWarpBytes;
@@ -374,6 +366,107 @@ __global__ void __launch_bounds__(kThreads, 1) k_msgs_d3D4(Args a) {
   }
 }
 
+template <bool EXT>
+__global__ void __launch_bounds__(kThreads, 1) k_msgs_d3D4(Args a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  if (!EXT && a.it > 0) {                                   // device-side early exit after convergence
+    if (*((volatile int32_t*)a.status) != 0) return;
+    const float num = a.resid[2 * (a.it - 1)], den = a.resid[2 * (a.it - 1) + 1];
+    if (sqrtf(num / den) < a.bp_eps) {
+      if (threadIdx.x == 0) { a.status[1] = a.it; __threadfence(); a.status[0] = 1; }
+      return;
+    }
+  }
+  sweep<EXT>(a, smem);
+}
+
+// ---- whole BP run in ONE cooperative launch (reference _run_bp, state.py:97-124) ----------------------------------
+// The persistent CTAs (one per SM, all co-resident) iterate: sweep -> grid barrier -> (multi-GPU: CTA 0 pushes the
+// residual maxima to the peers and runs the cross-GPU flag barrier, like bqa_sync.cu) -> every CTA reads the global
+// residual and stops or goes on.  No kernel launch and no host round trip per sweep.
+struct RunArgs {
+  Args base;                       // msgs_cur / msgs_out / peers / it / write_undamped are filled per sweep
+  float2* msgs[2];                 // ping-pong message buffers; sweep `it` reads msgs[(parity + it) & 1]
+  unsigned char* peers[2][BQA_MAX_PEERS];
+  int parity, max_iters;
+  int rank, world;                 // world == 1: single GPU
+  float* peer_resid[BQA_MAX_PEERS];
+  unsigned* peer_flags[BQA_MAX_PEERS];
+  unsigned seq_base;               // cross-GPU barrier sequence numbers seq_base + 1, + 2, ... (one per sweep)
+};
+
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// all CTAs of the grid; `counter` only grows (zeroed by the host before the launch); status[3] != 0 aborts everyone
+__device__ __forceinline__ bool grid_barrier(unsigned* counter, unsigned& generation, volatile int32_t* status) {
+  __syncthreads();
+  __shared__ int ok;
+  if (threadIdx.x == 0) {
+    ok = 1;
+    __threadfence();
+    ++generation;
+    atomicAdd(counter, 1u);
+    const unsigned target = generation * gridDim.x;
+    const long long t0 = clock64();
+    while (ld_acquire_gpu_u32(counter) < target) {
+      if (status[3] != 0 || clock64() - t0 > 20000000000LL) { status[3] = 1; ok = 0; break; }
+    }
+  }
+  __syncthreads();
+  return ok != 0;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) k_bp_run_d3D4(RunArgs r) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  Args a = r.base;
+  unsigned* counter = reinterpret_cast<unsigned*>(a.status + 2);
+  unsigned generation = 0;
+  int sweeps = r.max_iters, converged = 0;
+  for (int it = 0; it < r.max_iters; ++it) {
+    const int cur = (r.parity + it) & 1;
+    a.msgs_cur = r.msgs[cur];
+    a.msgs_out = r.msgs[cur ^ 1];
+#pragma unroll
+    for (int q = 0; q < BQA_MAX_PEERS; ++q) a.peers[q] = r.peers[cur ^ 1][q];
+    a.it = it;
+    a.write_undamped = it == r.max_iters - 1;               // cap reached: the undamped sweep is kept (state.py:122-123)
+    sweep<false>(a, smem);
+    if (!grid_barrier(counter, generation, a.status)) return;
+    if (r.world > 1) {
+      if (blockIdx.x == 0 && threadIdx.x < r.world && (int)threadIdx.x != r.rank) {
+        const int q = threadIdx.x;
+        const unsigned* mine = reinterpret_cast<const unsigned*>(a.resid) + 2 * it;
+        unsigned* theirs = reinterpret_cast<unsigned*>(r.peer_resid[q]) + 2 * it;
+        atomicMax_system(theirs, ld_acquire_gpu_u32(mine));
+        atomicMax_system(theirs + 1, ld_acquire_gpu_u32(mine + 1));
+        __threadfence_system();
+        const unsigned seq = r.seq_base + it + 1;
+        st_release_sys_u32(r.peer_flags[q] + r.rank, seq);
+        const long long t0 = clock64();
+        while ((int)(ld_acquire_sys_u32(r.peer_flags[r.rank] + q) - seq) < 0) {
+          if (clock64() - t0 > 20000000000LL) { a.status[3] = 1; break; }
+        }
+      }
+      if (!grid_barrier(counter, generation, a.status)) return;
+    }
+    const float num = __ldcg(a.resid + 2 * it), den = __ldcg(a.resid + 2 * it + 1);
+    if (sqrtf(num / den) < a.bp_eps) { sweeps = it + 1; converged = 1; break; }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { a.status[1] = sweeps; a.status[0] = converged; }
+}
+
 static int sm_count() {                     // of the current device (a process may drive several)
   int dev = 0, n = 0;
   cudaGetDevice(&dev);
@@ -382,6 +475,45 @@ static int sm_count() {                     // of the current device (a process 
 }
 
 }  // namespace fast
+
+int launch_fast_bp_run_d3D4(long long B, const void* T, void* msgs0, void* msgs1, int parity, const int32_t* in_pos,
+                            const int32_t* out_pos, double damping, double bp_eps, int max_iters, void* resid,
+                            int32_t* status, const int32_t* remote_pos, void* const* peers0, void* const* peers1, int rank,
+                            int world, void* const* peer_resid, void* const* peer_flags, unsigned seq_base,
+                            cudaStream_t st) {
+  using namespace fast;
+  if (B == 0) return 0;
+  if (world < 1 || world > BQA_MAX_PEERS) return set_error("bp_run: world %d outside [1, %d]", world, BQA_MAX_PEERS);
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(k_bp_run_d3D4, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(k_bp_run_d3D4): %s", cudaGetErrorString(e));
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  RunArgs r{};
+  Args& a = r.base;
+  a.B = B; a.T = (const float2*)T; a.in_pos = in_pos; a.out_pos = out_pos;
+  a.damping = (float)damping; a.bp_eps = (float)bp_eps; a.resid = (float*)resid; a.status = status;
+  a.remote_pos = (world > 1 && peers0 && peers1) ? remote_pos : nullptr;
+  r.msgs[0] = (float2*)msgs0; r.msgs[1] = (float2*)msgs1;
+  r.parity = parity & 1; r.max_iters = max_iters; r.rank = rank; r.world = world; r.seq_base = seq_base;
+  for (int q = 0; q < BQA_MAX_PEERS; ++q) {
+    r.peers[0][q] = (a.remote_pos && peers0) ? (unsigned char*)peers0[q] : nullptr;
+    r.peers[1][q] = (a.remote_pos && peers1) ? (unsigned char*)peers1[q] : nullptr;
+    r.peer_resid[q] = (world > 1 && q < world) ? (float*)peer_resid[q] : nullptr;
+    r.peer_flags[q] = (world > 1 && q < world) ? (unsigned*)peer_flags[q] : nullptr;
+  }
+  const long long groups = (B + 3) / 4;
+  long long grid = (groups + kWarps - 1) / kWarps;
+  if (grid > sm_count()) grid = sm_count();
+  void* params[] = {&r};
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_bp_run_d3D4, dim3((unsigned)grid), dim3(kThreads), params,
+                                              (size_t)kSmem, st);
+  if (e != cudaSuccess) return set_error("cudaLaunchCooperativeKernel(k_bp_run_d3D4): %s", cudaGetErrorString(e));
+  return after_launch("bp_run(d3D4)");
+}
 
 bool fast_d3D4_available(int prec, int degree, int D) { return prec == 0 && degree == 3 && D == 4; }
 

@@ -103,6 +103,8 @@ class Engine:
         self.D = 1
         self.stats = {"bp_sweeps": [], "bp_dist": [], "bond_dims": [], "trunc_err": []}
         self._bp_chunk = 4
+        self._single_launch_ok = self.cuda and os.environ.get("BQA_B200_SINGLE_LAUNCH_BP", "1") != "0"
+        self._no_bp_run = {}         # bond dimension -> True once bqa_b200_bp_run reported "no kernel for this shape"
 
         self.classes: list[_DegreeClass] = []
         self._node_class = np.zeros(self.N, np.int64)
@@ -303,6 +305,39 @@ class Engine:
     def _before_bp(self) -> None:
         """Hook for the partitioned engine (orders the control-block reset against the peers' residual pushes)."""
 
+    def _bp_run_peers(self):
+        """(rank, world, peers0, peers1, peer_resid, peer_flags, seq_base) of the single-launch BP run; one GPU here."""
+        return 0, 1, None, None, None, None, 0
+
+    def _bp_run_done(self, sweeps: int) -> None:
+        """Hook for the partitioned engine (advances the cross-GPU barrier sequence)."""
+
+    def _try_single_launch_bp(self):
+        """The whole BP run in one cooperative launch (bqa_b200_bp_run) when every BP-active node sits in one degree
+        class with a specialised kernel; returns (converged, sweeps, resid) or None."""
+        active = [c for c in self.classes if c.degree > 0 and c.B > 0]
+        if len(active) != 1 or not self._single_launch_ok or self._no_bp_run.get(self.D):
+            return None
+        c = active[0]
+        peers = self._bp_run_peers()
+        if peers is None:
+            return None
+        rank, world, p0, p1, presid, pflags, seq = peers
+        ok = self.lib.bp_run(self.prec, c.degree, self.D, c.B, c.T[c.cur].data_ptr(), self._msgs[0].data_ptr(),
+                             self._msgs[1].data_ptr(), self._msgs_cur, c.in_pos.data_ptr(), c.out_pos.data_ptr(),
+                             self.damping, self.bp_eps, self.max_iters, self._resid.data_ptr(), self._status.data_ptr(),
+                             c.remote_pos.data_ptr(), p0, p1, rank, world, presid, pflags, seq, self._stream())
+        if not ok:
+            self._no_bp_run[self.D] = True
+            return None
+        ctrl = self._to_host(self._ctrl)
+        resid = ctrl[: self._ctrl_rbytes].view(self.np_rdtype).reshape(-1, 2)
+        status = ctrl[self._ctrl_rbytes:].view(np.int32)
+        if status[3]:
+            raise RuntimeError("BP run aborted: a grid or peer barrier timed out (bqa_b200_bp_run)")
+        self._bp_run_done(int(status[1]))
+        return bool(status[0]), int(status[1]), resid
+
     def run_bp(self) -> int:
         max_it = self.max_iters
         assert max_it > 0, "max_bp_iter_number must be positive"      # reference: assert best_msgs is not None
@@ -310,6 +345,10 @@ class Engine:
         self._ctrl.zero_()
         self._before_bp()
         eps = self.np_rdtype(self.bp_eps)
+        single = self._try_single_launch_bp()
+        if single is not None:
+            done, sweeps, resid = single
+            return self._finish_bp(done, sweeps, resid, max_it)
         it = 0
         done = False
         sweeps = max_it
@@ -330,6 +369,9 @@ class Engine:
                 with np.errstate(divide="ignore", invalid="ignore"):
                     if np.sqrt(num / den) < eps:
                         done, sweeps = True, it
+        return self._finish_bp(done, sweeps, resid, max_it)
+
+    def _finish_bp(self, done: bool, sweeps: int, resid, max_it: int) -> int:
         num, den = resid[sweeps - 1]
         with np.errstate(divide="ignore", invalid="ignore"):
             dist = float(np.sqrt(num / den))

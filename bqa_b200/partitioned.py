@@ -370,6 +370,15 @@ class PartitionedEngine(Engine):
         self.lib.sweep_sync(self.prec, self.rank, self.world, self._peer_ptrs["ctrl"], it, self._peer_ptrs["flags"],
                             self._seq, self._status.data_ptr(), self._stream())
 
+    def _bp_run_peers(self):
+        if not self.p2p:
+            return None                # the torch.distributed transport exchanges between sweeps: no single launch
+        pp = self._peer_ptrs
+        return self.rank, self.world, pp[("msgs", 0)], pp[("msgs", 1)], pp["ctrl"], pp["flags"], self._seq
+
+    def _bp_run_done(self, sweeps: int) -> None:
+        self._seq += sweeps            # one cross-GPU barrier per executed sweep, same count on every rank
+
     def _before_bp(self) -> None:
         if self.p2p:
             self._sync(-1)            # nobody pushes residuals of the new run before everybody has reset its block

@@ -89,6 +89,18 @@ int bqa_b200_ext_msgs_p2p(int prec, int degree, int D, long long B, const void* 
  * zero-initialised; seq: 1, 2, 3, ... per call.  A peer that never arrives sets status[3] after ~10 s. */
 int bqa_b200_sweep_sync(int prec, int rank, int world, void* const* peer_resid, int it, void* const* peer_flags,
                         unsigned seq, int32_t* status, void* stream);
+/* The whole BP run of a degree class in ONE cooperative launch (reference _run_bp, state.py:97-124): persistent CTAs
+ * iterate sweep -> grid barrier -> (world > 1: residual push + flag barrier with the peers) -> global residual test.
+ * Sweep `it` reads msgs{(parity + it) & 1} and writes the other buffer; on return status[0] = converged (0 / 1),
+ * status[1] = number of sweeps executed; status[2] (grid-barrier counter) and resid must be zero before the call.
+ * Only for graphs whose nodes all sit in ONE degree class that has a specialised kernel; returns 2 (and changes
+ * nothing) when there is none -- the caller then enqueues bqa_b200_bp_sweep[_p2p] calls.  peers0/peers1 = peer bases
+ * of the two message buffers; cross-GPU barrier sequence numbers used: seq_base + 1 ... seq_base + status[1]. */
+int bqa_b200_bp_run(int prec, int degree, int D, long long B, const void* T, void* msgs0, void* msgs1, int parity,
+                    const int32_t* in_pos, const int32_t* out_pos, double damping, double bp_eps, int max_iters,
+                    void* resid, int32_t* status, const int32_t* remote_pos, void* const* peers0, void* const* peers1,
+                    int rank, int world, void* const* peer_resid, void* const* peer_flags, unsigned seq_base,
+                    void* stream);
 /* msgs_out[p] = diag(lmbds[p mod L][:D_new]) / trace for every slot p < 2L (state.py:56-57); lmbds: real (L, 2 D_old) */
 int bqa_b200_gauge_msgs(int prec, int D_old, int D_new, long long L, const void* lmbds, void* msgs_out, void* stream);
 

@@ -405,3 +405,34 @@ def test_isolated_qubit_gpu(lib, precision, tol):
     want = np.array(dict(O.run_qa(connected))["bloch_vectors"])
     assert np.abs(b[:3] - want).max() < (1e-9 if precision == "double" else 5e-4)
     assert len(res["measurement_outcomes"]) == 4
+
+
+def test_single_launch_bp_run_equals_per_sweep_launches(lib):
+    """bqa_b200_bp_run (the whole BP loop in one cooperative launch with in-kernel grid barriers) against the
+    per-sweep launches of bqa_b200_bp_sweep: same arithmetic, so identical sweep counts, residuals and marginals."""
+    from bqa_b200.config import config_to_context
+    from bqa_b200.engine import Engine
+    cfg = _rr_config(3000, 24, 4.8, [])
+    ctx = config_to_context(cfg)
+    out = {}
+    for single in (False, True):
+        eng = Engine(ctx, precision="single")
+        eng._single_launch_ok = single
+        for ins in [i for i in ctx.instructions if isinstance(i, dict)]:
+            eng.run_layer(ins["xtime"], ins["ztime"])
+        out[single] = (eng.bloch_vectors(), eng.stats["bp_sweeps"], eng.stats["bp_dist"], eng.stats["bond_dims"])
+    assert out[True][3] == out[False][3] and out[True][3][-1] == 4
+    assert out[True][1] == out[False][1]
+    assert out[True][2] == out[False][2]
+    assert np.array_equal(out[True][0], out[False][0])
+    # a capped run (3 iterations, damping): the undamped last sweep is kept (state.py:122-123) on both paths
+    cfg = _rr_config(1000, 12, 2.4, [], max_bp_iter_number=3, damping=0.2)
+    ctx = config_to_context(cfg)
+    res = {}
+    for single in (False, True):
+        eng = Engine(ctx, precision="single")
+        eng._single_launch_ok = single
+        for ins in [i for i in ctx.instructions if isinstance(i, dict)]:
+            eng.run_layer(ins["xtime"], ins["ztime"])
+        res[single] = (eng.bloch_vectors(), eng.stats["bp_sweeps"])
+    assert res[True][1] == res[False][1] and np.array_equal(res[True][0], res[False][0])

@@ -333,6 +333,14 @@ class PartitionedEngine(Engine):
         self._recv_idx = {q: torch.from_numpy(plan.recv_slots[q]).to(dev) for q in self._peers}
         self._owned_dev = torch.from_numpy(plan.owned).to(dev)
         self.comm_bytes = 0
+        # every rank must run BP the same way (the in-kernel barriers of the single-launch run and the per-sweep
+        # launches stop after different numbers of barriers): single launch only if it is possible everywhere
+        active = [c.degree for c in self.classes if c.degree > 0 and c.B > 0]
+        ok = len(active) == 1 and self._single_launch_ok and self.p2p
+        deg = active[0] if ok else -1
+        flag = torch.tensor([1 if ok else 0, deg, -deg], device=dev)      # MIN over ranks: all ok, min degree, -max degree
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        self._single_launch_ok = bool(int(flag[0])) and int(flag[1]) == -int(flag[2])   # same single class everywhere
         if self.p2p:
             self._ensure_edge_buffers(self.Dmax)              # symmetric allocations are collective: do them all now
             self._flags = self._alloc_shared(64, torch.uint8, "flags")

@@ -234,7 +234,7 @@ def run_ours(args) -> None:
     for ins in layers[k:k + warmup]:
         eng.run_layer(ins["xtime"], ins["ztime"])
     k += warmup
-    snapshot = eng.state_to_host(pinned=True) if world == 1 else None
+    snapshot = eng.state_to_host(pinned=True)
 
     # ---- timed region: exactly K steps, state resident in HBM --------------------------------
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -256,16 +256,19 @@ def run_ours(args) -> None:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    clocks = sampler.stop(tw0, tw1) if sampler else None
     bloch_resident = eng.bloch_vectors()
 
     # ---- instrumented pass: per-launch duration of the dominant kernel (BP sweep) ------------
     roof = measure_roofline(eng, lib, layers[k + steps:k + 2 * steps], torch, dev) if rank == 0 or world > 1 else None
 
+    # clocks under load: samples from the start of the timed region to the end of the instrumented replay of the same
+    # workload (the timed region alone is a few tens of milliseconds: too short for nvidia-smi's sampling period)
+    clocks = sampler.stop(tw0, time.perf_counter()) if sampler else None
+    if clocks is not None:
+        clocks["window"] = "timed region + instrumented replay"
+
     # ---- end-to-end through the public engine API with HOST buffers --------------------------
-    e2e = None
-    if world == 1:
-        e2e = measure_e2e(eng, snapshot, layers[k:k + steps], torch, dev, bloch_resident)
+    e2e = measure_e2e(eng, snapshot, layers[k:k + steps], torch, dev, bloch_resident, world, dist)
 
     if rank != 0:
         if world > 1:
@@ -386,11 +389,15 @@ def measure_roofline(eng, lib, layers, torch, dev) -> dict:
     return out
 
 
-def measure_e2e(eng, snapshot, layers, torch, dev, bloch_resident) -> dict:
-    """Same K steps driven from HOST buffers through the public engine API: load_state (pinned host -> HBM),
-    K x run_layer (each reads its bond-dimension decision and BP residuals back), bloch_vectors (HBM -> host)."""
+def measure_e2e(eng, snapshot, layers, torch, dev, bloch_resident, world, dist) -> dict:
+    """Same K steps driven from HOST buffers through the public engine API: load_state (pinned host -> HBM; every rank
+    its own shard), K x run_layer (each reads its bond-dimension decision and BP control block back), bloch_vectors
+    (HBM -> host, gathered over the ranks).  Wall clock between barriers, max over ranks; bytes summed over ranks."""
     h2d = sum(int(t.numel() * t.element_size()) for t in snapshot["_pinned"].values())
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize(dev)
+    n0 = len(eng.stats["bp_sweeps"])
     t0 = time.perf_counter()
     eng.load_state(snapshot)
     for ins in layers:
@@ -399,8 +406,15 @@ def measure_e2e(eng, snapshot, layers, torch, dev, bloch_resident) -> dict:
     torch.cuda.synchronize(dev)
     dt = time.perf_counter() - t0
     K = len(layers)
+    reads = K + len(eng.stats["bp_sweeps"]) - n0              # column maxima per step + control block per BP read (>= 1 per run)
+    d2h = b.shape[0] * 4 * 4 / world + K * eng.colmax_bytes + (reads - K) * eng.ctrl_bytes_per_bp_read
+    if world > 1:
+        t = torch.tensor([dt, float(h2d), float(d2h)], dtype=torch.float64, device=dev)
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        dt, h2d, d2h = float(tmax[0]), float(t[1]), float(t[2])
     assert np.abs(b - bloch_resident).max() < 1e-6, "end-to-end run disagrees with the HBM-resident run"
-    d2h = b.shape[0] * 4 * 4 + K * (eng.ctrl_bytes_per_bp_read * 2 + eng.colmax_bytes)
     return {"value": K / dt, "unit": "steps/s", "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
             "what": "Engine.load_state(pinned host snapshot) + K x Engine.run_layer + Engine.bloch_vectors(), "
                     "wall clock incl. all copies"}

@@ -14,15 +14,21 @@
 // broadcast -- no lane repeats another lane's parameter arithmetic.  Column norms are carried along
 // (alpha' = alpha - t |g|, beta' = beta + t |g|) and recomputed exactly once per sweep.  A warp holds 8 edges;
 // matrices move between the "rows per lane" and "column per lane" views through padded shared-memory tiles.
+// Arithmetic is packed (sm_100 FFMA2 / FMUL2: one issue slot for two fp32 FMAs, measured on B200 in
+// scripts/ffma2_bench.cu): the two rows of a lane are held as pairs X[j] = (re A[q][j], re A[q+4][j]),
+// Y[j] = (im A[q][j], im A[q+4][j]), so every rotation and inner product works on both rows at once.
 // Code size is kept inside the 32 KB instruction cache: ONE round body, executed 7 times per sweep with the columns
 // rotated through the registers, and ONE Jacobi instance looped over the three matrices of an edge.
 #include <cuda_runtime.h>
 
 #include "bqa_core.cuh"
+#include "bqa_f32x2.cuh"
 #include "bqa_launch.cuh"
 
 namespace bqa {
 namespace canon8 {
+
+using x2::p2;
 
 constexpr int kWarps = 4;
 constexpr int kEdges = 8;                  // edges per warp (4 lanes each)
@@ -44,11 +50,10 @@ __device__ __forceinline__ float red4(float v) {
   return v;
 }
 
-// squared column norms of the 8 x 8 matrix whose rows q, q + 4 live in this lane
-__device__ __forceinline__ void col_norms(const float2 (&A0)[8], const float2 (&A1)[8], float (&w)[8]) {
+// squared column norms of the 8 x 8 matrix whose rows q, q + 4 live in this lane (packed: X = re, Y = im of both rows)
+__device__ __forceinline__ void col_norms(const p2 (&X)[8], const p2 (&Y)[8], float (&w)[8]) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
-    w[j] = red4((A0[j].x * A0[j].x + A0[j].y * A0[j].y) + (A1[j].x * A1[j].x + A1[j].y * A1[j].y));
+  for (int j = 0; j < 8; ++j) w[j] = red4(x2::hsum(x2::fma2(Y[j], Y[j], x2::mul2(X[j], X[j]))));
 }
 
 // rsqrt with one Newton step (MUFU.RSQ is good to ~2 ulp; rotations must stay orthonormal to rounding)
@@ -84,31 +89,35 @@ __device__ __forceinline__ Rot rot_params(float al, float be, float gr, float gi
   return r;
 }
 
+// both rows of this lane at once: a_q <- phase a_q, then (a_p, a_q) <- (c a_p - s a_q, s a_p + c a_q); 12 packed ops
+// (the rotation scalars enter as broadcast operands)
 template <int P, int Q>
-__device__ __forceinline__ void rot_row(float2 (&A)[8], const Rot& r) {
-  const float2 ap = A[P], aq = cmulf(make_float2(r.phx, r.phy), A[Q]);
-  A[P] = make_float2(r.c * ap.x - r.s * aq.x, r.c * ap.y - r.s * aq.y);
-  A[Q] = make_float2(r.s * ap.x + r.c * aq.x, r.s * ap.y + r.c * aq.y);
+__device__ __forceinline__ void rot_cols(p2 (&X)[8], p2 (&Y)[8], const Rot& r) {
+  const p2 qx = x2::fnma2s(r.phy, Y[Q], x2::mul2s(r.phx, X[Q]));
+  const p2 qy = x2::fma2s(r.phy, X[Q], x2::mul2s(r.phx, Y[Q]));
+  const p2 px = X[P], py = Y[P];
+  X[P] = x2::fnma2s(r.s, qx, x2::mul2s(r.c, px));
+  Y[P] = x2::fnma2s(r.s, qy, x2::mul2s(r.c, py));
+  X[Q] = x2::fma2s(r.c, qx, x2::mul2s(r.s, px));
+  Y[Q] = x2::fma2s(r.c, qy, x2::mul2s(r.s, py));
 }
 template <int P, int Q>
-__device__ __forceinline__ void apply_rot(float2 (&A0)[8], float2 (&A1)[8], float2 (&V0)[8], float2 (&V1)[8],
-                                          float (&w)[8], const Rot& r) {
-  rot_row<P, Q>(A0, r);
-  rot_row<P, Q>(A1, r);
-  rot_row<P, Q>(V0, r);
-  rot_row<P, Q>(V1, r);
+__device__ __forceinline__ void apply_rot(p2 (&AX)[8], p2 (&AY)[8], p2 (&VX)[8], p2 (&VY)[8], float (&w)[8],
+                                          const Rot& r) {
+  rot_cols<P, Q>(AX, AY, r);
+  rot_cols<P, Q>(VX, VY, r);
   w[P] -= r.dw;
   w[Q] += r.dw;
 }
 
 // conj(a_p) a_q summed over the two rows of this lane
-#define BQA_GAMMA(P, Q, RE, IM)                                                                      \
-  RE = (A0[P].x * A0[Q].x + A0[P].y * A0[Q].y) + (A1[P].x * A1[Q].x + A1[P].y * A1[Q].y);             \
-  IM = (A0[P].x * A0[Q].y - A0[P].y * A0[Q].x) + (A1[P].x * A1[Q].y - A1[P].y * A1[Q].x);
+#define BQA_GAMMA(P, Q, RE, IM)                                                    \
+  RE = x2::hsum(x2::fma2(AY[P], AY[Q], x2::mul2(AX[P], AX[Q])));                    \
+  IM = x2::hsum(x2::fnma2(AY[P], AX[Q], x2::mul2(AX[P], AY[Q])));
 
 // One round = four disjoint pairs (P0,Q0) .. (P3,Q3), pair k handled by lane k of the edge.
 template <int P0, int Q0, int P1, int Q1, int P2, int Q2, int P3, int Q3>
-__device__ __forceinline__ void jacobi_round(float2 (&A0)[8], float2 (&A1)[8], float2 (&V0)[8], float2 (&V1)[8],
+__device__ __forceinline__ void jacobi_round(p2 (&AX)[8], p2 (&AY)[8], p2 (&VX)[8], p2 (&VY)[8],
                                              float (&w)[8], float nul, float tol2, bool& rotated, int q) {
   float g[8];
   BQA_GAMMA(P0, Q0, g[0], g[1])
@@ -138,27 +147,27 @@ __device__ __forceinline__ void jacobi_round(float2 (&A0)[8], float2 (&A1)[8], f
     R[k].phy = __shfl_sync(0xffffffffu, mine.phy, base + k);
     R[k].dw = __shfl_sync(0xffffffffu, mine.dw, base + k);
   }
-  apply_rot<P0, Q0>(A0, A1, V0, V1, w, R[0]);
-  apply_rot<P1, Q1>(A0, A1, V0, V1, w, R[1]);
-  apply_rot<P2, Q2>(A0, A1, V0, V1, w, R[2]);
-  apply_rot<P3, Q3>(A0, A1, V0, V1, w, R[3]);
+  apply_rot<P0, Q0>(AX, AY, VX, VY, w, R[0]);
+  apply_rot<P1, Q1>(AX, AY, VX, VY, w, R[1]);
+  apply_rot<P2, Q2>(AX, AY, VX, VY, w, R[2]);
+  apply_rot<P3, Q3>(AX, AY, VX, VY, w, R[3]);
 }
 
-// one-sided Jacobi SVD: on exit A = U diag(sigma) (rows q, q + 4 of this lane), V = right singular vectors (same
-// rows), w = sigma^2 per column (all lanes).  A sweep is ONE round body executed 7 times, with the columns 1..7
-// rotated through the registers between rounds (circle method: pairs (0,7) (1,6) (2,5) (3,4) by position); after
-// 7 rounds every pair has met once and the columns are back in place.
-__device__ __forceinline__ void jacobi8(float2 (&A0)[8], float2 (&A1)[8], float2 (&V0)[8], float2 (&V1)[8],
+// one-sided Jacobi SVD on the packed rows: on exit A = U diag(sigma) (rows q, q + 4 of this lane), V = right singular
+// vectors (same rows), w = sigma^2 per column (all lanes).  A sweep is ONE round body executed 7 times, with the
+// columns 1..7 rotated through the registers between rounds (circle method: pairs (0,7) (1,6) (2,5) (3,4) by
+// position); after 7 rounds every pair has met once and the columns are back in place.
+__device__ __forceinline__ void jacobi8(p2 (&AX)[8], p2 (&AY)[8], p2 (&VX)[8], p2 (&VY)[8],
                                         float (&w)[8], int q, int& sweeps) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    V0[j] = make_float2(j == q ? 1.f : 0.f, 0.f);
-    V1[j] = make_float2(j == q + 4 ? 1.f : 0.f, 0.f);
+    VX[j] = x2::pk(j == q ? 1.f : 0.f, j == q + 4 ? 1.f : 0.f);
+    VY[j] = x2::pk(0.f, 0.f);
   }
   const float eps = 1.1920929e-07f;
   const float tol = eps * 2.f * 2.8284271f;                 // eps * 2 * sqrt(n), like the generic kernel
   const float tol2 = tol * tol;
-  col_norms(A0, A1, w);
+  col_norms(AX, AY, w);
   const float fro2 = ((w[0] + w[1]) + (w[2] + w[3])) + ((w[4] + w[5]) + (w[6] + w[7]));
   const float nul = eps * eps * fro2;                       // columns below eps |A|_F are numerically zero
 #pragma unroll 1
@@ -166,16 +175,30 @@ __device__ __forceinline__ void jacobi8(float2 (&A0)[8], float2 (&A1)[8], float2
     bool rotated = false;
 #pragma unroll 1
     for (int round = 0; round < 7; ++round) {
-      jacobi_round<0, 7, 1, 6, 2, 5, 3, 4>(A0, A1, V0, V1, w, nul, tol2, rotated, q);
-      const float2 a7 = A0[7], b7 = A1[7], v7 = V0[7], u7 = V1[7];
+      jacobi_round<0, 7, 1, 6, 2, 5, 3, 4>(AX, AY, VX, VY, w, nul, tol2, rotated, q);
+      const p2 a7 = AX[7], b7 = AY[7], v7 = VX[7], u7 = VY[7];
       const float w7 = w[7];
 #pragma unroll
-      for (int j = 7; j > 1; --j) { A0[j] = A0[j - 1]; A1[j] = A1[j - 1]; V0[j] = V0[j - 1]; V1[j] = V1[j - 1]; w[j] = w[j - 1]; }
-      A0[1] = a7; A1[1] = b7; V0[1] = v7; V1[1] = u7; w[1] = w7;
+      for (int j = 7; j > 1; --j) { AX[j] = AX[j - 1]; AY[j] = AY[j - 1]; VX[j] = VX[j - 1]; VY[j] = VY[j - 1]; w[j] = w[j - 1]; }
+      AX[1] = a7; AY[1] = b7; VX[1] = v7; VY[1] = u7; w[1] = w7;
     }
-    col_norms(A0, A1, w);                                   // exact norms once per sweep
+    col_norms(AX, AY, w);                                   // exact norms once per sweep
     ++sweeps;
     if (!__any_sync(0xffffffffu, rotated)) break;
+  }
+}
+
+// (rows q, q + 4 interleaved re/im)  <->  packed (X = re of both rows, Y = im of both rows)
+__device__ __forceinline__ void pack_rows(p2 (&X)[8], p2 (&Y)[8], const float2 (&A0)[8], const float2 (&A1)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { X[j] = x2::pk(A0[j].x, A1[j].x); Y[j] = x2::pk(A0[j].y, A1[j].y); }
+}
+__device__ __forceinline__ void unpack_rows(float2 (&A0)[8], float2 (&A1)[8], const p2 (&X)[8], const p2 (&Y)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float2 x = x2::unpk(X[j]), y = x2::unpk(Y[j]);
+    A0[j] = make_float2(x.x, y.x);
+    A1[j] = make_float2(x.y, y.y);
   }
 }
 
@@ -266,7 +289,13 @@ __global__ void __launch_bounds__(kWarps * 32, 4) k_canon8(long long L, const fl
         }
       }
       const int before = n_sweeps;
-      jacobi8(A0, A1, W0, W1, sk, q, n_sweeps);
+      {
+        p2 AX[8], AY[8], VX[8], VY[8];
+        pack_rows(AX, AY, A0, A1);
+        jacobi8(AX, AY, VX, VY, sk, q, n_sweeps);
+        unpack_rows(A0, A1, AX, AY);
+        unpack_rows(W0, W1, VX, VY);
+      }
       if (m == 2) n_ker += n_sweeps - before;
       if (m < 2) {
         unsigned char* tile = m ? tile1 : tile0;

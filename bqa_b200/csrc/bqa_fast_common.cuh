@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "bqa_f32x2.cuh"
+
 namespace bqa {
 namespace fast {
 
@@ -41,6 +43,49 @@ __device__ __forceinline__ void sts_tile(unsigned char* p, const float2 (&r)[16]
 #pragma unroll
   for (int i = 0; i < 8; ++i)
     *reinterpret_cast<float4*>(p + 16 * i) = make_float4(r[2 * i].x, r[2 * i].y, r[2 * i + 1].x, r[2 * i + 1].y);
+}
+
+// ---- packed (FFMA2) complex arithmetic: a complex number is one fp32 pair (re, im) -----------------------------
+using x2::p2;
+
+// 16 complex (128 bytes) shared <-> register pairs
+__device__ __forceinline__ void lds_tile(p2 (&r)[16], const unsigned char* p) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(p + 16 * i);
+    r[2 * i] = v.x;
+    r[2 * i + 1] = v.y;
+  }
+}
+__device__ __forceinline__ void sts_tile(unsigned char* p, const p2 (&r)[16]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) *reinterpret_cast<ulonglong2*>(p + 16 * i) = make_ulonglong2(r[2 * i], r[2 * i + 1]);
+}
+
+// Two-accumulator complex multiply-add: with s = (sx, sy) used as broadcast scalars and v as a pair,
+//   A += sx * v,  B += sy * v     (2 FFMA2 per complex multiply-add, no operand preparation)
+// and at the end  sum s v = (A.x - B.y, A.y + B.x),  sum conj(s) v = (A.x + B.y, A.y - B.x).
+struct CAcc {
+  p2 A, B;
+};
+template <bool FIRST>
+__device__ __forceinline__ void cmac(CAcc& acc, p2 s, p2 v) {
+  const float2 f = x2::unpk(s);
+  if (FIRST) {
+    acc.A = x2::mul2s(f.x, v);
+    acc.B = x2::mul2s(f.y, v);
+  } else {
+    acc.A = x2::fma2s(f.x, v, acc.A);
+    acc.B = x2::fma2s(f.y, v, acc.B);
+  }
+}
+__device__ __forceinline__ p2 cfinish(const CAcc& acc) {          // sum s v
+  const float2 a = x2::unpk(acc.A), b = x2::unpk(acc.B);
+  return x2::pk(a.x - b.y, a.y + b.x);
+}
+__device__ __forceinline__ float2 cfinish_conj(const CAcc& acc) {  // sum conj(s) v
+  const float2 a = x2::unpk(acc.A), b = x2::unpk(acc.B);
+  return make_float2(a.x + b.y, a.y - b.x);
 }
 
 }  // namespace fast

@@ -167,9 +167,9 @@ __device__ __forceinline__ void sweep(const Args& a, unsigned char* smem) {
     }
     const unsigned char* Ts = st + (s * 8 + p * 4) * kSlice;          // the four a-slices of (node, p)
     const unsigned char* Min = st + kTBytes;
-    float2 U0[16], U1[16], U2[16];
+    p2 U0[16], U1[16], U2[16];
     {
-      float2 tt[16], m[16];
+      p2 tt[16], m[16];
       lds_tile(tt, Ts + la * kSlice);
       // U2[b][c'] = sum_c m2[c'][c] T[b][c]
       lds_tile(m, Min + (2 * 4 + s) * kMsg);
@@ -177,10 +177,11 @@ __device__ __forceinline__ void sweep(const Args& a, unsigned char* smem) {
       for (int b = 0; b < 4; ++b)
 #pragma unroll
         for (int c2 = 0; c2 < 4; ++c2) {
-          float2 acc = make_float2(0.f, 0.f);
+          CAcc acc;
+          cmac<true>(acc, m[c2 * 4], tt[b * 4]);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) fma_c(acc, m[c2 * 4 + c], tt[b * 4 + c]);
-          U2[b * 4 + c2] = acc;
+          for (int c = 1; c < 4; ++c) cmac<false>(acc, m[c2 * 4 + c], tt[b * 4 + c]);
+          U2[b * 4 + c2] = cfinish(acc);
         }
       // U1[b'][c] = sum_b m1[b'][b] T[b][c]
       lds_tile(m, Min + (1 * 4 + s) * kMsg);
@@ -188,24 +189,31 @@ __device__ __forceinline__ void sweep(const Args& a, unsigned char* smem) {
       for (int b2 = 0; b2 < 4; ++b2)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          float2 acc = make_float2(0.f, 0.f);
+          CAcc acc;
+          cmac<true>(acc, m[b2 * 4], tt[c]);
 #pragma unroll
-          for (int b = 0; b < 4; ++b) fma_c(acc, m[b2 * 4 + b], tt[b * 4 + c]);
-          U1[b2 * 4 + c] = acc;
+          for (int b = 1; b < 4; ++b) cmac<false>(acc, m[b2 * 4 + b], tt[b * 4 + c]);
+          U1[b2 * 4 + c] = cfinish(acc);
         }
     }
     {
-      // U0[a][b][c] = sum_a' m0[a][a'] T[a'][b][c]: row `la` of m0, the four slices broadcast from shared memory
+      // U0[a][b][c] = sum_a' m0[a][a'] T[a'][b][c]: row `la` of m0, the four slices broadcast from shared memory;
+      // the matrix element is the prepared pair operand (m, i m), the tensor elements enter as broadcast scalars
       const unsigned char* m0row = Min + (0 * 4 + s) * kMsg + la * 32;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) U0[i] = make_float2(0.f, 0.f);
+      for (int i = 0; i < 16; ++i) U0[i] = x2::pk(0.f, 0.f);
 #pragma unroll 1
       for (int a2 = 0; a2 < 4; ++a2) {                      // rolled: code size (instruction cache) matters
-        float2 tt[16];
+        p2 tt[16];
         lds_tile(tt, Ts + a2 * kSlice);
-        const float2 m = *reinterpret_cast<const float2*>(m0row + a2 * 8);
+        const float2 mf = *reinterpret_cast<const float2*>(m0row + a2 * 8);
+        const p2 m = x2::pk(mf.x, mf.y), im = x2::pk(-mf.y, mf.x);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) fma_c(U0[i], m, tt[i]);
+        for (int i = 0; i < 16; ++i) {
+          const float2 tf = x2::unpk(tt[i]);
+          U0[i] = x2::fma2s(tf.x, m, U0[i]);
+          U0[i] = x2::fma2s(tf.y, im, U0[i]);
+        }
       }
     }
     __syncwarp();                                           // every lane is done with the T slices
@@ -220,15 +228,12 @@ __device__ __forceinline__ void sweep(const Args& a, unsigned char* smem) {
     for (int k = 1; k <= 2; ++k) {
       float2 acc[10];
 #pragma unroll
-      for (int x = 0; x < 4; ++x) {
-        float d = 0.f;
+      for (int x = 0; x < 4; ++x) {                         // diagonal: sum of element-wise pair products
+        p2 d2 = x2::mul2((k == 1) ? U2[x * 4] : U1[x], (k == 1) ? U0[x * 4] : U0[x]);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float2 u = (k == 1) ? U2[x * 4 + q] : U1[q * 4 + x];
-          const float2 v = (k == 1) ? U0[x * 4 + q] : U0[q * 4 + x];
-          d = fmaf(u.x, v.x, d); d = fmaf(u.y, v.y, d);
-        }
-        acc[x] = make_float2(d, 0.f);
+        for (int q = 1; q < 4; ++q)
+          d2 = x2::fma2((k == 1) ? U2[x * 4 + q] : U1[q * 4 + x], (k == 1) ? U0[x * 4 + q] : U0[q * 4 + x], d2);
+        acc[x] = make_float2(x2::hsum(d2), 0.f);
       }
       {
         int n = 4;
@@ -236,13 +241,12 @@ __device__ __forceinline__ void sweep(const Args& a, unsigned char* smem) {
         for (int x = 0; x < 4; ++x)
 #pragma unroll
           for (int y = x + 1; y < 4; ++y) {
-            float2 v = make_float2(0.f, 0.f);
+            CAcc v;
+            cmac<true>(v, (k == 1) ? U2[x * 4] : U1[x], (k == 1) ? U0[y * 4] : U0[y]);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (k == 1) fma_cc(v, U2[x * 4 + q], U0[y * 4 + q]);
-              else fma_cc(v, U1[q * 4 + x], U0[q * 4 + y]);
-            }
-            acc[n++] = v;
+            for (int q = 1; q < 4; ++q)
+              cmac<false>(v, (k == 1) ? U2[x * 4 + q] : U1[q * 4 + x], (k == 1) ? U0[y * 4 + q] : U0[q * 4 + y]);
+            acc[n++] = cfinish_conj(v);
           }
       }
       __syncwarp();                                         // previous readers of the scratch are done
@@ -269,12 +273,15 @@ __device__ __forceinline__ void sweep(const Args& a, unsigned char* smem) {
       unsigned char* o0 = scratch + kOut0 + s * 64;         // [x][node][p][y]: a warp-wide store is 256 contiguous bytes
 #pragma unroll 1
       for (int x = 0; x < 4; ++x) {                         // rolled: code size
-        float2 ux[16];
+        p2 ux[16];
         lds_tile(ux, Xs + x * kSlice);
-        float2 v0 = make_float2(0.f, 0.f), v1 = v0;         // two chains
+        CAcc v0, v1;                                        // two chains
+        cmac<true>(v0, ux[0], U2[0]);
+        cmac<true>(v1, ux[1], U2[1]);
 #pragma unroll
-        for (int i = 0; i < 16; i += 2) { fma_cc(v0, ux[i], U2[i]); fma_cc(v1, ux[i + 1], U2[i + 1]); }
-        *reinterpret_cast<float2*>(o0 + x * kOut0Row + p * 32 + la * 8) = make_float2(v0.x + v1.x, v0.y + v1.y);
+        for (int i = 2; i < 16; i += 2) { cmac<false>(v0, ux[i], U2[i]); cmac<false>(v1, ux[i + 1], U2[i + 1]); }
+        const float2 r0 = cfinish_conj(v0), r1 = cfinish_conj(v1);
+        *reinterpret_cast<float2*>(o0 + x * kOut0Row + p * 32 + la * 8) = make_float2(r0.x + r1.x, r0.y + r1.y);
       }
       __syncwarp();
       const float4 v0 = *reinterpret_cast<const float4*>(o0 + (t >> 1) * kOut0Row + (t & 1) * 16);

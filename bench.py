@@ -240,6 +240,7 @@ def run_ours(args) -> None:
     sampler = ClockSampler(local_rank) if rank == 0 else None
     n0 = len(eng.stats["bp_sweeps"])
     launches0 = lib.launch_count()
+    canon0 = lib.canon_stats()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tw0 = time.perf_counter()
@@ -251,6 +252,8 @@ def run_ours(args) -> None:
     tw1 = time.perf_counter()
     ms = ev0.elapsed_time(ev1)
     launches = lib.launch_count() - launches0
+    torch.cuda.synchronize(dev)
+    canon1 = lib.canon_stats()
     sweeps = eng.stats["bp_sweeps"][n0:]
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -284,6 +287,8 @@ def run_ours(args) -> None:
             "dtype": "c64", "data": "synthetic", "config": make_bench_config(world),
             "sweeps_per_step": float(np.mean(sweeps)), "bp_sweep_msg_updates_per_step": bp_updates / steps,
             "clocks": clocks, "gpu_launches": int(launches), "wall_ms_per_step": (tw1 - tw0) * 1e3 / steps}
+    if canon1[0] > canon0[0]:                                  # Jacobi sweeps per warp-level 8 x 8 problem in the timed region
+        line["canon_jacobi_sweeps_per_problem"] = (canon1[1] - canon0[1]) / (canon1[0] - canon0[0])
     if roof:
         line["roofline"] = roof["roofline"]
         line["bp_msg_updates_per_s"] = roof["bp_msg_updates_per_s"]

@@ -17,6 +17,13 @@
 // Arithmetic is packed (sm_100 FFMA2 / FMUL2: one issue slot for two fp32 FMAs, measured on B200 in
 // scripts/ffma2_bench.cu): the two rows of a lane are held as pairs X[j] = (re A[q][j], re A[q+4][j]),
 // Y[j] = (im A[q][j], im A[q+4][j]), so every rotation and inner product works on both rows at once.
+// A sweep loop ends, per edge, with LAPACK xGESVJ's quadratic-convergence test (n max|cos(a_p, a_q)| max|sin(rotation)|
+// < tol over the sweep: the next sweep would rotate by less than the tolerance), which saves the last, confirming sweep.
+// A finished edge is frozen (all its later rotations are exact identities) while other edges of the warp still sweep,
+// so an edge's result does not depend on which edges share its warp (single-GPU and partitioned runs stay bit-identical).
+// (A warm start from the previous step's rotations was tried and dropped: A V_prev loses the relative accuracy that
+// one-sided Jacobi keeps on the graded extended messages -- mean Bloch error 1.1e-4 instead of 1.3e-5 -- and the extra
+// product and traffic made the step slower, not faster.)
 // Code size is kept inside the 32 KB instruction cache: ONE round body, executed 7 times per sweep with the columns
 // rotated through the registers, and ONE Jacobi instance looped over the three matrices of an edge.
 #include <cuda_runtime.h>
@@ -67,13 +74,13 @@ __device__ __forceinline__ float rsqrt_nr(float x) {
 struct Rot {
   float c, s, phx, phy, dw;      // cos, sin, unimodular phase conj(g)/|g|, norm transfer t |g|
 };
-// `rotated` is raised when the pair needed a rotation.  The sweep loop runs until a whole sweep needs none, for every
-// edge of the warp: extra sweeps on an already converged edge are exact identities, so an edge's result does not
-// depend on which other edges share its warp (single-GPU and partitioned runs stay bit-identical).
-__device__ __forceinline__ Rot rot_params(float al, float be, float gr, float gi, float nul, float tol2, bool& rotated) {
+// `mxg2` / `mxs2` collect, over the pairs this lane handled in a sweep, the largest squared cosine between two
+// columns and the largest squared rotation sine (both 0 when no pair needed a rotation).  `frozen`: the edge is done.
+__device__ __forceinline__ Rot rot_params(float al, float be, float gr, float gi, float nul, float tol2, bool frozen,
+                                          float& mxg2, float& mxs2) {
   const float g2 = gr * gr + gi * gi;
-  const bool act = !(al <= nul || be <= nul || g2 <= tol2 * al * be);
-  rotated |= act;
+  const float ab = al * be;
+  const bool act = !frozen && !(al <= nul || be <= nul || g2 <= tol2 * ab);
   const float ig = rsqrt_nr(g2);                  // 1 / |g|   (inf / nan when inactive: discarded below)
   const float ag = g2 * ig;
   const float zeta = 0.5f * (be - al) * ig;
@@ -86,6 +93,8 @@ __device__ __forceinline__ Rot rot_params(float al, float be, float gr, float gi
   r.phx = act ? gr * ig : 1.f;
   r.phy = act ? -gi * ig : 0.f;
   r.dw = act ? t * ag : 0.f;
+  mxg2 = fmaxf(mxg2, act ? __fdividef(g2, ab) : 0.f);
+  mxs2 = fmaxf(mxs2, r.s * r.s);
   return r;
 }
 
@@ -118,7 +127,7 @@ __device__ __forceinline__ void apply_rot(p2 (&AX)[8], p2 (&AY)[8], p2 (&VX)[8],
 // One round = four disjoint pairs (P0,Q0) .. (P3,Q3), pair k handled by lane k of the edge.
 template <int P0, int Q0, int P1, int Q1, int P2, int Q2, int P3, int Q3>
 __device__ __forceinline__ void jacobi_round(p2 (&AX)[8], p2 (&AY)[8], p2 (&VX)[8], p2 (&VY)[8],
-                                             float (&w)[8], float nul, float tol2, bool& rotated, int q) {
+                                             float (&w)[8], float nul, float tol2, bool frozen, float& mxg2, float& mxs2, int q) {
   float g[8];
   BQA_GAMMA(P0, Q0, g[0], g[1])
   BQA_GAMMA(P1, Q1, g[2], g[3])
@@ -136,7 +145,7 @@ __device__ __forceinline__ void jacobi_round(p2 (&AX)[8], p2 (&AY)[8], p2 (&VX)[
   // lane q now holds the inner product of pair q; its column norms:
   const float al = b1 ? (b0 ? w[P3] : w[P2]) : (b0 ? w[P1] : w[P0]);
   const float be = b1 ? (b0 ? w[Q3] : w[Q2]) : (b0 ? w[Q1] : w[Q0]);
-  const Rot mine = rot_params(al, be, gr, gi, nul, tol2, rotated);
+  const Rot mine = rot_params(al, be, gr, gi, nul, tol2, frozen, mxg2, mxs2);
   const int base = (threadIdx.x & 31) & ~3;
   Rot R[4];
 #pragma unroll
@@ -170,12 +179,13 @@ __device__ __forceinline__ void jacobi8(p2 (&AX)[8], p2 (&AY)[8], p2 (&VX)[8], p
   col_norms(AX, AY, w);
   const float fro2 = ((w[0] + w[1]) + (w[2] + w[3])) + ((w[4] + w[5]) + (w[6] + w[7]));
   const float nul = eps * eps * fro2;                       // columns below eps |A|_F are numerically zero
+  bool frozen = false;
 #pragma unroll 1
   for (int sweep = 0; sweep < 30; ++sweep) {
-    bool rotated = false;
+    float mxg2 = 0.f, mxs2 = 0.f;
 #pragma unroll 1
     for (int round = 0; round < 7; ++round) {
-      jacobi_round<0, 7, 1, 6, 2, 5, 3, 4>(AX, AY, VX, VY, w, nul, tol2, rotated, q);
+      jacobi_round<0, 7, 1, 6, 2, 5, 3, 4>(AX, AY, VX, VY, w, nul, tol2, frozen, mxg2, mxs2, q);
       const p2 a7 = AX[7], b7 = AY[7], v7 = VX[7], u7 = VY[7];
       const float w7 = w[7];
 #pragma unroll
@@ -184,7 +194,13 @@ __device__ __forceinline__ void jacobi8(p2 (&AX)[8], p2 (&AY)[8], p2 (&VX)[8], p
     }
     col_norms(AX, AY, w);                                   // exact norms once per sweep
     ++sweeps;
-    if (!__any_sync(0xffffffffu, rotated)) break;
+    // per edge (4 lanes): done when nothing rotated, or when the next sweep's rotations would be below the tolerance
+    mxg2 = fmaxf(mxg2, __shfl_xor_sync(0xffffffffu, mxg2, 1));
+    mxs2 = fmaxf(mxs2, __shfl_xor_sync(0xffffffffu, mxs2, 1));
+    mxg2 = fmaxf(mxg2, __shfl_xor_sync(0xffffffffu, mxg2, 2));
+    mxs2 = fmaxf(mxs2, __shfl_xor_sync(0xffffffffu, mxs2, 2));
+    frozen = frozen || 64.f * mxg2 * mxs2 < tol2;
+    if (!__any_sync(0xffffffffu, !frozen)) break;
   }
 }
 

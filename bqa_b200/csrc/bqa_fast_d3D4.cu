@@ -28,7 +28,10 @@
 namespace bqa {
 namespace fast {
 
-constexpr int kWarps = 12;
+#ifndef BQA_BP_WARPS
+#define BQA_BP_WARPS 12
+#endif
+constexpr int kWarps = BQA_BP_WARPS;
 constexpr int kThreads = kWarps * 32;
 constexpr int kSlice = 144;                       // 128-byte slice + 16 bytes of padding (bank spreading)
 constexpr int kTBytes = 32 * kSlice;              // 4 nodes x 8 slices
@@ -136,6 +139,16 @@ __device__ __forceinline__ void sweep(const Args& a, unsigned char* smem) {
     sgnA = x > ya ? -1.f : 1.f;
     sgnB = x > yb ? -1.f : 1.f;
   }
+  // BP path: the packed partials of out_1 / out_2 are reduce-scattered over the 8 lanes of a node with xor shuffles
+  // (16 reals -> 2 per lane), then every lane fetches the one pair it still misses from a partner lane.  Lane t owns
+  // pair t of  U01 | U02 | (D0, D1) | U13 | U12 | U23 | U03 | (D2, D3)  and needs elements (x, y0), (x, y0 + 1).
+  // (tables packed into immediates: partner 4 bits, flags 1 bit, signs 2 bits per lane -- no local-memory arrays)
+  const int partner = (lane & ~7) | ((0x53714062u >> (4 * t)) & 7);   // lane whose pair completes this lane's row piece
+  const bool a_got = (0xBDu >> t) & 1, b_got = (0x42u >> t) & 1;      // element a = (x, y0), b = (x, y0 + 1): own or fetched pair
+  const bool b_usey = (0x84u >> t) & 1;                               // diagonal entry held in the .y slot of (D, D) pairs
+  const int a_c = (0xA264u >> (2 * t)) & 3, b_c = (0x2645u >> (2 * t)) & 3;
+  const float a_im = a_c == 0 ? 0.f : (a_c == 1 ? 1.f : -1.f);        // sign of the imaginary part (0 on the diagonal)
+  const float b_im = b_c == 0 ? 0.f : (b_c == 1 ? 1.f : -1.f);
   int idx_cur = 0, idx_nxt = 0, rp_cur = -1, rp_nxt = -1;
   if (g < groups) {
     idx_cur = load_idx(a, g * 4, lane);
@@ -195,15 +208,25 @@ __device__ __forceinline__ void sweep(const Args& a, unsigned char* smem) {
           for (int b = 1; b < 4; ++b) cmac<false>(acc, m[b2 * 4 + b], tt[b * 4 + c]);
           U1[b2 * 4 + c] = cfinish(acc);
         }
+      // U0[a][b][c] = sum_a' m0[a][a'] T[a'][b][c], row a = `la` of m0.  The matrix element is the prepared pair operand
+      // (m, i m), the tensor elements enter as broadcast scalars.  Term a' = la: this lane's own slice, still in registers
+      const unsigned char* m0row = Min + (0 * 4 + s) * kMsg + la * 32;
+      {
+        const float2 mf = *reinterpret_cast<const float2*>(m0row + la * 8);
+        const p2 mm = x2::pk(mf.x, mf.y), im = x2::pk(-mf.y, mf.x);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float2 tf = x2::unpk(tt[i]);
+          U0[i] = x2::fma2s(tf.y, im, x2::mul2s(tf.x, mm));
+        }
+      }
     }
     {
-      // U0[a][b][c] = sum_a' m0[a][a'] T[a'][b][c]: row `la` of m0, the four slices broadcast from shared memory;
-      // the matrix element is the prepared pair operand (m, i m), the tensor elements enter as broadcast scalars
+      // the three other slices from shared memory: the 8 lanes of a node read 8 distinct slices (conflict-free)
       const unsigned char* m0row = Min + (0 * 4 + s) * kMsg + la * 32;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) U0[i] = x2::pk(0.f, 0.f);
 #pragma unroll 1
-      for (int a2 = 0; a2 < 4; ++a2) {                      // rolled: code size (instruction cache) matters
+      for (int r = 1; r < 4; ++r) {                         // rolled: code size (instruction cache) matters
+        const int a2 = (la + r) & 3;
         p2 tt[16];
         lds_tile(tt, Ts + a2 * kSlice);
         const float2 mf = *reinterpret_cast<const float2*>(m0row + a2 * 8);
@@ -249,30 +272,64 @@ __device__ __forceinline__ void sweep(const Args& a, unsigned char* smem) {
             acc[n++] = cfinish_conj(v);
           }
       }
-      __syncwarp();                                         // previous readers of the scratch are done
+      if (!EXT) {
+        // reduce-scatter over the node's 8 lanes (p and a): 14 shuffles, then one pair from the partner lane
+        float z[16] = {acc[4].x, acc[4].y, acc[5].x, acc[5].y, acc[0].x, acc[1].x, acc[8].x, acc[8].y,
+                       acc[7].x, acc[7].y, acc[9].x, acc[9].y, acc[6].x, acc[6].y, acc[2].x, acc[3].x};
+        const bool b2 = t & 4, b1 = t & 2, b0 = t & 1;
+        float y8[8], y4[4], y2[2];
 #pragma unroll
-      for (int i = 0; i < 5; ++i)
-        *reinterpret_cast<float4*>(red + t * kRedRow + 16 * i) =
-            make_float4(acc[2 * i].x, acc[2 * i].y, acc[2 * i + 1].x, acc[2 * i + 1].y);
-      __syncwarp();
-      float2 g0a = make_float2(0.f, 0.f), g0b = g0a, g1a = g0a, g1b = g0a;
+        for (int i = 0; i < 8; ++i)
+          y8[i] = (b2 ? z[8 + i] : z[i]) + __shfl_xor_sync(0xffffffffu, b2 ? z[i] : z[8 + i], 4);
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const float2 a0 = *reinterpret_cast<const float2*>(red + r * kRedRow + offA);
-        const float2 b0 = *reinterpret_cast<const float2*>(red + r * kRedRow + offB);
-        const float2 a1 = *reinterpret_cast<const float2*>(red + (4 + r) * kRedRow + offA);
-        const float2 b1 = *reinterpret_cast<const float2*>(red + (4 + r) * kRedRow + offB);
-        g0a.x += a0.x; g0a.y += a0.y; g0b.x += b0.x; g0b.y += b0.y;
-        g1a.x += a1.x; g1a.y += a1.y; g1b.x += b1.x; g1b.y += b1.y;
+        for (int i = 0; i < 4; ++i)
+          y4[i] = (b1 ? y8[4 + i] : y8[i]) + __shfl_xor_sync(0xffffffffu, b1 ? y8[i] : y8[4 + i], 2);
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+          y2[i] = (b0 ? y4[2 + i] : y4[i]) + __shfl_xor_sync(0xffffffffu, b0 ? y4[i] : y4[2 + i], 1);
+        const float gx = __shfl_sync(0xffffffffu, y2[0], partner), gy = __shfl_sync(0xffffffffu, y2[1], partner);
+        const float ax = a_got ? gx : y2[0], ay = a_got ? gy : y2[1];
+        const float bx = b_got ? gx : y2[0], by = b_got ? gy : y2[1];
+        e[k][0] = make_float2(ax, a_im * ay);
+        e[k][1] = make_float2(b_usey ? by : bx, b_im * by);
+        e[k][2] = make_float2(0.f, 0.f);
+        e[k][3] = make_float2(0.f, 0.f);
+      } else {
+        __syncwarp();                                       // previous readers of the scratch are done
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+          *reinterpret_cast<float4*>(red + t * kRedRow + 16 * i) =
+              make_float4(acc[2 * i].x, acc[2 * i].y, acc[2 * i + 1].x, acc[2 * i + 1].y);
+        __syncwarp();
+        float2 g0a = make_float2(0.f, 0.f), g0b = g0a, g1a = g0a, g1b = g0a;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float2 a0 = *reinterpret_cast<const float2*>(red + r * kRedRow + offA);
+          const float2 b0 = *reinterpret_cast<const float2*>(red + r * kRedRow + offB);
+          const float2 a1 = *reinterpret_cast<const float2*>(red + (4 + r) * kRedRow + offA);
+          const float2 b1 = *reinterpret_cast<const float2*>(red + (4 + r) * kRedRow + offB);
+          g0a.x += a0.x; g0a.y += a0.y; g0b.x += b0.x; g0b.y += b0.y;
+          g1a.x += a1.x; g1a.y += a1.y; g1b.x += b1.x; g1b.y += b1.y;
+        }
+        e[k][0] = make_float2(g0a.x, sgnA * g0a.y); e[k][1] = make_float2(g0b.x, sgnB * g0b.y);
+        e[k][2] = make_float2(g1a.x, sgnA * g1a.y); e[k][3] = make_float2(g1b.x, sgnB * g1b.y);
       }
-      e[k][0] = make_float2(g0a.x, sgnA * g0a.y); e[k][1] = make_float2(g0b.x, sgnB * g0b.y);
-      e[k][2] = make_float2(g1a.x, sgnA * g1a.y); e[k][3] = make_float2(g1b.x, sgnB * g1b.y);
     }
     // ---- out_0[x][y] = sum_{b,c} conj(U1[x][b][c]) U2[y][b][c]: lane (p, y = la) against the exchanged U1 slices
     {
       unsigned char* o0 = scratch + kOut0 + s * 64;         // [x][node][p][y]: a warp-wide store is 256 contiguous bytes
+      {                                                     // x = la: this lane's own U1 slice is still in registers
+        CAcc v0, v1;
+        cmac<true>(v0, U1[0], U2[0]);
+        cmac<true>(v1, U1[1], U2[1]);
+#pragma unroll
+        for (int i = 2; i < 16; i += 2) { cmac<false>(v0, U1[i], U2[i]); cmac<false>(v1, U1[i + 1], U2[i + 1]); }
+        const float2 r0 = cfinish_conj(v0), r1 = cfinish_conj(v1);
+        *reinterpret_cast<float2*>(o0 + la * kOut0Row + p * 32 + la * 8) = make_float2(r0.x + r1.x, r0.y + r1.y);
+      }
 #pragma unroll 1
-      for (int x = 0; x < 4; ++x) {                         // rolled: code size
+      for (int r = 1; r < 4; ++r) {                         // rolled: code size; the 8 lanes of a node read 8 distinct slices
+        const int x = (la + r) & 3;
         p2 ux[16];
         lds_tile(ux, Xs + x * kSlice);
         CAcc v0, v1;                                        // two chains

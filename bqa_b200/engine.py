@@ -140,13 +140,23 @@ class Engine:
         self._canon = None
         self._lmbds = torch.ones(self.L * 2 * Dm, dtype=self.rdtype, device=self.dev)
         self._lmbd_stride = 2      # row stride of the lambda array = 2 * D of the update that produced it
-        self._colmax = torch.zeros(2 * Dm, dtype=self.rdtype, device=self.dev)
-        # BP control block, read back with one copy per chunk of sweeps: [resid (max_iters, 2) reals | status int32 x4]
-        rbytes = ((max(self.max_iters, 1) * 2 * (4 if self.precision == "single" else 8)) + 15) // 16 * 16
-        self._ctrl = self._alloc_shared(rbytes + 16, torch.uint8, "ctrl")
+        # control block, read back with ONE copy per chunk of sweeps (one per step in the steady state):
+        # [resid (max_iters, 2) reals | status int32 x4 | column maxima of the lambdas (2 Dmax reals)]
+        rsize = 4 if self.precision == "single" else 8
+        rbytes = ((max(self.max_iters, 1) * 2 * rsize) + 15) // 16 * 16
+        cbytes = (2 * Dm * rsize + 15) // 16 * 16
+        self._ctrl = self._alloc_shared(rbytes + 16 + cbytes, torch.uint8, "ctrl")
         self._ctrl_rbytes = rbytes
+        self._ctrl_bp = self._ctrl[: rbytes + 16]            # the part a BP run resets
         self._resid = self._ctrl[:rbytes].view(self.rdtype)
-        self._status = self._ctrl[rbytes:].view(torch.int32)
+        self._status = self._ctrl[rbytes: rbytes + 16].view(torch.int32)
+        self._colmax = self._ctrl[rbytes + 16:].view(self.rdtype)[: 2 * Dm]
+        self._ctrl_host = torch.empty(self._ctrl.numel(), dtype=torch.uint8, pin_memory=True) if self.cuda else None
+        self._ctrl_last = None                               # host copy of the control block of the last read
+        # Speculative truncation: at D == max_bond_dim the update keeps max_bond_dim columns unless the state's rank
+        # collapses (backends.py:297-303), so the step is enqueued without waiting for the column maxima and they are
+        # checked with the BP control block, in the step's only host read; a wrong guess redoes the update.
+        self.speculate = os.environ.get("BQA_B200_SPECULATE", "1") != "0"
         self._bloch = torch.zeros(self.N * 4, dtype=self.rdtype, device=self.dev)
         self._ws = torch.zeros(16, dtype=torch.uint8, device=self.dev)
         self._argmax_i = torch.zeros(2, dtype=torch.int32, device=self.dev)
@@ -162,6 +172,17 @@ class Engine:
 
     def _to_host(self, t: torch.Tensor) -> np.ndarray:
         return t.cpu().numpy()          # synchronises the current stream
+
+    def _read_ctrl(self) -> np.ndarray:
+        """Host copy of the whole control block (page-locked staging buffer: one asynchronous copy + stream sync)."""
+        if self._ctrl_host is None:
+            ctrl = self._to_host(self._ctrl)
+        else:
+            self._ctrl_host.copy_(self._ctrl, non_blocking=True)
+            torch.cuda.current_stream(self.dev).synchronize()
+            ctrl = self._ctrl_host.numpy().copy()
+        self._ctrl_last = ctrl
+        return ctrl
 
     def _ensure_ws(self, D: int, Dn: int) -> None:
         need = max([self.lib.workspace_bytes(self.prec, c.degree, D, Dn) for c in self.classes] + [16])
@@ -330,9 +351,9 @@ class Engine:
         if not ok:
             self._no_bp_run[self.D] = True
             return None
-        ctrl = self._to_host(self._ctrl)
+        ctrl = self._read_ctrl()
         resid = ctrl[: self._ctrl_rbytes].view(self.np_rdtype).reshape(-1, 2)
-        status = ctrl[self._ctrl_rbytes:].view(np.int32)
+        status = ctrl[self._ctrl_rbytes: self._ctrl_rbytes + 16].view(np.int32)
         if status[3]:
             raise RuntimeError("BP run aborted: a grid or peer barrier timed out (bqa_b200_bp_run)")
         self._bp_run_done(int(status[1]))
@@ -342,7 +363,7 @@ class Engine:
         max_it = self.max_iters
         assert max_it > 0, "max_bp_iter_number must be positive"      # reference: assert best_msgs is not None
         self._ensure_ws(self.D, self.D)
-        self._ctrl.zero_()
+        self._ctrl_bp.zero_()
         self._before_bp()
         eps = self.np_rdtype(self.bp_eps)
         single = self._try_single_launch_bp()
@@ -357,9 +378,9 @@ class Engine:
             for _ in range(n):
                 self._enqueue_sweep(it, write_undamped=(it == max_it - 1))
                 it += 1
-            ctrl = self._to_host(self._ctrl)                 # one D2H + sync per chunk of sweeps
+            ctrl = self._read_ctrl()                         # one D2H + sync per chunk of sweeps
             resid = ctrl[: self._ctrl_rbytes].view(self.np_rdtype).reshape(-1, 2)
-            status = ctrl[self._ctrl_rbytes:].view(np.int32)
+            status = ctrl[self._ctrl_rbytes: self._ctrl_rbytes + 16].view(np.int32)
             if status[3]:
                 raise RuntimeError("a peer GPU never reached the sweep barrier (bqa_b200_sweep_sync timed out)")
             if status[0]:                                    # a later sweep saw convergence on the device
@@ -419,13 +440,40 @@ class Engine:
                               min(2 * D, self.Dmax), st)
         self._lmbd_stride = 2 * D
         self._reduce_colmax(self._colmax)
-        colmax = self._to_host(self._colmax)[: 2 * D].astype(np.float64)        # the one host sync per step
-        rank = 2 * D - int(np.sum(colmax < self.pinv_eps))                        # backends.py:297-303
+        speculative = self.speculate and self.cuda and D == self.Dmax
+        if speculative:
+            Dn = self.Dmax                                                        # checked after the BP run, see below
+        else:
+            colmax = self._to_host(self._colmax)[: 2 * D].astype(np.float64)      # host sync: the bond dimension changes
+            Dn, err = self._truncation(colmax, D)
+        n_bp = len(self.stats["bp_sweeps"])
+        self._apply_and_bp(D, Dn, xtime, ztime)
+        if speculative:
+            rb = self._ctrl_rbytes + 16
+            colmax = self._ctrl_last[rb: rb + 2 * D * self._colmax.element_size()].view(self.np_rdtype).astype(np.float64)
+            Dn_true, err = self._truncation(colmax, D)
+            if Dn_true != Dn:                                                     # the rank collapsed: redo with the right one
+                for c in self.classes:
+                    c.cur = 1 - c.cur
+                del self.stats["bp_sweeps"][n_bp:], self.stats["bp_dist"][n_bp:]
+                self.D, Dn = D, Dn_true
+                self._apply_and_bp(D, Dn, xtime, ztime)
+        self.stats["bond_dims"].append(Dn)
+        self.stats["trunc_err"].append(err)
+        log.info(f"Truncation performed, per edge error upper bound: {err}")
+        log.info(f"Layer with ztime {ztime} and xtime {xtime} has been applied")
+
+    def _truncation(self, colmax: np.ndarray, D: int):
+        """(new bond dimension, per-edge error bound) from the column maxima of the lambdas (backends.py:297-303)."""
+        rank = 2 * D - int(np.sum(colmax < self.pinv_eps))
         Dn = min(rank, self.Dmax)
-        err = float(np.sqrt(np.sum(colmax[Dn:] ** 2)))
         if Dn < 1:
             raise FloatingPointError("all singular values fell below pinv_eps: the state collapsed")
-        log.info(f"Truncation performed, per edge error upper bound: {err}")
+        return Dn, float(np.sqrt(np.sum(colmax[Dn:] ** 2)))
+
+    def _apply_and_bp(self, D: int, Dn: int, xtime: float, ztime: float) -> None:
+        """Truncated simple update D -> Dn of every class + Rz/Rx layers + symmetric gauge, then BP to convergence."""
+        st = self._stream()
         msgs_out = self._msgs[0]
         for c in self.classes:
             self.lib.apply_update(self.prec, c.degree, D, Dn, c.B, c.T[c.cur].data_ptr(), c.T[1 - c.cur].data_ptr(),
@@ -436,12 +484,9 @@ class Engine:
             c.cur = 1 - c.cur
         self._msgs_cur = 0
         self.D = Dn
-        self.stats["bond_dims"].append(Dn)
-        self.stats["trunc_err"].append(err)
         log.debug(f"Layer of interaction gates with truncation has been applied, current bond dimension is {Dn}")
         self._after_update()
         self.run_bp()
-        log.info(f"Layer with ztime {ztime} and xtime {xtime} has been applied")
 
     def _exchange_ext(self) -> None:
         """Hook for the partitioned engine (extended messages of cut edges); no-op on one GPU."""

@@ -69,7 +69,7 @@ int bqa_b200_bp_sweep_p2p(int prec, int degree, int D, long long B, const void* 
                           size_t workspace_bytes, const int32_t* remote_pos, void* const* peers, void* stream) {
   if (int rc = check_shape(prec, degree, D)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (g_kernel_mode.load() == 0 && fast_d3D4_available(prec, degree, D))
+  if (g_kernel_mode.load() == 0 && fast_d3D4_available(prec, degree, D, B))
     return launch_fast_msgs_d3D4(false, B, T, msgs_cur, msgs_nxt, in_pos, out_pos, nullptr, 0.0, damping, write_undamped,
                                  bp_eps, it, resid, status, remote_pos, peers, st);
   if (prec == BQA_C64)
@@ -95,7 +95,7 @@ int bqa_b200_ext_msgs_p2p(int prec, int degree, int D, long long B, const void* 
                           void* stream) {
   if (int rc = check_shape(prec, degree, D)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (g_kernel_mode.load() == 0 && fast_d3D4_available(prec, degree, D))
+  if (g_kernel_mode.load() == 0 && fast_d3D4_available(prec, degree, D, B))
     return launch_fast_msgs_d3D4(true, B, T, msgs_cur, ext, in_pos, out_pos, edge_ampls, ztime, 0.0, 0, 0.0, 0, nullptr,
                                  nullptr, remote_pos, peers, st);
   if (prec == BQA_C64)
@@ -119,7 +119,7 @@ int bqa_b200_bp_run(int prec, int degree, int D, long long B, const void* T, voi
                     void* stream) {
   if (int rc = check_shape(prec, degree, D)) return rc;
   if (max_iters < 1) return set_error("max_iters must be positive, got %d", max_iters);
-  if (g_kernel_mode.load() != 0 || !fast_d3D4_available(prec, degree, D)) {
+  if (g_kernel_mode.load() != 0 || !fast_d3D4_available(prec, degree, D, B)) {
     set_error("bp_run: no single-launch kernel for precision %d, degree %d, D = %d", prec, degree, D);
     return 2;                                              /* not an error: the caller enqueues bqa_b200_bp_sweep calls */
   }

@@ -26,6 +26,7 @@ __device__ __forceinline__ float2 unpk(p2 v) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
   return r;
 }
+__device__ __forceinline__ p2 swap(p2 v) { const float2 r = unpk(v); return pk(r.y, r.x); }   // (hi, lo): an operand swizzle
 __device__ __forceinline__ float hsum(p2 v) { const float2 r = unpk(v); return r.x + r.y; }
 __device__ __forceinline__ p2 fma2(p2 a, p2 b, p2 c) {       // a * b + c
   p2 d;

@@ -79,13 +79,13 @@ __device__ __forceinline__ void cmac(CAcc& acc, p2 s, p2 v) {
     acc.B = x2::fma2s(f.y, v, acc.B);
   }
 }
-__device__ __forceinline__ p2 cfinish(const CAcc& acc) {          // sum s v
-  const float2 a = x2::unpk(acc.A), b = x2::unpk(acc.B);
-  return x2::pk(a.x - b.y, a.y + b.x);
+// (one FFMA2 each: the second accumulator enters half-swapped and multiplied by (-1, 1) or (1, -1); x * (+-1) is exact,
+// so the results equal the separately rounded additions)
+__device__ __forceinline__ p2 cfinish(const CAcc& acc) {          // sum s v = (A.x - B.y, A.y + B.x)
+  return x2::fma2(x2::swap(acc.B), x2::pk(-1.f, 1.f), acc.A);
 }
-__device__ __forceinline__ float2 cfinish_conj(const CAcc& acc) {  // sum conj(s) v
-  const float2 a = x2::unpk(acc.A), b = x2::unpk(acc.B);
-  return make_float2(a.x + b.y, a.y - b.x);
+__device__ __forceinline__ float2 cfinish_conj(const CAcc& acc) {  // sum conj(s) v = (A.x + B.y, A.y - B.x)
+  return x2::unpk(x2::fma2(x2::swap(acc.B), x2::pk(1.f, -1.f), acc.A));
 }
 
 }  // namespace fast

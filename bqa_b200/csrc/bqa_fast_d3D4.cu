@@ -28,14 +28,20 @@
 namespace bqa {
 namespace fast {
 
+// 8 warps per CTA = 2 per SM sub-partition: the kernel needs ~230 registers to keep three 16-element tiles, the staged
+// tile and the copy pipeline's addresses live without spills; 3 warps per sub-partition (12 per CTA) are capped at 168
+// registers by the 16 K registers of a sub-partition and measured 9 % slower (62.6 vs 57.4 us per sweep).
 #ifndef BQA_BP_WARPS
-#define BQA_BP_WARPS 12
+#define BQA_BP_WARPS 8
 #endif
 constexpr int kWarps = BQA_BP_WARPS;
 constexpr int kThreads = kWarps * 32;
 constexpr int kSlice = 144;                       // 128-byte slice + 16 bytes of padding (bank spreading)
 constexpr int kTBytes = 32 * kSlice;              // 4 nodes x 8 slices
-constexpr int kMsg = 128;                         // one 128-byte message (no padding: 12 warps must fit in 227 KB)
+#ifndef BQA_BP_MSG_PITCH
+#define BQA_BP_MSG_PITCH 144
+#endif
+constexpr int kMsg = BQA_BP_MSG_PITCH;            // pitch of a 128-byte message: 144 spreads the 4 nodes' tiles over the banks
 constexpr int kMBytes = 12 * kMsg;                // 3 messages x 4 nodes
 constexpr int kRedRow = 80;                       // packed Hermitian partial: 4 diagonal + 6 upper entries (complex)
 constexpr int kRedSlot = 8 * kRedRow + 64;        // 8 lanes of a node (+ skew between the two nodes of a half warp)
@@ -63,74 +69,98 @@ struct Args {
   unsigned char* peers[BQA_MAX_PEERS];
 };
 
-// issue the copies of one 4-node group into a stage: T (coalesced 4 KB), 12 incoming and 12 previous
-// outgoing messages (each by the 8 lanes of a quarter warp: one full 128-byte line)
+__device__ __forceinline__ float rcp_approx(float v) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+// sum over the 8 lanes of a node (aligned groups of 8 lanes)
+__device__ __forceinline__ float allreduce8(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  return v;
+}
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16_s(unsigned dst, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(gmem) : "memory");
+}
+
+// Per-lane constants of the copy pipeline.  A group is 4 consecutive nodes starting at n0 = min(4 g, B - 4): the last
+// group of a class whose size is not a multiple of 4 overlaps its predecessor (those nodes are computed twice with
+// identical results), so no copy and no store is ever predicated.
+//   index register: lane 8 s + i holds in_pos[i][n0 + s] (i = 0..2) and out_pos[i - 3][n0 + s] (i = 3..5)
+struct Pipe {
+  unsigned sT, sM;                 // shared-memory destinations of this lane's first T chunk / message chunk (stage 0)
+  const unsigned char* gT;         // a.T + 16 lane
+  const unsigned char* gM;         // a.msgs_cur + 16 (lane % 8)
+  const int32_t* idx_ptr;          // this lane's row of in_pos / out_pos (+ node slot); nullptr for lanes t >= 6
+  const int32_t* rp_ptr;           // this lane's row of remote_pos; nullptr on one GPU and for lanes t >= 3
+};
+
+// (volatile: the loads stay where they are written, behind the copies that consume the previous index register --
+// hoisted above them they share a scoreboard with the older load and stall its consumers for a full memory latency)
+__device__ __forceinline__ int ldg_ordered(const int32_t* ptr) {
+  int v;
+  asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+  return v;
+}
+__device__ __forceinline__ int load_idx(const Pipe& q, int n0) { return q.idx_ptr ? ldg_ordered(q.idx_ptr + n0) : 0; }
+__device__ __forceinline__ int load_rpos(const Pipe& q, int n0) { return q.rp_ptr ? ldg_ordered(q.rp_ptr + n0) : -1; }
+
+// issue the copies of one 4-node group into a stage: T (coalesced 4 KB), 12 incoming and 12 previous outgoing
+// messages (each by the 8 lanes of a quarter warp: one full 128-byte line).  All offsets are immediates.
 template <bool EXT>
-__device__ __forceinline__ void issue_group(const Args& a, unsigned char* stage, long long node0, int lane,
-                                            int idx_reg) {
-  const long long last = a.B - 1;
-  const unsigned char* Tg = reinterpret_cast<const unsigned char*>(a.T);
+__device__ __forceinline__ void issue_group(const Pipe& q, unsigned stage_off, int n0, int idx_reg) {
+  const unsigned char* src = q.gT + (size_t)(unsigned)n0 * 1024;
+  const unsigned dT = q.sT + stage_off, dM = q.sM + stage_off;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int c = i * 32 + lane;                 // 16-byte chunk of the 4 KB block
-    const int s = c >> 6;                        // node slot
-    long long node = node0 + s;
-    node = node > last ? last : node;
-    cp_async16(stage + (c >> 3) * kSlice + (c & 7) * 16, Tg + node * 1024 + (c & 63) * 16);
-  }
-  const unsigned char* Mg = reinterpret_cast<const unsigned char*>(a.msgs_cur);
-  const int s = lane >> 3, ch = lane & 7;
+  for (int i = 0; i < 8; ++i) cp_async16_s(dT + i * 4 * kSlice, src + i * 512);
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
-    const int pin = __shfl_sync(0xffffffffu, idx_reg, j * 4 + s);
-    cp_async16(stage + kTBytes + (j * 4 + s) * kMsg + ch * 16, Mg + (size_t)pin * 128 + ch * 16);
+    const unsigned pin = (unsigned)__shfl_sync(0xffffffffu, idx_reg, j, 8);
+    cp_async16_s(dM + j * 4 * kMsg, q.gM + (size_t)pin * 128);
     if (!EXT) {
-      const int pout = __shfl_sync(0xffffffffu, idx_reg, 12 + j * 4 + s);
-      cp_async16(stage + kTBytes + kMBytes + (j * 4 + s) * kMsg + ch * 16, Mg + (size_t)pout * 128 + ch * 16);
+      const unsigned pout = (unsigned)__shfl_sync(0xffffffffu, idx_reg, 3 + j, 8);
+      cp_async16_s(dM + kMBytes + j * 4 * kMsg, q.gM + (size_t)pout * 128);
     }
   }
 }
 
-// lanes 0..11 hold in_pos[j][node0 + s], lanes 12..23 hold out_pos[j][node0 + s]  (index j * 4 + s)
-__device__ __forceinline__ int load_idx(const Args& a, long long node0, int lane) {
-  int v = 0;
-  if (lane < 24) {
-    const int l = lane < 12 ? lane : lane - 12;
-    long long node = node0 + (l & 3);
-    node = node > a.B - 1 ? a.B - 1 : node;
-    const int32_t* src = lane < 12 ? a.in_pos : a.out_pos;
-    v = __ldg(src + (size_t)(l >> 2) * a.B + node);
-  }
-  return v;
-}
-
-// lanes 0..11 hold remote_pos[j][node0 + s] (index j * 4 + s); -1 everywhere on one GPU
-__device__ __forceinline__ int load_rpos(const Args& a, long long node0, int lane) {
-  int v = -1;
-  if (a.remote_pos != nullptr && lane < 12) {
-    long long node = node0 + (lane & 3);
-    if (node < a.B) v = __ldg(a.remote_pos + (size_t)(lane >> 2) * a.B + node);
-  }
-  return v;
-}
-
-// One sweep (or one extended-message pass) over the degree class by this CTA's warps.
-template <bool EXT>
-__device__ __forceinline__ void sweep(const Args& a, unsigned char* smem) {
+// One sweep (or one extended-message pass) over the degree class by this CTA's warps.  Requires 4 <= B < 2^29.
+// (the per-sweep fields are parameters and the peer table is an accessor so that the single-launch kernel can keep its
+// arguments in constant memory: a modified local copy of `Args` would live on the stack because of the dynamic peer index)
+struct PeersOfArgs {
+  const Args& a;
+  __device__ __forceinline__ unsigned char* operator()(int q) const { return a.peers[q]; }
+};
+template <bool EXT, bool MULTI, class Peers>
+__device__ __forceinline__ void sweep(const Args& a, const float2* msgs_cur, float2* msgs_out, int it, int write_undamped,
+                                      const Peers peers, unsigned char* smem) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int s = lane >> 3, t = lane & 7, p = t >> 2, la = t & 3;     // node slot, lane in node, physical, leg-0 index
   unsigned char* wbase = smem + wib * kWarpBytes;
   unsigned char* scratch = wbase + 2 * kStage;
-  const long long groups = (a.B + 3) >> 2;
-  const long long nwarps = (long long)gridDim.x * kWarps;
-  long long g = (long long)blockIdx.x * kWarps + wib;
+  const int B = (int)a.B;
+  const int groups = (B + 3) >> 2, tail0 = B - 4;
+  const int nwarps = (int)gridDim.x * kWarps;
+  int g = (int)blockIdx.x * kWarps + wib;
+  constexpr bool multi = MULTI;                             // boundary messages are also stored into the peers' halo slots
   float mnum = 0.f, mden = 0.f;
+
+  Pipe q;
+  q.sT = smem_u32(wbase) + (lane >> 3) * kSlice + (lane & 7) * 16;
+  q.sM = smem_u32(wbase) + kTBytes + s * kMsg + t * 16;
+  q.gT = reinterpret_cast<const unsigned char*>(a.T) + lane * 16;
+  q.gM = reinterpret_cast<const unsigned char*>(msgs_cur) + t * 16;
+  q.idx_ptr = t < 6 ? (t < 3 ? a.in_pos + (size_t)t * B : a.out_pos + (size_t)(t - 3) * B) + s : nullptr;
+  q.rp_ptr = (multi && t < 3) ? a.remote_pos + (size_t)t * B + s : nullptr;
 
   // packed Hermitian partials: entry (x, x) at complex index x, entry (x < y) at 4 + pair(x, y); this lane finally
   // owns (x, y0) and (x, y0 + 1), x = t / 2, y0 = 2 (t % 2); a lower-triangle entry is the conjugate of its mirror
-  int offA, offB;
-  float sgnA, sgnB;
-  {
+  int offA = 0, offB = 0;
+  float sgnA = 1.f, sgnB = 1.f;
+  if (EXT) {
     const int x = t >> 1, y0 = (t & 1) * 2;
     auto pack = [](int i, int j) { return i == j ? i : 4 + (i == 0 ? j - 1 : (i == 1 ? j + 1 : 5)); };
     const int ya = y0, yb = y0 + 1;
@@ -149,23 +179,33 @@ __device__ __forceinline__ void sweep(const Args& a, unsigned char* smem) {
   const int a_c = (0xA264u >> (2 * t)) & 3, b_c = (0x2645u >> (2 * t)) & 3;
   const float a_im = a_c == 0 ? 0.f : (a_c == 1 ? 1.f : -1.f);        // sign of the imaginary part (0 on the diagonal)
   const float b_im = b_c == 0 ? 0.f : (b_c == 1 ? 1.f : -1.f);
+  const p2 rot = x2::pk(-1.f, 1.f);                                   // (y, x) * rot = (-y, x) = i (x + i y)
   int idx_cur = 0, idx_nxt = 0, rp_cur = -1, rp_nxt = -1;
   if (g < groups) {
-    idx_cur = load_idx(a, g * 4, lane);
-    rp_cur = load_rpos(a, g * 4, lane);
-    issue_group<EXT>(a, wbase, g * 4, lane, idx_cur);
+    const int n0 = min(g * 4, tail0);
+    idx_cur = load_idx(q, n0);
+    rp_cur = load_rpos(q, n0);
+    issue_group<EXT>(q, 0u, n0, idx_cur);
     cp_async_commit();
-    if (g + nwarps < groups) { idx_nxt = load_idx(a, (g + nwarps) * 4, lane); rp_nxt = load_rpos(a, (g + nwarps) * 4, lane); }
+    if (g + nwarps < groups) {
+      const int n1 = min((g + nwarps) * 4, tail0);
+      idx_nxt = load_idx(q, n1);
+      rp_nxt = load_rpos(q, n1);
+    }
   }
   int cur = 0;
 #pragma unroll 1
   for (; g < groups; g += nwarps, cur ^= 1) {
     unsigned char* st = wbase + cur * kStage;
-    const bool has_next = g + nwarps < groups;
+    const int n0 = min(g * 4, tail0);
     int idx_nn = 0, rp_nn = -1;
-    if (has_next) {
-      issue_group<EXT>(a, wbase + (cur ^ 1) * kStage, (g + nwarps) * 4, lane, idx_nxt);
-      if (g + 2 * nwarps < groups) { idx_nn = load_idx(a, (g + 2 * nwarps) * 4, lane); rp_nn = load_rpos(a, (g + 2 * nwarps) * 4, lane); }
+    if (g + nwarps < groups) {
+      issue_group<EXT>(q, cur ? 0u : (unsigned)kStage, min((g + nwarps) * 4, tail0), idx_nxt);
+      if (g + 2 * nwarps < groups) {
+        const int n2 = min((g + 2 * nwarps) * 4, tail0);
+        idx_nn = load_idx(q, n2);
+        rp_nn = load_rpos(q, n2);
+      }
     }
     cp_async_commit();                                      // always commit (possibly empty): one loop body, one wait
     cp_async_wait<1>();
@@ -173,13 +213,12 @@ __device__ __forceinline__ void sweep(const Args& a, unsigned char* smem) {
 
     float th[3] = {0.f, 0.f, 0.f};
     if (EXT) {                                              // coupling angles of this node's 3 legs, fetched early
-      long long nn = g * 4 + s;
-      nn = nn > a.B - 1 ? a.B - 1 : nn;
 #pragma unroll
-      for (int k = 0; k < 3; ++k) th[k] = __ldg(a.edge_ampls + (size_t)k * a.B + nn) * a.ztime;
+      for (int k = 0; k < 3; ++k) th[k] = __ldg(a.edge_ampls + (size_t)k * B + n0 + s) * a.ztime;
     }
     const unsigned char* Ts = st + (s * 8 + p * 4) * kSlice;          // the four a-slices of (node, p)
     const unsigned char* Min = st + kTBytes;
+    const unsigned char* m0row = Min + (0 * 4 + s) * kMsg + la * 32;  // row `la` of m0
     p2 U0[16], U1[16], U2[16];
     {
       p2 tt[16], m[16];
@@ -210,10 +249,9 @@ __device__ __forceinline__ void sweep(const Args& a, unsigned char* smem) {
         }
       // U0[a][b][c] = sum_a' m0[a][a'] T[a'][b][c], row a = `la` of m0.  The matrix element is the prepared pair operand
       // (m, i m), the tensor elements enter as broadcast scalars.  Term a' = la: this lane's own slice, still in registers
-      const unsigned char* m0row = Min + (0 * 4 + s) * kMsg + la * 32;
       {
-        const float2 mf = *reinterpret_cast<const float2*>(m0row + la * 8);
-        const p2 mm = x2::pk(mf.x, mf.y), im = x2::pk(-mf.y, mf.x);
+        const p2 mm = *reinterpret_cast<const p2*>(m0row + la * 8);
+        const p2 im = x2::mul2(x2::swap(mm), rot);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float2 tf = x2::unpk(tt[i]);
@@ -221,22 +259,20 @@ __device__ __forceinline__ void sweep(const Args& a, unsigned char* smem) {
         }
       }
     }
-    {
-      // the three other slices from shared memory: the 8 lanes of a node read 8 distinct slices (conflict-free)
-      const unsigned char* m0row = Min + (0 * 4 + s) * kMsg + la * 32;
-#pragma unroll 1
-      for (int r = 1; r < 4; ++r) {                         // rolled: code size (instruction cache) matters
-        const int a2 = (la + r) & 3;
-        p2 tt[16];
-        lds_tile(tt, Ts + a2 * kSlice);
-        const float2 mf = *reinterpret_cast<const float2*>(m0row + a2 * 8);
-        const p2 m = x2::pk(mf.x, mf.y), im = x2::pk(-mf.y, mf.x);
+    // the three other slices from shared memory: the 8 lanes of a node read 8 distinct slices (conflict-free)
+    // (unrolled in the BP kernel; rolled in the extended-message kernel, whose body must stay inside the I-cache)
+#pragma unroll(EXT ? 1 : 3)
+    for (int r = 1; r < 4; ++r) {
+      const int a2 = (la + r) & 3;
+      p2 tt[16];
+      lds_tile(tt, Ts + a2 * kSlice);
+      const p2 mm = *reinterpret_cast<const p2*>(m0row + a2 * 8);
+      const p2 im = x2::mul2(x2::swap(mm), rot);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float2 tf = x2::unpk(tt[i]);
-          U0[i] = x2::fma2s(tf.x, m, U0[i]);
-          U0[i] = x2::fma2s(tf.y, im, U0[i]);
-        }
+      for (int i = 0; i < 16; ++i) {
+        const float2 tf = x2::unpk(tt[i]);
+        U0[i] = x2::fma2s(tf.x, mm, U0[i]);
+        U0[i] = x2::fma2s(tf.y, im, U0[i]);
       }
     }
     __syncwarp();                                           // every lane is done with the T slices
@@ -244,6 +280,9 @@ __device__ __forceinline__ void sweep(const Args& a, unsigned char* smem) {
     sts_tile(Xs + la * kSlice, U1);
 
     float2 e[3][4];                                         // per message k: [g0 piece (2), g1 piece (2)]; BP sums them
+    float tr[3];                                            // traces (real: the outputs are Hermitian), all-reduced over the
+                                                            // node's 8 lanes from the lanes' partial diagonals -- three short
+                                                            // shuffle chains that overlap the arithmetic instead of ending it
     unsigned char* red = scratch + s * kRedSlot;
     // ---- out_1[x][y] = sum_{a,c} conj(U2[a][x][c]) U0[a][y][c],  out_2[x][y] = sum_{a,b} conj(U1[a][b][x]) U0[a][b][y]
     // (partial over this lane's (p, a); Hermitian: diagonal real parts and the upper triangle only)
@@ -254,8 +293,8 @@ __device__ __forceinline__ void sweep(const Args& a, unsigned char* smem) {
       for (int x = 0; x < 4; ++x) {                         // diagonal: sum of element-wise pair products
         p2 d2 = x2::mul2((k == 1) ? U2[x * 4] : U1[x], (k == 1) ? U0[x * 4] : U0[x]);
 #pragma unroll
-        for (int q = 1; q < 4; ++q)
-          d2 = x2::fma2((k == 1) ? U2[x * 4 + q] : U1[q * 4 + x], (k == 1) ? U0[x * 4 + q] : U0[q * 4 + x], d2);
+        for (int qq = 1; qq < 4; ++qq)
+          d2 = x2::fma2((k == 1) ? U2[x * 4 + qq] : U1[qq * 4 + x], (k == 1) ? U0[x * 4 + qq] : U0[qq * 4 + x], d2);
         acc[x] = make_float2(x2::hsum(d2), 0.f);
       }
       {
@@ -267,11 +306,12 @@ __device__ __forceinline__ void sweep(const Args& a, unsigned char* smem) {
             CAcc v;
             cmac<true>(v, (k == 1) ? U2[x * 4] : U1[x], (k == 1) ? U0[y * 4] : U0[y]);
 #pragma unroll
-            for (int q = 1; q < 4; ++q)
-              cmac<false>(v, (k == 1) ? U2[x * 4 + q] : U1[q * 4 + x], (k == 1) ? U0[y * 4 + q] : U0[q * 4 + y]);
+            for (int qq = 1; qq < 4; ++qq)
+              cmac<false>(v, (k == 1) ? U2[x * 4 + qq] : U1[qq * 4 + x], (k == 1) ? U0[y * 4 + qq] : U0[qq * 4 + y]);
             acc[n++] = cfinish_conj(v);
           }
       }
+      tr[k] = allreduce8((acc[0].x + acc[1].x) + (acc[2].x + acc[3].x));
       if (!EXT) {
         // reduce-scatter over the node's 8 lanes (p and a): 14 shuffles, then one pair from the partner lane
         float z[16] = {acc[4].x, acc[4].y, acc[5].x, acc[5].y, acc[0].x, acc[1].x, acc[8].x, acc[8].y,
@@ -315,7 +355,9 @@ __device__ __forceinline__ void sweep(const Args& a, unsigned char* smem) {
         e[k][2] = make_float2(g1a.x, sgnA * g1a.y); e[k][3] = make_float2(g1b.x, sgnB * g1b.y);
       }
     }
-    // ---- out_0[x][y] = sum_{b,c} conj(U1[x][b][c]) U2[y][b][c]: lane (p, y = la) against the exchanged U1 slices
+    // ---- out_0[x][y] = sum_{b,c} conj(U1[x][b][c]) U2[y][b][c]: lane (p, y = la) against the exchanged U1 slices.
+    // Hermitian: the lane computes (la, la), (la + 1, la) and -- lanes la < 2 only keep it -- (la + 2, la); the mirrored
+    // entries are stored as conjugates, (la + 3, la) is the mirror of the next lane's (la + 1, la).
     {
       unsigned char* o0 = scratch + kOut0 + s * 64;         // [x][node][p][y]: a warp-wide store is 256 contiguous bytes
       {                                                     // x = la: this lane's own U1 slice is still in registers
@@ -325,10 +367,13 @@ __device__ __forceinline__ void sweep(const Args& a, unsigned char* smem) {
 #pragma unroll
         for (int i = 2; i < 16; i += 2) { cmac<false>(v0, U1[i], U2[i]); cmac<false>(v1, U1[i + 1], U2[i + 1]); }
         const float2 r0 = cfinish_conj(v0), r1 = cfinish_conj(v1);
-        *reinterpret_cast<float2*>(o0 + la * kOut0Row + p * 32 + la * 8) = make_float2(r0.x + r1.x, r0.y + r1.y);
+        const float dg = r0.x + r1.x;
+        tr[0] = allreduce8(dg);
+        *reinterpret_cast<float2*>(o0 + la * kOut0Row + p * 32 + la * 8) = make_float2(dg, 0.f);
       }
-#pragma unroll 1
-      for (int r = 1; r < 4; ++r) {                         // rolled: code size; the 8 lanes of a node read 8 distinct slices
+      __syncwarp();                                         // the U1 slices of the other lanes are visible
+#pragma unroll(EXT ? 1 : 2)
+      for (int r = 1; r < 3; ++r) {                         // the 8 lanes of a node read 8 distinct slices
         const int x = (la + r) & 3;
         p2 ux[16];
         lds_tile(ux, Xs + x * kSlice);
@@ -338,7 +383,11 @@ __device__ __forceinline__ void sweep(const Args& a, unsigned char* smem) {
 #pragma unroll
         for (int i = 2; i < 16; i += 2) { cmac<false>(v0, ux[i], U2[i]); cmac<false>(v1, ux[i + 1], U2[i + 1]); }
         const float2 r0 = cfinish_conj(v0), r1 = cfinish_conj(v1);
-        *reinterpret_cast<float2*>(o0 + x * kOut0Row + p * 32 + la * 8) = make_float2(r0.x + r1.x, r0.y + r1.y);
+        const float2 v = make_float2(r0.x + r1.x, r0.y + r1.y);
+        if (r == 1 || la < 2) {
+          *reinterpret_cast<float2*>(o0 + x * kOut0Row + p * 32 + la * 8) = v;
+          *reinterpret_cast<float2*>(o0 + la * kOut0Row + p * 32 + x * 8) = make_float2(v.x, -v.y);
+        }
       }
       __syncwarp();
       const float4 v0 = *reinterpret_cast<const float4*>(o0 + (t >> 1) * kOut0Row + (t & 1) * 16);
@@ -348,67 +397,57 @@ __device__ __forceinline__ void sweep(const Args& a, unsigned char* smem) {
     }
 
     // ---- epilogue: lane t owns elements (x, y0) and (x, y0 + 1) of every message, x = t / 2, y0 = 2 (t % 2)
-    const long long node = g * 4 + s;
-    const bool live = node < a.B;
     const int x = t >> 1, y0 = (t & 1) * 2;
+    unsigned char* const out_base = reinterpret_cast<unsigned char*>(msgs_out) + t * 16;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       const float2 sa = make_float2(e[k][0].x + e[k][2].x, e[k][0].y + e[k][2].y);
       const float2 sb = make_float2(e[k][1].x + e[k][3].x, e[k][1].y + e[k][3].y);
-      float2 tr = (x == y0) ? sa : ((x == y0 + 1) ? sb : make_float2(0.f, 0.f));
-#pragma unroll
-      for (int o = 1; o < 8; o <<= 1) {
-        tr.x += __shfl_xor_sync(0xffffffffu, tr.x, o);
-        tr.y += __shfl_xor_sync(0xffffffffu, tr.y, o);
+      const unsigned slot = (unsigned)__shfl_sync(0xffffffffu, idx_cur, 3 + k, 8);
+      unsigned char* far = nullptr;
+      if (multi) {
+        const int rp = __shfl_sync(0xffffffffu, rp_cur, k, 8);
+        if (rp >= 0) far = peers(rp >> 27) + (size_t)(rp & ((1 << 27) - 1)) * (EXT ? 512 : 128) + (EXT ? 0 : t * 16);
       }
-      const int slot = __shfl_sync(0xffffffffu, idx_cur, 12 + k * 4 + s);
-      const int rp = __shfl_sync(0xffffffffu, rp_cur, k * 4 + s);
-      unsigned char* far = rp < 0 ? nullptr : a.peers[rp >> 27] + (size_t)(rp & ((1 << 27) - 1)) * (EXT ? 512 : 128);
       if (!EXT) {
-        const float d = 1.f / (tr.x * tr.x + tr.y * tr.y);
-        const float2 itr = make_float2(tr.x * d, -tr.y * d);
-        const float2 na = cmul(itr, sa), nb = cmul(itr, sb);
+        const float d = rcp_approx(tr[k]);
+        const float2 na = make_float2(sa.x * d, sa.y * d), nb = make_float2(sb.x * d, sb.y * d);
         const float4 ov = *reinterpret_cast<const float4*>(st + kTBytes + kMBytes + (k * 4 + s) * kMsg + t * 16);
-        if (live) {
-          float da = (na.x - ov.x) * (na.x - ov.x) + (na.y - ov.y) * (na.y - ov.y);
-          float db = (nb.x - ov.z) * (nb.x - ov.z) + (nb.y - ov.w) * (nb.y - ov.w);
-          mnum = fmaxf(mnum, fmaxf(da, db));
-          da = (na.x + ov.x) * (na.x + ov.x) + (na.y + ov.y) * (na.y + ov.y);
-          db = (nb.x + ov.z) * (nb.x + ov.z) + (nb.y + ov.w) * (nb.y + ov.w);
-          mden = fmaxf(mden, fmaxf(da, db));
-          float4 w;
-          if (a.write_undamped) {
-            w = make_float4(na.x, na.y, nb.x, nb.y);
-          } else {
-            const float al = a.damping, be = 1.f - a.damping;
-            w = make_float4(al * ov.x + be * na.x, al * ov.y + be * na.y, al * ov.z + be * nb.x, al * ov.w + be * nb.y);
-          }
-          *reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(a.msgs_out) + (size_t)slot * 128 + t * 16) = w;
-          if (far) *reinterpret_cast<float4*>(far + t * 16) = w;      // halo slot on the peer that owns the receiver
+        float da = (na.x - ov.x) * (na.x - ov.x) + (na.y - ov.y) * (na.y - ov.y);
+        float db = (nb.x - ov.z) * (nb.x - ov.z) + (nb.y - ov.w) * (nb.y - ov.w);
+        mnum = fmaxf(mnum, fmaxf(da, db));
+        da = (na.x + ov.x) * (na.x + ov.x) + (na.y + ov.y) * (na.y + ov.y);
+        db = (nb.x + ov.z) * (nb.x + ov.z) + (nb.y + ov.w) * (nb.y + ov.w);
+        mden = fmaxf(mden, fmaxf(da, db));
+        float4 w;
+        if (write_undamped) {
+          w = make_float4(na.x, na.y, nb.x, nb.y);
+        } else {
+          const float al = a.damping, be = 1.f - a.damping;
+          w = make_float4(al * ov.x + be * na.x, al * ov.y + be * na.y, al * ov.z + be * nb.x, al * ov.w + be * nb.y);
         }
+        *reinterpret_cast<float4*>(out_base + (size_t)slot * 128) = w;
+        if (far) *reinterpret_cast<float4*>(far) = w;      // halo slot on the peer that owns the receiver
       } else {
         // ext[(s1,x),(s2,y)] = conj(f_s1) f_s2 (g0 + (-1)^(s1+s2) g1)[x][y] / ((|f0|^2 + |f1|^2) trace)
         cx<float> f0, f1;
         zz_factors<float>(th[k], f0, f1);
         const float2 ff[2] = {make_float2(f0.re, f0.im), make_float2(f1.re, f1.im)};
         const float w = (f0.re * f0.re + f0.im * f0.im + f1.re * f1.re + f1.im * f1.im);
-        const float d = 1.f / (w * (tr.x * tr.x + tr.y * tr.y));
-        const float2 itr = make_float2(tr.x * d, -tr.y * d);
+        const float2 itr = make_float2(1.f / (w * tr[k]), 0.f);
         const float2 da = make_float2(e[k][0].x - e[k][2].x, e[k][0].y - e[k][2].y);
         const float2 db = make_float2(e[k][1].x - e[k][3].x, e[k][1].y - e[k][3].y);
-        if (live) {
-          unsigned char* dst = reinterpret_cast<unsigned char*>(a.msgs_out) + (size_t)slot * 512;
+        unsigned char* dst = reinterpret_cast<unsigned char*>(msgs_out) + (size_t)slot * 512;
 #pragma unroll
-          for (int s1 = 0; s1 < 2; ++s1)
+        for (int s1 = 0; s1 < 2; ++s1)
 #pragma unroll
-            for (int s2 = 0; s2 < 2; ++s2) {
-              const float2 cf = cmul(itr, cmul(make_float2(ff[s1].x, -ff[s1].y), ff[s2]));
-              const float2 va = cmul(cf, s1 == s2 ? sa : da), vb = cmul(cf, s1 == s2 ? sb : db);
-              const float4 w4 = make_float4(va.x, va.y, vb.x, vb.y);
-              *reinterpret_cast<float4*>(dst + ((s1 * 4 + x) * 8 + s2 * 4 + y0) * 8) = w4;
-              if (far) *reinterpret_cast<float4*>(far + ((s1 * 4 + x) * 8 + s2 * 4 + y0) * 8) = w4;
-            }
-        }
+          for (int s2 = 0; s2 < 2; ++s2) {
+            const float2 cf = cmul(itr, cmul(make_float2(ff[s1].x, -ff[s1].y), ff[s2]));
+            const float2 va = cmul(cf, s1 == s2 ? sa : da), vb = cmul(cf, s1 == s2 ? sb : db);
+            const float4 w4 = make_float4(va.x, va.y, vb.x, vb.y);
+            *reinterpret_cast<float4*>(dst + ((s1 * 4 + x) * 8 + s2 * 4 + y0) * 8) = w4;
+            if (far) *reinterpret_cast<float4*>(far + ((s1 * 4 + x) * 8 + s2 * 4 + y0) * 8) = w4;
+          }
       }
     }
     idx_cur = idx_nxt;
@@ -424,14 +463,14 @@ __device__ __forceinline__ void sweep(const Args& a, unsigned char* smem) {
       mden = fmaxf(mden, __shfl_xor_sync(0xffffffffu, mden, o));
     }
     if (lane == 0) {
-      atomicMax(reinterpret_cast<unsigned int*>(a.resid + 2 * a.it), __float_as_uint(mnum));
-      atomicMax(reinterpret_cast<unsigned int*>(a.resid + 2 * a.it + 1), __float_as_uint(mden));
+      atomicMax(reinterpret_cast<unsigned int*>(a.resid + 2 * it), __float_as_uint(mnum));
+      atomicMax(reinterpret_cast<unsigned int*>(a.resid + 2 * it + 1), __float_as_uint(mden));
     }
   }
 }
 
-template <bool EXT>
-__global__ void __launch_bounds__(kThreads, 1) k_msgs_d3D4(Args a) {
+template <bool EXT, bool MULTI>
+__global__ void __launch_bounds__(kThreads, 1) k_msgs_d3D4(const __grid_constant__ Args a) {
   extern __shared__ __align__(16) unsigned char smem[];
   if (!EXT && a.it > 0) {                                   // device-side early exit after convergence
     if (*((volatile int32_t*)a.status) != 0) return;
@@ -441,7 +480,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_msgs_d3D4(Args a) {
       return;
     }
   }
-  sweep<EXT>(a, smem);
+  sweep<EXT, MULTI>(a, a.msgs_cur, a.msgs_out, a.it, a.write_undamped, PeersOfArgs{a}, smem);
 }
 
 // ---- whole BP run in ONE cooperative launch (reference _run_bp, state.py:97-124) ----------------------------------
@@ -492,23 +531,25 @@ __device__ __forceinline__ bool grid_barrier(unsigned* counter, unsigned& genera
   return ok != 0;
 }
 
-__global__ void __launch_bounds__(kThreads, 1) k_bp_run_d3D4(RunArgs r) {
+struct PeersOfRun {
+  const RunArgs& r;
+  int buf;
+  __device__ __forceinline__ unsigned char* operator()(int q) const { return r.peers[buf][q]; }
+};
+
+template <bool MULTI>
+__global__ void __launch_bounds__(kThreads, 1) k_bp_run_d3D4(const __grid_constant__ RunArgs r) {
   extern __shared__ __align__(16) unsigned char smem[];
-  Args a = r.base;
+  const Args& a = r.base;
   unsigned* counter = reinterpret_cast<unsigned*>(a.status + 2);
   unsigned generation = 0;
   int sweeps = r.max_iters, converged = 0;
   for (int it = 0; it < r.max_iters; ++it) {
     const int cur = (r.parity + it) & 1;
-    a.msgs_cur = r.msgs[cur];
-    a.msgs_out = r.msgs[cur ^ 1];
-#pragma unroll
-    for (int q = 0; q < BQA_MAX_PEERS; ++q) a.peers[q] = r.peers[cur ^ 1][q];
-    a.it = it;
-    a.write_undamped = it == r.max_iters - 1;               // cap reached: the undamped sweep is kept (state.py:122-123)
-    sweep<false>(a, smem);
+    // cap reached: the undamped sweep is kept (state.py:122-123)
+    sweep<false, MULTI>(a, r.msgs[cur], r.msgs[cur ^ 1], it, it == r.max_iters - 1, PeersOfRun{r, cur ^ 1}, smem);
     if (!grid_barrier(counter, generation, a.status)) return;
-    if (r.world > 1) {
+    if (MULTI && r.world > 1) {
       if (blockIdx.x == 0 && threadIdx.x < r.world && (int)threadIdx.x != r.rank) {
         const int q = threadIdx.x;
         const unsigned* mine = reinterpret_cast<const unsigned*>(a.resid) + 2 * it;
@@ -552,7 +593,8 @@ int launch_fast_bp_run_d3D4(long long B, const void* T, void* msgs0, void* msgs1
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(k_bp_run_d3D4, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaError_t e = cudaFuncSetAttribute(k_bp_run_d3D4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_bp_run_d3D4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(k_bp_run_d3D4): %s", cudaGetErrorString(e));
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
@@ -573,13 +615,17 @@ int launch_fast_bp_run_d3D4(long long B, const void* T, void* msgs0, void* msgs1
   long long grid = (groups + kWarps - 1) / kWarps;
   if (grid > sm_count()) grid = sm_count();
   void* params[] = {&r};
-  cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_bp_run_d3D4, dim3((unsigned)grid), dim3(kThreads), params,
-                                              (size_t)kSmem, st);
+  const bool multi = world > 1 || a.remote_pos != nullptr;
+  const void* fn = multi ? (const void*)k_bp_run_d3D4<true> : (const void*)k_bp_run_d3D4<false>;
+  cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(kThreads), params, (size_t)kSmem, st);
   if (e != cudaSuccess) return set_error("cudaLaunchCooperativeKernel(k_bp_run_d3D4): %s", cudaGetErrorString(e));
   return after_launch("bp_run(d3D4)");
 }
 
-bool fast_d3D4_available(int prec, int degree, int D) { return prec == 0 && degree == 3 && D == 4; }
+// a group is 4 nodes (the last one may overlap its predecessor), node offsets are 32-bit: 4 <= B < 2^29 (or empty)
+bool fast_d3D4_available(int prec, int degree, int D, long long B) {
+  return prec == 0 && degree == 3 && D == 4 && (B == 0 || (B >= 4 && B < (1LL << 29)));
+}
 
 int launch_fast_msgs_d3D4(bool ext, long long B, const void* T, const void* msgs_cur, void* msgs_out,
                           const int32_t* in_pos, const int32_t* out_pos, const void* edge_ampls, double ztime,
@@ -591,8 +637,10 @@ int launch_fast_msgs_d3D4(bool ext, long long B, const void* T, const void* msgs
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    cudaError_t e1 = cudaFuncSetAttribute(k_msgs_d3D4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    cudaError_t e2 = cudaFuncSetAttribute(k_msgs_d3D4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaError_t e1 = cudaFuncSetAttribute(k_msgs_d3D4<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaError_t e2 = cudaFuncSetAttribute(k_msgs_d3D4<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_msgs_d3D4<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_msgs_d3D4<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e1 != cudaSuccess || e2 != cudaSuccess)
       return set_error("cudaFuncSetAttribute(k_msgs_d3D4): %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
     if (dev >= 0 && dev < 64) configured[dev] = true;
@@ -607,8 +655,11 @@ int launch_fast_msgs_d3D4(bool ext, long long B, const void* T, const void* msgs
   const long long groups = (B + 3) / 4;
   long long grid = (groups + kWarps - 1) / kWarps;
   if (grid > sm_count()) grid = sm_count();
-  if (ext) k_msgs_d3D4<true><<<(int)grid, kThreads, kSmem, st>>>(a);
-  else k_msgs_d3D4<false><<<(int)grid, kThreads, kSmem, st>>>(a);
+  const bool multi = a.remote_pos != nullptr;
+  if (ext && multi) k_msgs_d3D4<true, true><<<(int)grid, kThreads, kSmem, st>>>(a);
+  else if (ext) k_msgs_d3D4<true, false><<<(int)grid, kThreads, kSmem, st>>>(a);
+  else if (multi) k_msgs_d3D4<false, true><<<(int)grid, kThreads, kSmem, st>>>(a);
+  else k_msgs_d3D4<false, false><<<(int)grid, kThreads, kSmem, st>>>(a);
   return after_launch(ext ? "ext_msgs(d3D4)" : "bp_sweep(d3D4)");
 }
 

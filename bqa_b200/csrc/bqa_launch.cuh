@@ -50,7 +50,7 @@ int launch_threshold(int d, int D, long long B, void* T, const int32_t* node_ids
                      int32_t* outcomes, double thr, int32_t* n_proj, cudaStream_t st);
 
 // specialised kernels (bqa_fast_d3D4.cu): degree 3, D = 4, complex64
-bool fast_d3D4_available(int prec, int degree, int D);
+bool fast_d3D4_available(int prec, int degree, int D, long long B);
 int launch_fast_msgs_d3D4(bool ext, long long B, const void* T, const void* msgs_cur, void* msgs_out,
                           const int32_t* in_pos, const int32_t* out_pos, const void* edge_ampls, double ztime,
                           double damping, int write_undamped, double bp_eps, int it, void* resid, int32_t* status,

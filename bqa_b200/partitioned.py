@@ -337,6 +337,7 @@ class PartitionedEngine(Engine):
         # launches stop after different numbers of barriers): single launch only if it is possible everywhere
         active = [c.degree for c in self.classes if c.degree > 0 and c.B > 0]
         ok = len(active) == 1 and self._single_launch_ok and self.p2p
+        ok = ok and all(c.B >= 4 for c in self.classes if c.degree > 0 and c.B > 0)   # groups of 4 nodes (bqa_fast_d3D4.cu)
         deg = active[0] if ok else -1
         flag = torch.tensor([1 if ok else 0, deg, -deg], device=dev)      # MIN over ranks: all ok, min degree, -max degree
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)

@@ -8,7 +8,7 @@
 //
 // Four lanes own an edge: lane q holds ROWS q and q + 4 of the working matrix and of the accumulated rotations, so
 // a one-sided (Hestenes) Jacobi rotation of columns (p, q) is thread-local once the column inner product has been
-// reduced over the 4 lanes.  Rotations are scheduled round-robin (7 rounds of 4 disjoint pairs per sweep).  Per
+// reduced over the 4 lanes.  Rotations follow the odd-even ordering (8 rounds of 4 / 3 neighbouring pairs per sweep).  Per
 // round the 8 inner-product components (re, im of 4 pairs) are reduce-scattered with xor shuffles so that lane q
 // ends up with BOTH components of pair q, derives that pair's rotation alone, and the four parameter sets are
 // broadcast -- no lane repeats another lane's parameter arithmetic.  Column norms are carried along
@@ -24,8 +24,8 @@
 // (A warm start from the previous step's rotations was tried and dropped: A V_prev loses the relative accuracy that
 // one-sided Jacobi keeps on the graded extended messages -- mean Bloch error 1.1e-4 instead of 1.3e-5 -- and the extra
 // product and traffic made the step slower, not faster.)
-// Code size is kept inside the 32 KB instruction cache: ONE round body, executed 7 times per sweep with the columns
-// rotated through the registers, and ONE Jacobi instance looped over the three matrices of an edge.
+// Code size is kept inside the 32 KB instruction cache: TWO round bodies (even and odd pairs), executed 4 times per
+// sweep, and ONE Jacobi instance looped over the three matrices of an edge.
 #include <cuda_runtime.h>
 
 #include "bqa_core.cuh"
@@ -98,25 +98,27 @@ __device__ __forceinline__ Rot rot_params(float al, float be, float gr, float gi
   return r;
 }
 
-// both rows of this lane at once: a_q <- phase a_q, then (a_p, a_q) <- (c a_p - s a_q, s a_p + c a_q); 12 packed ops
-// (the rotation scalars enter as broadcast operands)
+// both rows of this lane at once: a_q <- phase a_q, then (a_p, a_q) <- (s a_p + c a_q, c a_p - s a_q): the rotation
+// AND the exchange of the two columns (odd-even ordering, see jacobi8); 12 packed ops, the rotation scalars enter as
+// broadcast operands
 template <int P, int Q>
 __device__ __forceinline__ void rot_cols(p2 (&X)[8], p2 (&Y)[8], const Rot& r) {
   const p2 qx = x2::fnma2s(r.phy, Y[Q], x2::mul2s(r.phx, X[Q]));
   const p2 qy = x2::fma2s(r.phy, X[Q], x2::mul2s(r.phx, Y[Q]));
   const p2 px = X[P], py = Y[P];
-  X[P] = x2::fnma2s(r.s, qx, x2::mul2s(r.c, px));
-  Y[P] = x2::fnma2s(r.s, qy, x2::mul2s(r.c, py));
-  X[Q] = x2::fma2s(r.c, qx, x2::mul2s(r.s, px));
-  Y[Q] = x2::fma2s(r.c, qy, x2::mul2s(r.s, py));
+  X[Q] = x2::fnma2s(r.s, qx, x2::mul2s(r.c, px));
+  Y[Q] = x2::fnma2s(r.s, qy, x2::mul2s(r.c, py));
+  X[P] = x2::fma2s(r.c, qx, x2::mul2s(r.s, px));
+  Y[P] = x2::fma2s(r.c, qy, x2::mul2s(r.s, py));
 }
 template <int P, int Q>
 __device__ __forceinline__ void apply_rot(p2 (&AX)[8], p2 (&AY)[8], p2 (&VX)[8], p2 (&VY)[8], float (&w)[8],
                                           const Rot& r) {
   rot_cols<P, Q>(AX, AY, r);
   rot_cols<P, Q>(VX, VY, r);
-  w[P] -= r.dw;
-  w[Q] += r.dw;
+  const float al = w[P], be = w[Q];
+  w[Q] = al - r.dw;
+  w[P] = be + r.dw;
 }
 
 // conj(a_p) a_q summed over the two rows of this lane
@@ -124,15 +126,19 @@ __device__ __forceinline__ void apply_rot(p2 (&AX)[8], p2 (&AY)[8], p2 (&VX)[8],
   RE = x2::hsum(x2::fma2(AY[P], AY[Q], x2::mul2(AX[P], AX[Q])));                    \
   IM = x2::hsum(x2::fnma2(AY[P], AX[Q], x2::mul2(AX[P], AY[Q])));
 
-// One round = four disjoint pairs (P0,Q0) .. (P3,Q3), pair k handled by lane k of the edge.
-template <int P0, int Q0, int P1, int Q1, int P2, int Q2, int P3, int Q3>
+// One round = NP (4 or 3) disjoint pairs of neighbouring positions (P0,Q0) .. (P3,Q3), pair k handled by lane k of the edge.
+template <int NP, int P0, int Q0, int P1, int Q1, int P2, int Q2, int P3, int Q3>
 __device__ __forceinline__ void jacobi_round(p2 (&AX)[8], p2 (&AY)[8], p2 (&VX)[8], p2 (&VY)[8],
                                              float (&w)[8], float nul, float tol2, bool frozen, float& mxg2, float& mxs2, int q) {
   float g[8];
   BQA_GAMMA(P0, Q0, g[0], g[1])
   BQA_GAMMA(P1, Q1, g[2], g[3])
   BQA_GAMMA(P2, Q2, g[4], g[5])
-  BQA_GAMMA(P3, Q3, g[6], g[7])
+  if (NP == 4) {
+    BQA_GAMMA(P3, Q3, g[6], g[7])
+  } else {
+    g[6] = 0.f; g[7] = 0.f;
+  }
   const bool b1 = q & 2, b0 = q & 1;
   float h[4];
 #pragma unroll
@@ -142,14 +148,14 @@ __device__ __forceinline__ void jacobi_round(p2 (&AX)[8], p2 (&AY)[8], p2 (&VX)[
   }
   const float gr = (b0 ? h[2] : h[0]) + __shfl_xor_sync(0xffffffffu, b0 ? h[0] : h[2], 1);
   const float gi = (b0 ? h[3] : h[1]) + __shfl_xor_sync(0xffffffffu, b0 ? h[1] : h[3], 1);
-  // lane q now holds the inner product of pair q; its column norms:
-  const float al = b1 ? (b0 ? w[P3] : w[P2]) : (b0 ? w[P1] : w[P0]);
-  const float be = b1 ? (b0 ? w[Q3] : w[Q2]) : (b0 ? w[Q1] : w[Q0]);
+  // lane q now holds the inner product of pair q; its column norms (lane 3 of a 3-pair round: zero norms = no rotation)
+  const float al = b1 ? (b0 ? (NP == 4 ? w[P3] : 0.f) : w[P2]) : (b0 ? w[P1] : w[P0]);
+  const float be = b1 ? (b0 ? (NP == 4 ? w[Q3] : 0.f) : w[Q2]) : (b0 ? w[Q1] : w[Q0]);
   const Rot mine = rot_params(al, be, gr, gi, nul, tol2, frozen, mxg2, mxs2);
   const int base = (threadIdx.x & 31) & ~3;
   Rot R[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < NP; ++k) {
     R[k].c = __shfl_sync(0xffffffffu, mine.c, base + k);
     R[k].s = __shfl_sync(0xffffffffu, mine.s, base + k);
     R[k].phx = __shfl_sync(0xffffffffu, mine.phx, base + k);
@@ -159,13 +165,16 @@ __device__ __forceinline__ void jacobi_round(p2 (&AX)[8], p2 (&AY)[8], p2 (&VX)[
   apply_rot<P0, Q0>(AX, AY, VX, VY, w, R[0]);
   apply_rot<P1, Q1>(AX, AY, VX, VY, w, R[1]);
   apply_rot<P2, Q2>(AX, AY, VX, VY, w, R[2]);
-  apply_rot<P3, Q3>(AX, AY, VX, VY, w, R[3]);
+  if (NP == 4) apply_rot<P3, Q3>(AX, AY, VX, VY, w, R[3]);
 }
 
 // one-sided Jacobi SVD on the packed rows: on exit A = U diag(sigma) (rows q, q + 4 of this lane), V = right singular
-// vectors (same rows), w = sigma^2 per column (all lanes).  A sweep is ONE round body executed 7 times, with the
-// columns 1..7 rotated through the registers between rounds (circle method: pairs (0,7) (1,6) (2,5) (3,4) by
-// position); after 7 rounds every pair has met once and the columns are back in place.
+// vectors (same rows), w = sigma^2 per column (all lanes).  Odd-even (transposition) ordering: a sweep is 4 x [pairs
+// (0,1) (2,3) (4,5) (6,7) | pairs (1,2) (3,4) (5,6)] by POSITION, and every rotation also exchanges its two columns
+// (for free: the two results are written to each other's registers).  After the 8 rounds every pair of columns has met
+// exactly once and the column order is reversed -- no register shuffling between rounds (the round-robin ordering used
+// before spent 22 % of a round's instructions moving columns) and two round bodies of code.  An odd number of sweeps
+// is undone by one reversal at the end, so the column order on exit does not depend on the sweep count.
 __device__ __forceinline__ void jacobi8(p2 (&AX)[8], p2 (&AY)[8], p2 (&VX)[8], p2 (&VY)[8],
                                         float (&w)[8], int q, int& sweeps) {
 #pragma unroll
@@ -180,20 +189,17 @@ __device__ __forceinline__ void jacobi8(p2 (&AX)[8], p2 (&AY)[8], p2 (&VX)[8], p
   const float fro2 = ((w[0] + w[1]) + (w[2] + w[3])) + ((w[4] + w[5]) + (w[6] + w[7]));
   const float nul = eps * eps * fro2;                       // columns below eps |A|_F are numerically zero
   bool frozen = false;
+  int done = 0;
 #pragma unroll 1
   for (int sweep = 0; sweep < 30; ++sweep) {
     float mxg2 = 0.f, mxs2 = 0.f;
 #pragma unroll 1
-    for (int round = 0; round < 7; ++round) {
-      jacobi_round<0, 7, 1, 6, 2, 5, 3, 4>(AX, AY, VX, VY, w, nul, tol2, frozen, mxg2, mxs2, q);
-      const p2 a7 = AX[7], b7 = AY[7], v7 = VX[7], u7 = VY[7];
-      const float w7 = w[7];
-#pragma unroll
-      for (int j = 7; j > 1; --j) { AX[j] = AX[j - 1]; AY[j] = AY[j - 1]; VX[j] = VX[j - 1]; VY[j] = VY[j - 1]; w[j] = w[j - 1]; }
-      AX[1] = a7; AY[1] = b7; VX[1] = v7; VY[1] = u7; w[1] = w7;
+    for (int rr = 0; rr < 4; ++rr) {
+      jacobi_round<4, 0, 1, 2, 3, 4, 5, 6, 7>(AX, AY, VX, VY, w, nul, tol2, frozen, mxg2, mxs2, q);
+      jacobi_round<3, 1, 2, 3, 4, 5, 6, 0, 0>(AX, AY, VX, VY, w, nul, tol2, frozen, mxg2, mxs2, q);
     }
     col_norms(AX, AY, w);                                   // exact norms once per sweep
-    ++sweeps;
+    ++done;
     // per edge (4 lanes): done when nothing rotated, or when the next sweep's rotations would be below the tolerance
     mxg2 = fmaxf(mxg2, __shfl_xor_sync(0xffffffffu, mxg2, 1));
     mxs2 = fmaxf(mxs2, __shfl_xor_sync(0xffffffffu, mxs2, 1));
@@ -201,6 +207,16 @@ __device__ __forceinline__ void jacobi8(p2 (&AX)[8], p2 (&AY)[8], p2 (&VX)[8], p
     mxs2 = fmaxf(mxs2, __shfl_xor_sync(0xffffffffu, mxs2, 2));
     frozen = frozen || 64.f * mxg2 * mxs2 < tol2;
     if (!__any_sync(0xffffffffu, !frozen)) break;
+  }
+  sweeps += done;
+  if (done & 1) {                                           // warp-uniform: restore the original column order
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const p2 ax = AX[j], ay = AY[j], vx = VX[j], vy = VY[j];
+      const float wj = w[j];
+      AX[j] = AX[7 - j]; AY[j] = AY[7 - j]; VX[j] = VX[7 - j]; VY[j] = VY[7 - j]; w[j] = w[7 - j];
+      AX[7 - j] = ax; AY[7 - j] = ay; VX[7 - j] = vx; VY[7 - j] = vy; w[7 - j] = wj;
+    }
   }
 }
 

@@ -81,6 +81,7 @@ __device__ __forceinline__ float allreduce8(float v) {
   v += __shfl_xor_sync(0xffffffffu, v, 4);
   return v;
 }
+__device__ __forceinline__ float abs2_rn(float x, float y) { return fmaf(x, x, __fmul_rn(y, y)); }
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async16_s(unsigned dst, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(gmem) : "memory");
@@ -145,7 +146,10 @@ __device__ __forceinline__ void sweep(const Args& a, const float2* msgs_cur, flo
   const int groups = (B + 3) >> 2, tail0 = B - 4;
   const int nwarps = (int)gridDim.x * kWarps;
   int g = (int)blockIdx.x * kWarps + wib;
-  constexpr bool multi = MULTI;                             // boundary messages are also stored into the peers' halo slots
+  // boundary messages are also stored into the peers' halo slots.  Compile-time in the BP kernels; the extended-message
+  // kernel has ONE instantiation that tests the pointer (two instantiations contracted its epilogue arithmetic into FMAs
+  // differently, and single- and multi-GPU runs must stay bit-identical)
+  const bool multi = EXT ? a.remote_pos != nullptr : MULTI;
   float mnum = 0.f, mden = 0.f;
 
   Pipe q;
@@ -411,20 +415,18 @@ __device__ __forceinline__ void sweep(const Args& a, const float2* msgs_cur, flo
       }
       if (!EXT) {
         const float d = rcp_approx(tr[k]);
-        const float2 na = make_float2(sa.x * d, sa.y * d), nb = make_float2(sb.x * d, sb.y * d);
+        const float2 na = make_float2(__fmul_rn(sa.x, d), __fmul_rn(sa.y, d)), nb = make_float2(__fmul_rn(sb.x, d), __fmul_rn(sb.y, d));
         const float4 ov = *reinterpret_cast<const float4*>(st + kTBytes + kMBytes + (k * 4 + s) * kMsg + t * 16);
-        float da = (na.x - ov.x) * (na.x - ov.x) + (na.y - ov.y) * (na.y - ov.y);
-        float db = (nb.x - ov.z) * (nb.x - ov.z) + (nb.y - ov.w) * (nb.y - ov.w);
-        mnum = fmaxf(mnum, fmaxf(da, db));
-        da = (na.x + ov.x) * (na.x + ov.x) + (na.y + ov.y) * (na.y + ov.y);
-        db = (nb.x + ov.z) * (nb.x + ov.z) + (nb.y + ov.w) * (nb.y + ov.w);
-        mden = fmaxf(mden, fmaxf(da, db));
+        // (explicit fused / unfused operations: the result must not depend on how an instantiation was contracted)
+        mnum = fmaxf(mnum, fmaxf(abs2_rn(na.x - ov.x, na.y - ov.y), abs2_rn(nb.x - ov.z, nb.y - ov.w)));
+        mden = fmaxf(mden, fmaxf(abs2_rn(na.x + ov.x, na.y + ov.y), abs2_rn(nb.x + ov.z, nb.y + ov.w)));
         float4 w;
         if (write_undamped) {
           w = make_float4(na.x, na.y, nb.x, nb.y);
         } else {
           const float al = a.damping, be = 1.f - a.damping;
-          w = make_float4(al * ov.x + be * na.x, al * ov.y + be * na.y, al * ov.z + be * nb.x, al * ov.w + be * nb.y);
+          w = make_float4(fmaf(al, ov.x, __fmul_rn(be, na.x)), fmaf(al, ov.y, __fmul_rn(be, na.y)),
+                          fmaf(al, ov.z, __fmul_rn(be, nb.x)), fmaf(al, ov.w, __fmul_rn(be, nb.y)));
         }
         *reinterpret_cast<float4*>(out_base + (size_t)slot * 128) = w;
         if (far) *reinterpret_cast<float4*>(far) = w;      // halo slot on the peer that owns the receiver
@@ -638,9 +640,8 @@ int launch_fast_msgs_d3D4(bool ext, long long B, const void* T, const void* msgs
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !configured[dev]) {
     cudaError_t e1 = cudaFuncSetAttribute(k_msgs_d3D4<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    cudaError_t e2 = cudaFuncSetAttribute(k_msgs_d3D4<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaError_t e2 = cudaFuncSetAttribute(k_msgs_d3D4<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_msgs_d3D4<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_msgs_d3D4<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e1 != cudaSuccess || e2 != cudaSuccess)
       return set_error("cudaFuncSetAttribute(k_msgs_d3D4): %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
     if (dev >= 0 && dev < 64) configured[dev] = true;
@@ -656,8 +657,7 @@ int launch_fast_msgs_d3D4(bool ext, long long B, const void* T, const void* msgs
   long long grid = (groups + kWarps - 1) / kWarps;
   if (grid > sm_count()) grid = sm_count();
   const bool multi = a.remote_pos != nullptr;
-  if (ext && multi) k_msgs_d3D4<true, true><<<(int)grid, kThreads, kSmem, st>>>(a);
-  else if (ext) k_msgs_d3D4<true, false><<<(int)grid, kThreads, kSmem, st>>>(a);
+  if (ext) k_msgs_d3D4<true, true><<<(int)grid, kThreads, kSmem, st>>>(a);      // one instantiation: see sweep()
   else if (multi) k_msgs_d3D4<false, true><<<(int)grid, kThreads, kSmem, st>>>(a);
   else k_msgs_d3D4<false, false><<<(int)grid, kThreads, kSmem, st>>>(a);
   return after_launch(ext ? "ext_msgs(d3D4)" : "bp_sweep(d3D4)");

@@ -79,6 +79,19 @@ __device__ __forceinline__ void cmac(CAcc& acc, p2 s, p2 v) {
     acc.B = x2::fma2s(f.y, v, acc.B);
   }
 }
+// the same with a REAL scalar s (the diagonal of a Hermitian message): only the first accumulator moves.  B_FIRST marks
+// the first term that touches B when the chain started with a real scalar.
+template <bool FIRST>
+__device__ __forceinline__ void cmac_real(CAcc& acc, p2 s, p2 v) {
+  const float2 f = x2::unpk(s);
+  acc.A = FIRST ? x2::mul2s(f.x, v) : x2::fma2s(f.x, v, acc.A);
+}
+template <bool B_FIRST>
+__device__ __forceinline__ void cmac_bfirst(CAcc& acc, p2 s, p2 v) {
+  const float2 f = x2::unpk(s);
+  acc.A = x2::fma2s(f.x, v, acc.A);
+  acc.B = B_FIRST ? x2::mul2s(f.y, v) : x2::fma2s(f.y, v, acc.B);
+}
 // (one FFMA2 each: the second accumulator enters half-swapped and multiplied by (-1, 1) or (1, -1); x * (+-1) is exact,
 // so the results equal the separately rounded additions)
 __device__ __forceinline__ p2 cfinish(const CAcc& acc) {          // sum s v = (A.x - B.y, A.y + B.x)

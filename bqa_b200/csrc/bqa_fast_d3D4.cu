@@ -145,7 +145,9 @@ __device__ __forceinline__ void sweep(const Args& a, const float2* msgs_cur, flo
   const int B = (int)a.B;
   const int groups = (B + 3) >> 2, tail0 = B - 4;
   const int nwarps = (int)gridDim.x * kWarps;
-  int g = (int)blockIdx.x * kWarps + wib;
+  // warp-major numbering: the groups of the last, partial round land on one warp each of as many CTAs as possible
+  // (a lone warp runs much faster than eight sharing the SM) instead of filling all warps of a few CTAs
+  int g = wib * (int)gridDim.x + (int)blockIdx.x;
   // boundary messages are also stored into the peers' halo slots.  Compile-time in the BP kernels; the extended-message
   // kernel has ONE instantiation that tests the pointer (two instantiations contracted its epilogue arithmetic into FMAs
   // differently, and single- and multi-GPU runs must stay bit-identical)
@@ -227,16 +229,20 @@ __device__ __forceinline__ void sweep(const Args& a, const float2* msgs_cur, flo
     {
       p2 tt[16], m[16];
       lds_tile(tt, Ts + la * kSlice);
-      // U2[b][c'] = sum_c m2[c'][c] T[b][c]
+      // U2[b][c'] = sum_c m2[c'][c] T[b][c]   (the diagonal of a Hermitian message is real: half a multiply-add there)
       lds_tile(m, Min + (2 * 4 + s) * kMsg);
 #pragma unroll
       for (int b = 0; b < 4; ++b)
 #pragma unroll
         for (int c2 = 0; c2 < 4; ++c2) {
           CAcc acc;
-          cmac<true>(acc, m[c2 * 4], tt[b * 4]);
+          if (c2 == 0) cmac_real<true>(acc, m[0], tt[b * 4]); else cmac<true>(acc, m[c2 * 4], tt[b * 4]);
 #pragma unroll
-          for (int c = 1; c < 4; ++c) cmac<false>(acc, m[c2 * 4 + c], tt[b * 4 + c]);
+          for (int c = 1; c < 4; ++c) {
+            if (c == c2) cmac_real<false>(acc, m[c2 * 4 + c], tt[b * 4 + c]);
+            else if (c2 == 0 && c == 1) cmac_bfirst<true>(acc, m[c2 * 4 + c], tt[b * 4 + c]);
+            else cmac<false>(acc, m[c2 * 4 + c], tt[b * 4 + c]);
+          }
           U2[b * 4 + c2] = cfinish(acc);
         }
       // U1[b'][c] = sum_b m1[b'][b] T[b][c]
@@ -246,21 +252,22 @@ __device__ __forceinline__ void sweep(const Args& a, const float2* msgs_cur, flo
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           CAcc acc;
-          cmac<true>(acc, m[b2 * 4], tt[c]);
+          if (b2 == 0) cmac_real<true>(acc, m[0], tt[c]); else cmac<true>(acc, m[b2 * 4], tt[c]);
 #pragma unroll
-          for (int b = 1; b < 4; ++b) cmac<false>(acc, m[b2 * 4 + b], tt[b * 4 + c]);
+          for (int b = 1; b < 4; ++b) {
+            if (b == b2) cmac_real<false>(acc, m[b2 * 4 + b], tt[b * 4 + c]);
+            else if (b2 == 0 && b == 1) cmac_bfirst<true>(acc, m[b2 * 4 + b], tt[b * 4 + c]);
+            else cmac<false>(acc, m[b2 * 4 + b], tt[b * 4 + c]);
+          }
           U1[b2 * 4 + c] = cfinish(acc);
         }
       // U0[a][b][c] = sum_a' m0[a][a'] T[a'][b][c], row a = `la` of m0.  The matrix element is the prepared pair operand
-      // (m, i m), the tensor elements enter as broadcast scalars.  Term a' = la: this lane's own slice, still in registers
+      // (m, i m), the tensor elements enter as broadcast scalars.  Term a' = la: this lane's own slice, still in
+      // registers, times the real diagonal element
       {
-        const p2 mm = *reinterpret_cast<const p2*>(m0row + la * 8);
-        const p2 im = x2::mul2(x2::swap(mm), rot);
+        const float mr = *reinterpret_cast<const float*>(m0row + la * 8);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float2 tf = x2::unpk(tt[i]);
-          U0[i] = x2::fma2s(tf.y, im, x2::mul2s(tf.x, mm));
-        }
+        for (int i = 0; i < 16; ++i) U0[i] = x2::mul2s(mr, tt[i]);
       }
     }
     // the three other slices from shared memory: the 8 lanes of a node read 8 distinct slices (conflict-free)
@@ -365,13 +372,10 @@ __device__ __forceinline__ void sweep(const Args& a, const float2* msgs_cur, flo
     {
       unsigned char* o0 = scratch + kOut0 + s * 64;         // [x][node][p][y]: a warp-wide store is 256 contiguous bytes
       {                                                     // x = la: this lane's own U1 slice is still in registers
-        CAcc v0, v1;
-        cmac<true>(v0, U1[0], U2[0]);
-        cmac<true>(v1, U1[1], U2[1]);
+        p2 d0 = x2::mul2(U1[0], U2[0]), d1 = x2::mul2(U1[1], U2[1]);     // real part only: element-wise pair products
 #pragma unroll
-        for (int i = 2; i < 16; i += 2) { cmac<false>(v0, U1[i], U2[i]); cmac<false>(v1, U1[i + 1], U2[i + 1]); }
-        const float2 r0 = cfinish_conj(v0), r1 = cfinish_conj(v1);
-        const float dg = r0.x + r1.x;
+        for (int i = 2; i < 16; i += 2) { d0 = x2::fma2(U1[i], U2[i], d0); d1 = x2::fma2(U1[i + 1], U2[i + 1], d1); }
+        const float dg = x2::hsum(d0) + x2::hsum(d1);
         tr[0] = allreduce8(dg);
         *reinterpret_cast<float2*>(o0 + la * kOut0Row + p * 32 + la * 8) = make_float2(dg, 0.f);
       }

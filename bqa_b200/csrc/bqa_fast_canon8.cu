@@ -64,8 +64,11 @@ __device__ __forceinline__ void col_norms(const p2 (&X)[8], const p2 (&Y)[8], fl
 }
 
 // rsqrt with one Newton step (MUFU.RSQ is good to ~2 ulp; rotations must stay orthonormal to rounding)
+// (MUFU.RSQ directly: `rsqrtf` wraps it in a denormal-input path of ~8 instructions; the one caller whose argument
+// can be denormal pre-scales it by an even power of two, which leaves every mantissa bit unchanged)
 __device__ __forceinline__ float rsqrt_nr(float x) {
-  const float y = rsqrtf(x);
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y * (1.5f - 0.5f * x * y * y);
 }
 
@@ -81,7 +84,7 @@ __device__ __forceinline__ Rot rot_params(float al, float be, float gr, float gi
   const float g2 = gr * gr + gi * gi;
   const float ab = al * be;
   const bool act = !frozen && !(al <= nul || be <= nul || g2 <= tol2 * ab);
-  const float ig = rsqrt_nr(g2);                  // 1 / |g|   (inf / nan when inactive: discarded below)
+  const float ig = rsqrt_nr(g2 * 0x1p60f) * 0x1p30f;   // 1 / |g|   (inf / nan when inactive: discarded below)
   const float ag = g2 * ig;
   const float zeta = 0.5f * (be - al) * ig;
   const float z2 = 1.f + zeta * zeta;
@@ -193,7 +196,7 @@ __device__ __forceinline__ void jacobi8(p2 (&AX)[8], p2 (&AY)[8], p2 (&VX)[8], p
 #pragma unroll 1
   for (int sweep = 0; sweep < 30; ++sweep) {
     float mxg2 = 0.f, mxs2 = 0.f;
-#pragma unroll 1
+#pragma unroll 2                                            // (the back edge costs ~22 register-pair moves: amortised over 4 rounds)
     for (int rr = 0; rr < 4; ++rr) {
       jacobi_round<4, 0, 1, 2, 3, 4, 5, 6, 7>(AX, AY, VX, VY, w, nul, tol2, frozen, mxg2, mxs2, q);
       jacobi_round<3, 1, 2, 3, 4, 5, 6, 0, 0>(AX, AY, VX, VY, w, nul, tol2, frozen, mxg2, mxs2, q);

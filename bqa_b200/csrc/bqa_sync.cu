@@ -34,9 +34,56 @@ __global__ void __launch_bounds__(256) k_gauge_msgs(int stride, int Dn, long lon
   }
 }
 
+// Dn = 4, complex64 (the headline shape): one thread per message ROW -- the 4 lambdas of the row's edge in one 16-byte load,
+// the row (4 complex) in two 16-byte stores, shifts instead of the 64-bit divisions of the generic index arithmetic.
+// `pos_of(q)` = (slot, lambda row) of message q.  Same arithmetic as emit_gauge_msg (bqa_core.cuh).
+template <class PosOf>
+__global__ void __launch_bounds__(256) k_gauge_rows4(int stride, long long n, PosOf pos_of, const float* __restrict__ lmbds,
+                                                     float4* __restrict__ msgs) {
+  const long long total = n * 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long q = i >> 2;
+    const int r = (int)(i & 3);
+    long long slot, row;
+    pos_of(q, slot, row);
+    const float4 lam = __ldg(reinterpret_cast<const float4*>(lmbds + (size_t)row * stride));
+    float tr = 0.f;
+    tr += lam.x; tr += lam.y; tr += lam.z; tr += lam.w;
+    const float inv = 1.f / tr;
+    const float v = (r == 0 ? lam.x : r == 1 ? lam.y : r == 2 ? lam.z : lam.w) * inv;
+    float4* dst = msgs + (size_t)slot * 8 + r * 2;          // a message is 8 float4, a row 2
+    dst[0] = make_float4(r == 0 ? v : 0.f, 0.f, r == 1 ? v : 0.f, 0.f);
+    dst[1] = make_float4(r == 2 ? v : 0.f, 0.f, r == 3 ? v : 0.f, 0.f);
+  }
+}
+struct PosFromArrays {
+  const int32_t* out_pos;
+  const int32_t* lmbd_pos;
+  __device__ __forceinline__ void operator()(long long q, long long& slot, long long& row) const {
+    slot = __ldg(out_pos + q);
+    row = __ldg(lmbd_pos + q);
+  }
+};
+struct PosAllSlots {
+  long long L;
+  __device__ __forceinline__ void operator()(long long q, long long& slot, long long& row) const {
+    slot = q;
+    row = q >= L ? q - L : q;
+  }
+};
+static bool rows4_ok(int D_old, int Dn, const void* lmbds, const void* msgs) {
+  return Dn == 4 && (2 * D_old) % 4 == 0 && ((uintptr_t)lmbds & 15) == 0 && ((uintptr_t)msgs & 15) == 0;
+}
+
 template <typename R>
 int launch_gauge_msgs(int D_old, int Dn, long long L, const void* lmbds, void* msgs_out, cudaStream_t st) {
   if (L == 0) return 0;
+  if (sizeof(R) == 4 && rows4_ok(D_old, Dn, lmbds, msgs_out)) {
+    long long blocks = (2 * L * 4 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_gauge_rows4<<<(int)blocks, 256, 0, st>>>(2 * D_old, 2 * L, PosAllSlots{L}, (const float*)lmbds, (float4*)msgs_out);
+    return after_launch("gauge_msgs(rows4)");
+  }
   const long long total = 2 * L * Dn * Dn;
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
@@ -69,6 +116,13 @@ template <typename R>
 int launch_gauge_slots(int D_old, int Dn, long long n, const int32_t* out_pos, const int32_t* lmbd_pos, const void* lmbds,
                        void* msgs_out, cudaStream_t st) {
   if (n == 0) return 0;
+  if (sizeof(R) == 4 && rows4_ok(D_old, Dn, lmbds, msgs_out)) {
+    long long blocks = (n * 4 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_gauge_rows4<<<(int)blocks, 256, 0, st>>>(2 * D_old, n, PosFromArrays{out_pos, lmbd_pos}, (const float*)lmbds,
+                                               (float4*)msgs_out);
+    return after_launch("gauge_slots(rows4)");
+  }
   long long blocks = (n * Dn * Dn + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   k_gauge_slots<R><<<(int)blocks, 256, 0, st>>>(2 * D_old, Dn, n, out_pos, lmbd_pos, (const R*)lmbds, (cx<R>*)msgs_out);

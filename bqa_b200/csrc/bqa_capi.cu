@@ -161,7 +161,7 @@ int bqa_b200_apply_update(int prec, int degree, int D, int D_new, long long B, c
   if (int rc = check_shape(prec, degree, D)) return rc;
   if (D_new < 1 || D_new > 2 * D || D_new > BQA_MAX_D) return set_error("new bond dimension %d invalid for D = %d", D_new, D);
   cudaStream_t st = (cudaStream_t)stream;
-  if (g_kernel_mode.load() == 0 && fast_apply_available(prec, degree, D, D_new)) {
+  if (g_kernel_mode.load() == 0 && fast_apply_available(prec, degree, D, D_new, B)) {
     // the specialised kernel leaves the re-initialised messages to bqa_b200_gauge_msgs: write this class's slots here
     // so that the entry point keeps its contract (msgs_out[out_pos] = diag(lambda) / trace)
     if (int rc = launch_fast_apply_d3D4(B, T_in, T_out, canon, lmbds, in_pos, lmbd_pos, node_ampls, edge_ampls, ztime,

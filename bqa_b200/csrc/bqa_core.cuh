@@ -168,8 +168,14 @@ BQA_HDN void node_gram(G g, int d, int D, const cx<R>* T, const cx<R>* const* ms
 // complex principal square roots of cos(theta), sin(theta) and the ZZ half-gate factors
 //   f0 = sqrt(cos th), f1 = e^{-i pi/4} sqrt(sin th)           (reference backends.py:20-22, 519-526)
 template <typename R>
+BQA_HD void zz_factors_cs(R c, R s, cx<R>& f0, cx<R>& f1);
+template <typename R>
 BQA_HD void zz_factors(R theta, cx<R>& f0, cx<R>& f1) {
-  const R c = mcos(theta), s = msin(theta);
+  zz_factors_cs<R>(mcos(theta), msin(theta), f0, f1);
+}
+// the same from c = cos(theta), s = sin(theta)
+template <typename R>
+BQA_HD void zz_factors_cs(R c, R s, cx<R>& f0, cx<R>& f1) {
   f0 = (c >= R(0)) ? mk<R>(msqrt(c), R(0)) : mk<R>(R(0), msqrt(-c));
   const cx<R> rs = (s >= R(0)) ? mk<R>(msqrt(s), R(0)) : mk<R>(R(0), msqrt(-s));
   const R h = R(0.70710678118654752440);

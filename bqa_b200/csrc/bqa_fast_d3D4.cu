@@ -217,10 +217,12 @@ __device__ __forceinline__ void sweep(const Args& a, const float2* msgs_cur, flo
     cp_async_wait<1>();
     __syncwarp();
 
-    float th[3] = {0.f, 0.f, 0.f};
-    if (EXT) {                                              // coupling angles of this node's 3 legs, fetched early
-#pragma unroll
-      for (int k = 0; k < 3; ++k) th[k] = __ldg(a.edge_ampls + (size_t)k * B + n0 + s) * a.ztime;
+    // ZZ half-gate factors (extended messages): lane t of a node evaluates leg min(t % 4, 2) -- one sincos per lane and
+    // group; the epilogue fetches leg k's factors from lane k of the node
+    cx<float> zf0 = mk<float>(0.f, 0.f), zf1 = zf0;
+    if (EXT) {
+      const int sel = (t & 3) < 2 ? (t & 3) : 2;
+      zz_factors<float>(__ldg(a.edge_ampls + (size_t)sel * B + n0 + s) * a.ztime, zf0, zf1);
     }
     const unsigned char* Ts = st + (s * 8 + p * 4) * kSlice;          // the four a-slices of (node, p)
     const unsigned char* Min = st + kTBytes;
@@ -436,10 +438,9 @@ __device__ __forceinline__ void sweep(const Args& a, const float2* msgs_cur, flo
         if (far) *reinterpret_cast<float4*>(far) = w;      // halo slot on the peer that owns the receiver
       } else {
         // ext[(s1,x),(s2,y)] = conj(f_s1) f_s2 (g0 + (-1)^(s1+s2) g1)[x][y] / ((|f0|^2 + |f1|^2) trace)
-        cx<float> f0, f1;
-        zz_factors<float>(th[k], f0, f1);
-        const float2 ff[2] = {make_float2(f0.re, f0.im), make_float2(f1.re, f1.im)};
-        const float w = (f0.re * f0.re + f0.im * f0.im + f1.re * f1.re + f1.im * f1.im);
+        const float2 ff[2] = {make_float2(__shfl_sync(0xffffffffu, zf0.re, k, 8), __shfl_sync(0xffffffffu, zf0.im, k, 8)),
+                              make_float2(__shfl_sync(0xffffffffu, zf1.re, k, 8), __shfl_sync(0xffffffffu, zf1.im, k, 8))};
+        const float w = (ff[0].x * ff[0].x + ff[0].y * ff[0].y + ff[1].x * ff[1].x + ff[1].y * ff[1].y);
         const float2 itr = make_float2(1.f / (w * tr[k]), 0.f);
         const float2 da = make_float2(e[k][0].x - e[k][2].x, e[k][0].y - e[k][2].y);
         const float2 db = make_float2(e[k][1].x - e[k][3].x, e[k][1].y - e[k][3].y);

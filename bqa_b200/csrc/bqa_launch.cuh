@@ -69,7 +69,7 @@ template <typename R>
 int launch_gauge_slots(int D_old, int Dn, long long n, const int32_t* out_pos, const int32_t* lmbd_pos, const void* lmbds,
                        void* msgs_out, cudaStream_t st);
 // specialised simple-update application (bqa_fast_apply.cu): degree 3, D = 4 -> 4, complex64
-bool fast_apply_available(int prec, int degree, int D, int Dn);
+bool fast_apply_available(int prec, int degree, int D, int Dn, long long B);
 int launch_fast_apply_d3D4(long long B, const void* T_in, void* T_out, const void* canon, const void* lmbds,
                            const int32_t* in_pos, const int32_t* lmbd_pos, const void* node_ampls,
                            const void* edge_ampls, double ztime, double xtime, cudaStream_t st);

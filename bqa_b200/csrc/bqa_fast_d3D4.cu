@@ -557,21 +557,27 @@ __global__ void __launch_bounds__(kThreads, 1) k_bp_run_d3D4(const __grid_consta
     sweep<false, MULTI>(a, r.msgs[cur], r.msgs[cur ^ 1], it, it == r.max_iters - 1, PeersOfRun{r, cur ^ 1}, smem);
     if (!grid_barrier(counter, generation, a.status)) return;
     if (MULTI && r.world > 1) {
-      if (blockIdx.x == 0 && threadIdx.x < r.world && (int)threadIdx.x != r.rank) {
+      // every local CTA has finished its stores (barrier above).  CTA 0 pushes the residual maxima to the peers and
+      // releases this rank's flag in their memory; EVERY CTA then waits for the peers' flags in local memory (no second
+      // grid barrier: the acquire of a peer's flag orders that peer's halo stores and maxima before this CTA's next sweep)
+      const unsigned seq = r.seq_base + it + 1;
+      if (threadIdx.x < r.world && (int)threadIdx.x != r.rank) {
         const int q = threadIdx.x;
-        const unsigned* mine = reinterpret_cast<const unsigned*>(a.resid) + 2 * it;
-        unsigned* theirs = reinterpret_cast<unsigned*>(r.peer_resid[q]) + 2 * it;
-        atomicMax_system(theirs, ld_acquire_gpu_u32(mine));
-        atomicMax_system(theirs + 1, ld_acquire_gpu_u32(mine + 1));
-        __threadfence_system();
-        const unsigned seq = r.seq_base + it + 1;
-        st_release_sys_u32(r.peer_flags[q] + r.rank, seq);
+        if (blockIdx.x == 0) {
+          const unsigned* mine = reinterpret_cast<const unsigned*>(a.resid) + 2 * it;
+          unsigned* theirs = reinterpret_cast<unsigned*>(r.peer_resid[q]) + 2 * it;
+          atomicMax_system(theirs, ld_acquire_gpu_u32(mine));
+          atomicMax_system(theirs + 1, ld_acquire_gpu_u32(mine + 1));
+          __threadfence_system();
+          st_release_sys_u32(r.peer_flags[q] + r.rank, seq);
+        }
         const long long t0 = clock64();
         while ((int)(ld_acquire_sys_u32(r.peer_flags[r.rank] + q) - seq) < 0) {
-          if (clock64() - t0 > 20000000000LL) { a.status[3] = 1; break; }
+          if (*((volatile int32_t*)a.status + 3) != 0 || clock64() - t0 > 20000000000LL) { a.status[3] = 1; break; }
         }
       }
-      if (!grid_barrier(counter, generation, a.status)) return;
+      __syncthreads();
+      if (*((volatile int32_t*)a.status + 3) != 0) return;
     }
     const float num = __ldcg(a.resid + 2 * it), den = __ldcg(a.resid + 2 * it + 1);
     if (sqrtf(num / den) < a.bp_eps) { sweeps = it + 1; converged = 1; break; }

@@ -60,7 +60,12 @@ size_t bqa_b200_workspace_bytes(int prec, int degree, int D, int D_new);
  * max |new - old|^2 and max |new + old|^2 into resid[it] with atomic max.  Device-side early exit:
  * sweep it > 0 first tests resid[it-1] (sqrt(num/den) < bp_eps) and, if converged, sets
  * status[0] = 1, status[1] = it and returns without touching the messages -- so the host can enqueue
- * sweeps ahead without a sync per sweep.  resid and status must be zeroed before sweep 0. */
+ * sweeps ahead without a sync per sweep.  resid and status must be zeroed before sweep 0.
+ *
+ * Messages are Hermitian (BP messages are Hermitian positive semi-definite by construction: state.py:56-57 starts
+ * them as diag(lambda) / trace and pass_msgs keeps the property).  The specialised complex64 kernels for degree 3,
+ * D = 4 rely on it (3 mode products instead of 6, real diagonals) and write exactly Hermitian outputs; the generic
+ * kernels evaluate the reference formula for any input. */
 int bqa_b200_bp_sweep(int prec, int degree, int D, long long B, const void* T, const void* msgs_cur,
                       void* msgs_nxt, const int32_t* in_pos, const int32_t* out_pos, double damping,
                       int write_undamped, double bp_eps, int it, void* resid, int32_t* status,

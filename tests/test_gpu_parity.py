@@ -169,7 +169,7 @@ def test_full_size_properties_100k(lib):
     assert np.abs(eng2.bloch_vectors() - eng.bloch_vectors()).max() == 0.0
 
 
-@pytest.mark.parametrize("B", [1, 4, 1003, 40_001])
+@pytest.mark.parametrize("B", [1, 3, 4, 5, 7, 1003, 40_001])     # < 4: generic fallback; not a multiple of 4: overlapping last group
 def test_fast_d3D4_kernels_match_generic_and_oracle(lib, B):
     """Specialised degree-3 / D=4 / complex64 kernels (bqa_fast_d3D4.cu) against the generic kernels and
     against the oracle's pass_msgs (reference backends.py:406-408) on scattered message slots, a ragged
@@ -299,7 +299,7 @@ def test_partitioned_nccl(lib):
     assert r.returncode == 0 and "multigpu_check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
-@pytest.mark.parametrize("B", [1, 6, 2003])
+@pytest.mark.parametrize("B", [1, 3, 5, 6, 2003])
 def test_fast_apply_update_matches_generic(lib, B):
     """Specialised degree-3 / D = 4 -> 4 / complex64 simple-update application (bqa_fast_apply.cu) against the
     generic kernel (itself checked against the oracle end to end) on random canonicalizers, lambdas and scattered

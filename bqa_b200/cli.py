@@ -1,13 +1,14 @@
 """Command line front end: the JSON wire format of ``bqa_cli`` (reference src/bqa/cli.py:17-176) on the B200 engine.
 
     python -m bqa_b200.cli [-i config.json] [-o result.json] [-l LOG_LEVEL] [--precision single|double] [--device cuda:0]
+                           [--checkpoint state.npz --checkpoint-every N [--resume]]
 
 Same contract as the reference tool: the config is read from ``-i`` (a ``*.json`` path relative to the current working
 directory) or from stdin, ``run_qa`` is called on it, and the result list
 ``[["bloch_vectors", [[x, y, z], ...]] | ["measurement_outcomes", [+1 | -1, ...]], ...]`` is written as JSON to ``-o``
 or to stdout; ``-l`` takes DEBUG / INFO / WARNING / ERROR (default INFO).  Any failure prints the chain of error
 messages to stderr and exits with status 1 (reference cli.py:158-176); an unknown argument prints a hint and exits with
-status 1 (:36-37, :88-90).  ``--precision`` / ``--device`` are additions of this engine (the reference selects the
+status 1 (:36-37, :88-90).  ``--precision`` / ``--device`` / ``--checkpoint*`` / ``--resume`` are additions of this engine (the reference selects the
 precision with the BQA_PRECISION environment variable, utils.py:9-20, which is honoured here too)."""
 from __future__ import annotations
 
@@ -36,6 +37,9 @@ def usage() -> str:
         f"  -l | --log-level LEVEL       one of {', '.join(LOG_LEVELS)} (default {DEFAULT_LOG_LEVEL})\n"
         f"       --precision PRECISION   one of {', '.join(PRECISIONS)} (default: BQA_PRECISION, else single)\n"
         "       --device DEVICE         CUDA device of the engine (default cuda:0)\n"
+        f"       --checkpoint PATH       *.npz file, relative to {cwd}: state + schedule position, written every\n"
+        "                               --checkpoint-every N instructions (default 0: never)\n"
+        "       --resume                continue from --checkpoint if the file exists\n"
         "  -h | --help                  show this message and exit")
 
 
@@ -52,14 +56,19 @@ def _json_path(text: str) -> Path:
 def parse_args(argv: list[str]) -> dict:
     """Options as a dict: input / output (a Path, or None for stdin / stdout), log-level, precision, device.
     ``-h`` prints the usage and exits 0; an unknown argument prints a hint and exits 1."""
-    opts = {"input": None, "output": None, "log-level": DEFAULT_LOG_LEVEL, "precision": None, "device": None}
+    opts = {"input": None, "output": None, "log-level": DEFAULT_LOG_LEVEL, "precision": None, "device": None,
+            "checkpoint": None, "checkpoint-every": 0, "resume": False}
     takes_value = {"-i": "input", "--input": "input", "-o": "output", "--output": "output", "-l": "log-level",
-                   "--log-level": "log-level", "--precision": "precision", "--device": "device"}
+                   "--log-level": "log-level", "--precision": "precision", "--device": "device",
+                   "--checkpoint": "checkpoint", "--checkpoint-every": "checkpoint-every"}
     args = iter(argv[1:])
     for arg in args:
         if arg in ("-h", "--help"):
             print(usage())
             sys.exit(0)
+        if arg == "--resume":
+            opts["resume"] = True
+            continue
         if arg not in takes_value:
             print(f"Invalid command line argument {arg}, run `{argv[0]} --help` to get the documentation")
             sys.exit(1)
@@ -73,6 +82,18 @@ def parse_args(argv: list[str]) -> dict:
             if value not in LOG_LEVELS:
                 raise CliError(f"{value} is not a logging level, must be one of {', '.join(LOG_LEVELS)}")
             opts[key] = value
+        elif key == "checkpoint":
+            try:
+                path = (Path(os.getcwd()) / Path(value)).resolve()
+            except (RuntimeError, OSError) as e:
+                raise CliError(f"cannot resolve the path {value}") from e
+            if path.suffix != ".npz":
+                raise CliError(f"{path} must have the .npz suffix")
+            opts[key] = str(path)
+        elif key == "checkpoint-every":
+            if not value.isdigit():
+                raise CliError(f"{value} is not a number of instructions")
+            opts[key] = int(value)
         elif key == "precision":
             if value not in PRECISIONS:
                 raise CliError(f"{value} is not a precision, must be one of {', '.join(PRECISIONS)}")
@@ -123,7 +144,8 @@ def main(argv: list[str] | None = None, run=None) -> int:
             from .core import run_qa
 
             def run(cfg):
-                return run_qa(cfg, precision=opts["precision"], device=opts["device"])
+                return run_qa(cfg, precision=opts["precision"], device=opts["device"], checkpoint=opts["checkpoint"],
+                              checkpoint_every=opts["checkpoint-every"], resume=opts["resume"])
         write_result(opts["output"], run(config))
     except Exception as e:                      # like the reference: every failure is reported, status 1
         print(format_error(e), file=sys.stderr)

@@ -26,7 +26,10 @@ def json_config(cfg: dict) -> dict:
 def test_parse_args_defaults_and_paths(tmp_path, monkeypatch):
     monkeypatch.chdir(tmp_path)
     opts = cli.parse_args(["prog"])
-    assert opts == {"input": None, "output": None, "log-level": "INFO", "precision": None, "device": None}
+    assert opts == {"input": None, "output": None, "log-level": "INFO", "precision": None, "device": None,
+                    "checkpoint": None, "checkpoint-every": 0, "resume": False}
+    opts = cli.parse_args(["prog", "--checkpoint", "run.npz", "--checkpoint-every", "50", "--resume"])
+    assert opts["checkpoint"] == str((tmp_path / "run.npz").resolve()) and opts["checkpoint-every"] == 50 and opts["resume"]
     opts = cli.parse_args(["prog", "-i", "a.json", "--output", "sub/b.json", "-l", "DEBUG", "--precision", "double",
                            "--device", "cuda:1"])
     assert opts["input"] == (tmp_path / "a.json").resolve() and opts["output"] == (tmp_path / "sub" / "b.json").resolve()
@@ -38,6 +41,8 @@ def test_parse_args_defaults_and_paths(tmp_path, monkeypatch):
     (["prog", "-l", "LOUD"], "logging level"),
     (["prog", "--precision", "half"], "precision"),
     (["prog", "-o"], "no value"),
+    (["prog", "--checkpoint", "state.bin"], ".npz suffix"),
+    (["prog", "--checkpoint-every", "often"], "number of instructions"),
 ])
 def test_bad_options_are_reported_with_status_1(argv, msg, capsys):
     assert cli.main(argv, run=lambda cfg: []) == 1

@@ -215,3 +215,33 @@ def test_isolated_qubit_follows_single_qubit_evolution(emu):
     res, _ = _run(cfg, emu, "double")
     assert np.abs(np.array(res["bloch_vectors"])[3] - instances.isolated_qubit_bloch(cfg)).max() < 1e-12
     assert sorted(set(res["measurement_outcomes"])) <= [-1, 1] and len(res["measurement_outcomes"]) == 4
+
+
+def test_checkpoint_resume_continues_bit_for_bit(tmp_path, emu):
+    """An interrupted run resumed from its checkpoint returns exactly what the uninterrupted run returns: Bloch
+    vectors, sampled bitstring (host RNG state is part of the checkpoint), bond dimensions (core.save_checkpoint)."""
+    cfg = instances.cfg_grid4()                             # 16 steps, then get_bloch_vectors, measure
+    ctx = config_to_context(cfg)
+    want = run_context(ctx, precision="double", _testing_lib=emu)
+    path = str(tmp_path / "anneal.npz")
+
+    class Crash(RuntimeError):
+        pass
+
+    class Flaky(Engine):
+        def run_layer(self, xtime, ztime):
+            if len(self.stats["bond_dims"]) == 11:
+                raise Crash("power cut")
+            return super().run_layer(xtime, ztime)
+
+    with pytest.raises(Crash):
+        run_context(ctx, precision="double", engine_cls=Flaky, checkpoint=path, checkpoint_every=4, _testing_lib=emu)
+    assert os.path.exists(path)
+    got = run_context(ctx, precision="double", checkpoint=path, checkpoint_every=4, resume=True, _testing_lib=emu)
+    assert got == want                                      # lists of Python floats / ints: exact equality
+    # a checkpoint of another schedule or precision is refused
+    with pytest.raises(ValueError):
+        run_context(ctx, precision="single", checkpoint=path, resume=True, _testing_lib=emu)
+    short = config_to_context(instances.cfg_ring24())
+    with pytest.raises(ValueError):
+        run_context(short, precision="double", checkpoint=path, resume=True, _testing_lib=emu)

@@ -1,9 +1,11 @@
 // bqa_fast_d3D4.cu -- specialised sm_100a kernels for the headline shape: degree-3 nodes, bond dimension 4,
 // complex64 (random 3-regular QUBO at max_bond_dim 4: BASELINE.json configs 4 and 5).
 //
-//   k_msgs_d3D4<false> : one BP sweep            (Tensor.pass_msgs, src/bqa/backends.py:381-408, + get_dist :492-495
+//   k_msgs_d3D4<false, MULTI> : one BP sweep     (Tensor.pass_msgs, src/bqa/backends.py:381-408, + get_dist :492-495
 //                                                 + damping :539-540 + the gathers/scatters of state.py:109-112)
-//   k_msgs_d3D4<true>  : ZZ-extended messages    (_get_extended_msgs, state.py:127-139; backends.py:519-526)
+//   k_msgs_d3D4<true, true>   : ZZ-extended messages (_get_extended_msgs, state.py:127-139; backends.py:519-526)
+//   k_bp_run_d3D4<MULTI>      : the whole BP run (_run_bp, state.py:97-124) in one cooperative launch
+//   (MULTI: boundary messages are also stored into the peers' halo slots over NVLink)
 //
 // Work decomposition.  Eight lanes own a node: lane (p, a) holds the slice T[p, a, :, :] (16 complex) in
 // registers, a warp works on 4 consecutive nodes, a CTA of 8 warps is persistent (one per SM) and every warp
@@ -15,10 +17,13 @@
 //   U_j = T x_j m_j                                   (3 mode products instead of the reference's 6)
 //   out_0[x,y] = sum conj(U_1[x,b,c]) U_2[y,b,c],  out_1[x,y] = sum conj(U_2[a,x,c]) U_0[a,y,c],
 //   out_2[x,y] = sum conj(U_1[a,b,x]) U_0[a,b,y]
-// is the same sum as conj(T) . prod_{j != k} m_j . T, at 384 complex multiply-adds per lane.  Legs 1 and 2
-// are thread-local; leg 0 is spread over the 4 `a` lanes, so U_0 and out_0 read the other lanes' slices from
-// shared memory (broadcast reads of padded 144-byte slices: conflict-free), and the per-lane partial sums of
-// out_1 / out_2 are reduced through shared memory into the 16-byte piece of the message each lane stores.
+// is the same sum as conj(T) . prod_{j != k} m_j . T.  Legs 1 and 2 are thread-local; leg 0 is spread over the 4 `a`
+// lanes, so U_0 and out_0 read the other lanes' slices from shared memory (padded 144-byte slices: conflict-free).
+// Only the Hermitian half of every output is computed (real diagonals, upper triangle; out_0: entries (a, a),
+// (a + 1, a), (a + 2, a) per lane), the diagonal of a message is real (half a multiply-add), arithmetic is packed
+// (FFMA2: a complex number is one register pair): ~600 packed multiply-adds per lane and 4-node group.  The per-lane
+// partial sums of out_1 / out_2 are reduce-scattered over the node's 8 lanes with xor shuffles into the 16-byte piece
+// of the message each lane stores; the traces are all-reduced early from the partial diagonals.
 #include <cuda_runtime.h>
 
 #include "bqa_core.cuh"

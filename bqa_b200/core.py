@@ -26,15 +26,17 @@ def save_checkpoint(path: str, engine, next_instruction: int, n_instructions: in
     meta = {"version": CHECKPOINT_VERSION, "D": int(snap["D"]), "next": int(next_instruction), "n": int(n_instructions),
             "precision": engine.precision, "rng": engine.rng.bit_generator.state, "results": results,
             "degrees": sorted(int(d) for d in snap["tensors"])}
+    path = engine.checkpoint_file(path)
     tmp = f"{path}.tmp.{os.getpid()}"
     with open(tmp, "wb") as f:
         np.savez(f, meta=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8), **arrays)
+    engine.checkpoint_barrier()                 # partitioned run: every rank has its file before any is published
     os.replace(tmp, path)
 
 
 def load_checkpoint(path: str, engine, n_instructions: int):
     """Restores the engine from ``save_checkpoint``'s file; returns (next instruction index, results so far)."""
-    with np.load(path) as z:
+    with np.load(engine.checkpoint_file(path)) as z:
         meta = json.loads(bytes(z["meta"]).decode())
         if meta.get("version") != CHECKPOINT_VERSION:
             raise ValueError(f"{path}: checkpoint version {meta.get('version')} is not {CHECKPOINT_VERSION}")
@@ -46,6 +48,7 @@ def load_checkpoint(path: str, engine, n_instructions: int):
                 "lmbds": z["lmbds"]}
         engine.load_state(snap)
     engine.rng.bit_generator.state = meta["rng"]
+    engine.checkpoint_agree(int(meta["next"]), "schedule position")
     return int(meta["next"]), meta["results"]
 
 
@@ -55,13 +58,14 @@ def run_context(context, precision=None, device=None, engine_cls=Engine, checkpo
 
     ``checkpoint``: path of an ``.npz`` file written every ``checkpoint_every`` instructions (0: never) and, with
     ``resume=True`` and the file present, read back first: the run continues after the last completed instruction
-    and returns the same result list as an uninterrupted run."""
+    and returns the same result list as an uninterrupted run.  A partitioned engine writes one file per rank
+    (``<name>.rank<r>of<P>.npz``) and resumes only when every rank holds a file of the same save."""
     engine = engine_cls(context, precision=precision, device=device, **engine_kwargs)
     instructions = list(context.instructions)
     n = len(instructions)
     results = []
     start = 0
-    if resume and checkpoint and os.path.exists(checkpoint):
+    if resume and checkpoint and engine.checkpoint_agree(os.path.exists(engine.checkpoint_file(checkpoint)), "presence"):
         start, results = load_checkpoint(checkpoint, engine, n)
         log.info(f"Resumed from {checkpoint} at instruction number {start} / {n}")
     for i in range(start, n):

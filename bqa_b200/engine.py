@@ -264,6 +264,17 @@ class Engine:
             snap["_pinned"] = keep          # page-locked torch tensors behind the numpy views above
         return snap
 
+    # checkpoint hooks of core.save_checkpoint / load_checkpoint (the partitioned engine writes one file per rank)
+    def checkpoint_file(self, path: str) -> str:
+        return path
+
+    def checkpoint_barrier(self) -> None:
+        """All ranks have written their temporary file (single process: nothing to wait for)."""
+
+    def checkpoint_agree(self, value: int, what: str) -> int:
+        """The value every rank holds (single process: the value); raises when the ranks disagree."""
+        return int(value)
+
     def load_state(self, snap: dict) -> None:
         """Uploads a checkpoint / an oracle state: tensors {degree: (B, 2, D..)}, msgs (2L, D, D), lmbds (L, D)."""
         D = int(snap["D"])

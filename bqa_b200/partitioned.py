@@ -438,6 +438,25 @@ class PartitionedEngine(Engine):
                             self.msgs_buffer.data_ptr(), self._stream())
 
     # -- results ---------------------------------------------------------------------------------------
+    # checkpoint hooks (core.save_checkpoint / load_checkpoint): one file per rank holding the rank's local state
+    # (owned nodes, halo slots, lambdas of its edges); the partition is deterministic, so a resumed run rebuilds the
+    # same local contexts
+    def checkpoint_file(self, path: str) -> str:
+        root, ext = os.path.splitext(path)
+        return f"{root}.rank{self.rank}of{self.world}{ext}"
+
+    def checkpoint_barrier(self) -> None:
+        dist.barrier(group=self.group)
+
+    def checkpoint_agree(self, value: int, what: str) -> int:
+        t = torch.tensor([int(value), -int(value)], dtype=torch.int64, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+        lo, hi = int(t[0]), -int(t[1])
+        if lo != hi:
+            raise RuntimeError(f"the ranks disagree on the checkpoint's {what} ({lo} .. {hi}): the per-rank files "
+                               "are not from the same save; delete them to start over")
+        return lo
+
     def _gather_rows(self, local: torch.Tensor, width: int) -> torch.Tensor:
         """(N_global, width) array assembled from every rank's owned rows (all ranks get it)."""
         full = torch.zeros((self.N_global, width), dtype=local.dtype, device=local.device)

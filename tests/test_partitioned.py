@@ -139,3 +139,47 @@ def test_partitioned_run_matches_reference_golden(golden_dir):
     got = _run_partitioned(instances.cfg_ring24(), 2)
     assert np.abs(got[0]["bloch"] - g["bloch"]).max() < 1e-8
     assert got[0]["outcomes"] == g["outcomes"].tolist()
+
+
+def _worker_ckpt(rank, world, port, cfg, emu_path, path, crash_after, out):
+    """run_context on the partitioned engine with checkpoints; `crash_after` layers every rank raises."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import logging
+        logging.disable(logging.WARNING)
+        from bqa_b200.core import run_context
+
+        class Flaky(PartitionedEngine):
+            def run_layer(self, xtime, ztime):
+                if crash_after is not None and len(self.stats["bond_dims"]) == crash_after:
+                    raise KeyboardInterrupt("power cut")
+                return super().run_layer(xtime, ztime)
+        try:
+            res = run_context(config_to_context(cfg), precision="double", engine_cls=Flaky, checkpoint=path,
+                              checkpoint_every=4, resume=True, _testing_lib=_lib.bind(emu_path))
+            out[rank] = res
+        except KeyboardInterrupt:
+            out[rank] = "crashed"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_partitioned_checkpoint_resume(tmp_path):
+    """Per-rank checkpoint files; the resumed 2-rank run returns what the uninterrupted single-process run returns."""
+    from bqa_b200.core import run_context
+    cfg = instances.cfg_grid4()
+    emu_path = build_hostemu()
+    want = run_context(config_to_context(cfg), precision="double", _testing_lib=_lib.bind(emu_path))
+    path = str(tmp_path / "anneal.npz")
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_ckpt, args=(2, _free_port(), cfg, emu_path, path, 10, out), nprocs=2, join=True)
+    assert out[0] == "crashed" and out[1] == "crashed"
+    assert sorted(os.listdir(tmp_path)) == ["anneal.rank0of2.npz", "anneal.rank1of2.npz"]
+    out2 = mgr.dict()
+    mp.spawn(_worker_ckpt, args=(2, _free_port(), cfg, emu_path, path, None, out2), nprocs=2, join=True)
+    for r in range(2):
+        got = dict(out2[r])
+        assert np.abs(np.array(got["bloch_vectors"]) - np.array(dict(want)["bloch_vectors"])).max() < 1e-12
+        assert got["measurement_outcomes"] == dict(want)["measurement_outcomes"]

@@ -39,3 +39,17 @@ def test_bqa_run_qa_with_b200_backend_equals_numpy_backend(bqa, name):
     got = dict(bqa.run_qa({**cfg, "backend": "b200"}, precision="double", _testing_lib=_lib.bind(build_hostemu())))
     assert np.abs(np.array(got["bloch_vectors"]) - np.array(want["bloch_vectors"])).max() < 1e-8
     assert got["measurement_outcomes"] == want["measurement_outcomes"]
+
+
+def test_b200_backend_has_no_host_arithmetic(bqa):
+    """Index tensors of the compile step work; the numerical Tensor methods raise instead of running numpy under the
+    name "b200" (no CPU fallback, not even through inheritance)."""
+    from bqa_b200 import register_with_bqa
+    cls = register_with_bqa()
+    idx = cls.make_from_list([3, 1, 2])
+    assert idx.numpy.tolist() == [3, 1, 2]
+    t = cls.make_from_numpy(np.ones((2, 2, 3, 3), complex))
+    for call in (lambda: t.get_density_matrices([t]), lambda: t.pass_msgs([t]), lambda: t.apply_x_gates(0.1),
+                 lambda: t.sqrt(), lambda: t.measure(0, 0)):
+        with pytest.raises(RuntimeError, match="no per-op host path"):
+            call()

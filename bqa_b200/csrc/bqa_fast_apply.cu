@@ -39,6 +39,7 @@ constexpr int kStage = kTBytes + kCBytes + kLBytes;
 constexpr int kWBytes = 4 * 3 * 2 * 128;          // W_j^(p) of the 4 nodes
 constexpr int kWarpBytes = 2 * kStage + kWBytes;
 constexpr int kSmem = kWarps * kWarpBytes;
+static_assert(kSmem <= 227 * 1024, "BQA_APPLY_WARPS x (two stages + W tiles) exceeds the 227 KB of shared memory a CTA can own");
 
 struct Args {
   long long B;

@@ -56,6 +56,7 @@ constexpr int kStage = kTBytes + 2 * kMBytes;     // T | incoming messages | pre
 constexpr int kScratch = kOut0 + 4 * kOut0Row;     // packed partials of out_1 / out_2 + the out_0 exchange
 constexpr int kWarpBytes = 2 * kStage + kScratch; // two stages + reduction scratch
 constexpr int kSmem = kWarps * kWarpBytes;
+static_assert(kSmem <= 227 * 1024, "BQA_BP_WARPS x (two stages + scratch) exceeds the 227 KB of shared memory a CTA can own");
 
 struct Args {
   long long B;

@@ -2,7 +2,9 @@
 """bench.py -- annealing steps/s and BP msg-updates/s on the 100k-qubit random 3-regular QUBO (BASELINE.json).
 
     python bench.py [--gpus N] [--steps K] [--warmup W]              our arm (CUDA kernels through the C ABI)
-    python bench.py --impl reference [--steps K] [--warmup W]        reference arm (CPU oracle port, host cores)
+    python bench.py --impl reference [--steps K] [--warmup W]        reference arm (the reference's numpy backend from
+                                                                     baseline/_ref -- the oracle port if that install is
+                                                                     absent -- on the host cores, at the SAME 100k config)
 
 A "step" is one annealing step = one ``run_layer`` (reference src/bqa/state.py:315-321): simple update
 (extended messages, canonicalizers, truncation, Rz/Rx, symmetric gauge) followed by BP to convergence.
@@ -35,7 +37,9 @@ N_QUBITS = 100_000
 SCHEDULE_STEPS = 100          # S
 RAMP = 30                     # untimed steps that take the bond dimension from 1 to 4
 DT = 0.2
-CPU_SAMPLE_QUBITS = 5_000     # bounded sample for the CPU legs (see cpu_baseline.sample)
+CPU_REF_STEPS = 3             # steps the reference arm times at the full 100k config (about 25-45 s each)
+# stated fp32 tolerances (BASELINE.md section 4 / DESIGN.md section 4) asserted on the parity block
+TOL_BLOCH_MAX, TOL_BLOCH_MEAN, TOL_ENERGY_REL, TOL_SWEEPS = 5e-3, 1e-4, 1e-4, 1
 METRIC = "annealing steps/s @100k-qubit random 3-regular QUBO (D=4, complex64)"
 
 
@@ -104,66 +108,193 @@ class ClockSampler:
 
 
 # -------------------------------------------------------------------------------------------------
-# CPU legs: the oracle port of the reference numpy backend on the host cores
+# CPU legs: the reference's own numpy backend (baseline/_ref, unmodified) or, without that install, the oracle
+# port, on the host cores, at the SAME 100k-qubit config -- no scaling from a smaller instance
 # -------------------------------------------------------------------------------------------------
-def cpu_steps_per_s(n_sample: int, steps: int, warmup: int, inject=None) -> dict:
-    """Times `steps` steady-state (D = 4) annealing steps of the oracle on an n_sample-qubit instance of the
-    same generator/schedule and scales by n_sample / 100k (cost is linear in the qubit count; the measured
-    per-qubit cost grows slightly with size, BASELINE.md section 2, so the scaling flatters the CPU).
-    `inject` = (engine factory) lets the GPU arm hand over a D = 4 state instead of ramping on the CPU."""
-    from oracle import bqa_oracle as O
-    total = schedule_len(steps, warmup)
-    cfg = make_config(n_sample, total)
-    octx = O.compile_config(cfg)
-    layers = [i for i in octx.instructions if isinstance(i, dict)]
-    ost = O.init_state(octx)
+class CpuRunner:
+    """Uniform driver of the two CPU implementations of the path.  kind = "reference": LuchnikovI/bqa installed
+    unmodified into baseline/_ref by baseline/install_ref.py (numpy backend, complex128 default, src/bqa/state.py);
+    kind = "port": oracle/bqa_oracle.py (numpy restatement pinned to the reference's outputs, tests/test_oracle.py)."""
+
+    def __init__(self):
+        os.environ["BQA_PRECISION"] = "double"               # the reference's default (src/bqa/utils.py:9-20)
+        sys.path.insert(0, os.path.join(ROOT, "baseline"))
+        self.kind = "port"
+        try:
+            import install_ref
+            if install_ref.add_to_path():
+                import bqa                                    # noqa: F401
+                from bqa import state as rstate
+                from bqa.backends import NumPyBackend
+                from bqa.config.core import config_to_context as ref_compile
+                self.rstate, self.NB, self.ref_compile = rstate, NumPyBackend, ref_compile
+                self.kind = "reference"
+        except Exception as e:                                # a broken install must not take the bench down
+            log(f"baseline/_ref is not usable ({type(e).__name__}: {e}); the CPU legs use the oracle port")
+        if self.kind == "port":
+            from oracle import bqa_oracle as O
+            self.O = O
+        self._sweeps = 0
+
+    def compile(self, cfg: dict):
+        if self.kind == "reference":
+            return self.ref_compile({**cfg, "backend": "numpy"})
+        return self.O.compile_config(cfg)
+
+    def layers(self, ctx) -> list:
+        return [i for i in ctx.instructions if isinstance(i, dict)]
+
+    def node_ids(self, ctx) -> dict:
+        if self.kind == "reference":
+            return {int(d): np.asarray(l.node_ids.numpy) for d, l in ctx.degree_to_layout.items()}
+        return {int(d): np.asarray(l.node_ids) for d, l in ctx.layouts.items()}
+
+    def init_state(self, ctx):
+        return self.rstate._initialize_state(ctx) if self.kind == "reference" else self.O.init_state(ctx)
+
+    def load(self, ctx, st, snap: dict) -> None:
+        """D = 4 state handed over from the GPU run: tensors {degree: (B, 2, D..)}, msgs (2L, D, D), lmbds (L, D)."""
+        c = np.complex128
+        if self.kind == "reference":
+            for d in list(st.degree_to_tensor):
+                st.degree_to_tensor[d] = self.NB(np.ascontiguousarray(snap["tensors"][int(d)], dtype=c))
+            st.msgs = self.NB(np.ascontiguousarray(snap["msgs"], dtype=c))
+            st.lmbds = self.NB(np.ascontiguousarray(snap["lmbds"], dtype=c))
+        else:
+            st.tensors = {d: np.asarray(t, c) for d, t in snap["tensors"].items()}
+            st.msgs = np.asarray(snap["msgs"], c)
+            st.lmbds = np.asarray(snap["lmbds"], c)
+
+    def bond_dim(self, st) -> int:
+        return int(st.bond_dim)
+
+    def run_layer(self, ctx, st, xtime: float, ztime: float) -> int:
+        """one annealing step (src/bqa/state.py:315-321); returns the number of BP sweeps it ran"""
+        if self.kind == "port":
+            n0 = len(st.stats["bp_sweeps"])
+            self.O.run_layer(ctx, st, xtime, ztime)
+            return int(sum(st.stats["bp_sweeps"][n0:]))
+        NB, counter = self.NB, {"n": 0}
+        orig = NB.get_dist
+
+        def counting(this, other):                            # one get_dist per sweep (state.py:113)
+            counter["n"] += 1
+            return orig(this, other)
+        NB.get_dist = counting
+        try:
+            self.rstate.run_layer(ctx, xtime, ztime, st)
+        finally:
+            NB.get_dist = orig
+        return counter["n"]
+
+    def bloch(self, ctx, st) -> np.ndarray:
+        rho = self.rstate.get_density_matrices(ctx, st) if self.kind == "reference" else self.O.density_matrices(ctx, st)
+        return np.stack([(rho[:, 0, 1] + rho[:, 1, 0]).real, (rho[:, 1, 0] - rho[:, 0, 1]).imag,
+                         (rho[:, 0, 0] - rho[:, 1, 1]).real], axis=1)          # src/bqa/utils.py:23-27
+
+    def lmbds(self, st) -> np.ndarray:
+        lm = st.lmbds.numpy if self.kind == "reference" else st.lmbds
+        return np.real(np.asarray(lm))
+
+
+def gpu_state_after_ramp(cfg: dict, n_steps: int, dev=None) -> dict:
+    """The GPU engine (complex64, the arm being benchmarked) takes the schedule's first n_steps steps; its state is
+    what the CPU legs continue from -- the CPU would need about 15 minutes for this ramp at 100k qubits."""
+    from bqa_b200.config import config_to_context
+    from bqa_b200.engine import Engine
+    ctx = config_to_context(cfg)
+    eng = Engine(ctx, precision="single", device=dev)
+    for ins in [i for i in ctx.instructions if isinstance(i, dict)][:n_steps]:
+        eng.run_layer(ins["xtime"], ins["ztime"])
+    snap = eng.state_to_host()
+    snap["node_ids"] = {c.degree: c.node_ids_host for c in eng.classes}
+    return snap
+
+
+def cpu_run(runner: CpuRunner, cfg: dict, snap: dict | None, first: int, steps: int) -> dict:
+    """`steps` annealing steps of the CPU implementation at the full config, starting at schedule position `first`
+    from `snap` (None: ramped on the CPU from the initial state).  Wall clock per step, sweeps, final observables."""
+    ctx = runner.compile(cfg)
+    layers = runner.layers(ctx)
+    st = runner.init_state(ctx)
     t_ramp = time.perf_counter()
-    if inject is not None:
-        snap = inject(cfg, layers[:RAMP])
-        ost.tensors = {d: np.asarray(t, octx.dtype) for d, t in snap["tensors"].items()}
-        ost.msgs = np.asarray(snap["msgs"], octx.dtype)
-        ost.lmbds = np.asarray(snap["lmbds"], octx.dtype)
-        how = "D=4 state handed over from the GPU run"
+    if snap is not None:
+        ids = runner.node_ids(ctx)
+        for d, mine in snap["node_ids"].items():              # both compile steps order the degree classes the same way
+            assert np.array_equal(ids[int(d)], mine), "the CPU and GPU compile steps order the nodes differently"
+        runner.load(ctx, st, snap)
+        how = f"D=4 state after {first} steps handed over from the GPU run"
     else:
-        for ins in layers[:RAMP]:
-            O.run_layer(octx, ost, ins["xtime"], ins["ztime"])
-        how = f"ramped on the CPU ({RAMP} untimed steps)"
+        for ins in layers[:first]:
+            runner.run_layer(ctx, st, ins["xtime"], ins["ztime"])
+        how = f"ramped on the CPU ({first} untimed steps)"
     t_ramp = time.perf_counter() - t_ramp
-    assert ost.bond_dim == 4, f"bond dimension {ost.bond_dim} after the ramp"
-    k = RAMP
-    for ins in layers[k:k + warmup]:
-        O.run_layer(octx, ost, ins["xtime"], ins["ztime"])
-    k += warmup
-    n0 = len(ost.stats["bp_sweeps"])
-    t0 = time.perf_counter()
-    for ins in layers[k:k + steps]:
-        O.run_layer(octx, ost, ins["xtime"], ins["ztime"])
-    dt = time.perf_counter() - t0
-    sweeps = ost.stats["bp_sweeps"][n0:]
-    scale = n_sample / N_QUBITS
-    return {"value": steps / dt * scale, "unit": "steps/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": (f"{steps} steady-state steps (D=4, complex128 like the reference default) of a "
-                       f"{n_sample}-qubit instance of the same generator and schedule, {how}; "
-                       f"{dt / steps:.3f} s/step measured, scaled by {n_sample}/{N_QUBITS} to 100k qubits; "
+    assert runner.bond_dim(st) == 4, f"bond dimension {runner.bond_dim(st)} after the ramp"
+    secs, sweeps = [], []
+    for ins in layers[first:first + steps]:
+        t0 = time.perf_counter()
+        sweeps.append(runner.run_layer(ctx, st, ins["xtime"], ins["ztime"]))
+        secs.append(time.perf_counter() - t0)
+        log(f"[cpu {runner.kind}] step {len(secs)}/{steps}: {secs[-1]:.1f} s, {sweeps[-1]} sweeps")
+    dt = float(np.sum(secs))
+    return {"value": steps / dt, "unit": "steps/s", "cores": os.cpu_count(), "kind": runner.kind,
+            "sample": (f"{steps} steady-state step(s) (D=4, complex128: the reference's default precision) of the full "
+                       f"{N_QUBITS}-qubit config itself, {how}; {dt / steps:.1f} s/step measured, nothing scaled; "
                        f"numpy/OpenBLAS may use all {os.cpu_count()} host cores"),
-            "s_per_step_sample": dt / steps, "sweeps_per_step": float(np.mean(sweeps)) if sweeps else None,
-            "ramp_s": t_ramp}
+            "s_per_step": dt / steps, "sweeps_per_step": float(np.mean(sweeps)), "sweeps": sweeps, "ramp_s": t_ramp,
+            "bloch": runner.bloch(ctx, st), "lmbds": runner.lmbds(st)}
+
+
+def parity_block(cfg: dict, bloch_gpu, lmbds_gpu, sweeps_gpu, cpu: dict) -> dict:
+    """c64 GPU against the c128 CPU implementation after the same steps from the same state (gauge-invariant
+    observables only); asserts the stated fp32 tolerances."""
+    from bqa_b200.benchmarking import ising_energy
+    d = np.abs(np.asarray(bloch_gpu) - cpu["bloch"])
+    spins = lambda b: np.where(b[:, 2] > 0, 1.0, -1.0)
+    e_gpu = ising_energy(cfg["edges"], cfg["nodes"], spins(np.asarray(bloch_gpu)))
+    e_cpu = ising_energy(cfg["edges"], cfg["nodes"], spins(cpu["bloch"]))
+    lm_g, lm_c = np.sort(lmbds_gpu, axis=1)[:, ::-1], np.sort(cpu["lmbds"], axis=1)[:, ::-1]
+    par = {"max_abs": float(d.max()), "mean_abs": float(d.mean()), "energy_rel": abs(e_gpu - e_cpu) / max(abs(e_cpu), 1e-300),
+           "sweeps_diff": int(np.max(np.abs(np.asarray(sweeps_gpu) - np.asarray(cpu["sweeps"])))),
+           "lmbds_max_abs": float(np.abs(lm_g - lm_c).max()), "sign_flips": int(np.sum(spins(np.asarray(bloch_gpu)) != spins(cpu["bloch"]))),
+           "qubits": int(d.shape[0]), "steps": len(cpu["sweeps"]), "against": cpu["kind"],
+           "tolerance": {"max_abs": TOL_BLOCH_MAX, "mean_abs": TOL_BLOCH_MEAN, "energy_rel": TOL_ENERGY_REL,
+                         "sweeps_diff": TOL_SWEEPS}}
+    par["ok"] = bool(par["max_abs"] <= TOL_BLOCH_MAX and par["mean_abs"] <= TOL_BLOCH_MEAN
+                     and par["energy_rel"] <= TOL_ENERGY_REL and par["sweeps_diff"] <= TOL_SWEEPS)
+    return par
 
 
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = args.steps, args.warmup
     t0 = time.perf_counter()
-    r = cpu_steps_per_s(CPU_SAMPLE_QUBITS, steps, warmup)
+    steps = max(1, min(args.steps, CPU_REF_STEPS))
+    total = schedule_len(args.steps, max(args.warmup, 3))     # the schedule our arm runs for the same K, W
+    cfg = make_config(N_QUBITS, total)
+    first = RAMP + max(args.warmup, 3)                        # schedule position of our arm's first timed step
+    runner = CpuRunner()
+    snap = None
+    try:
+        import torch
+        if torch.cuda.is_available():
+            from bqa_b200.build import build
+            build()
+            snap = gpu_state_after_ramp(cfg, first, torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
+    except Exception as e:
+        log(f"no GPU hand-over ({type(e).__name__}: {e}): the CPU ramps from the initial state (about 15 minutes)")
+    r = cpu_run(runner, cfg, snap, first, steps)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "steps/s", "n_gpus": args.gpus,
-            "steps": steps, "warmup": warmup, "ms_per_step": 1e3 / r["value"], "higher_is_better": True,
+            "steps": steps, "warmup": 0, "requested": {"steps": args.steps, "warmup": args.warmup},
+            "ms_per_step": 1e3 / r["value"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
             "config": make_bench_config(args.gpus),
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "sweeps_per_step": r["sweeps_per_step"], "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
+            "sweeps_per_step": r["sweeps_per_step"], "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+            "note": (f"the first {steps} of the K timed steps of the 100k config, each a full annealing step on the "
+                     "host cores; the D=4 start state comes from the GPU run (untimed)")}
     emit(line)
 
 
@@ -273,6 +404,19 @@ def run_ours(args) -> None:
     # ---- end-to-end through the public engine API with HOST buffers --------------------------
     e2e = measure_e2e(eng, snapshot, layers[k:k + steps], torch, dev, bloch_resident, world, dist)
 
+    # ---- multi-GPU correctness: rank 0 replays ramp + warm-up + the K timed steps on a single-GPU engine ------
+    par1 = None
+    if world > 1 and rank == 0:
+        from bqa_b200.engine import Engine
+        one = Engine(ctx, precision="single", device=dev)
+        for ins in layers[:k + steps]:
+            one.run_layer(ins["xtime"], ins["ztime"])
+        d1 = np.abs(one.bloch_vectors() - bloch_resident)
+        par1 = {"max_abs": float(d1.max()), "expected": 0.0, "steps_compared": k + steps,
+                "sweeps_equal": one.stats["bp_sweeps"][:k + steps] == eng.stats["bp_sweeps"][:k + steps],
+                "what": "Bloch vectors of the partitioned run after the timed region vs a single-GPU replay on rank 0"}
+        del one
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -292,19 +436,33 @@ def run_ours(args) -> None:
     if roof:
         line["roofline"] = roof["roofline"]
         line["bp_msg_updates_per_s"] = roof["bp_msg_updates_per_s"]
-        line["kernel_ms_per_step"] = roof["kernel_ms_per_step"]
+        line["kernel_ms_per_step"] = roof["kernel_ms_per_step"]     # instrumented replay of the NEXT K steps of the schedule
+        line["kernel_ms_per_step"]["replay_sweeps_per_step"] = roof["replay_sweeps_per_step"]
     if e2e:
         line["e2e"] = e2e
+    if roof and world > 1:
+        line["roofline"]["traffic"] = None                    # the ncu capture behind `traffic` is a 1-GPU launch
     if world == 1 and not args.no_cpu:
-        def inject(cfg_s, ramp_layers):
-            from bqa_b200.engine import Engine
-            e = Engine(config_to_context(cfg_s), precision="double", device=dev)
-            for ins in ramp_layers:
-                e.run_layer(ins["xtime"], ins["ztime"])
-            return e.state_to_host()
-        r = cpu_steps_per_s(CPU_SAMPLE_QUBITS, args.cpu_steps, 0, inject=inject)
+        # cpu_baseline + parity: ONE steady-state step of the full 100k config on the host cores (the reference's numpy
+        # backend from baseline/_ref, else the oracle port) from the state the timed region started with, against the
+        # same step on the GPU from the same state
+        runner = CpuRunner()
+        snap = {k: v for k, v in snapshot.items() if k != "_pinned"}
+        snap["node_ids"] = {c.degree: c.node_ids_host for c in eng.classes}
+        r = cpu_run(runner, cfg, snap, k, args.cpu_steps)
+        eng.load_state(snapshot)
+        n1 = len(eng.stats["bp_sweeps"])
+        for ins in layers[k:k + args.cpu_steps]:
+            eng.run_layer(ins["xtime"], ins["ztime"])
         line["cpu_baseline"] = {kk: r[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
+        line["parity"] = parity_block(cfg, eng.bloch_vectors(), eng.lmbds_numpy(), eng.stats["bp_sweeps"][n1:], r)
+    if par1 is not None:
+        line["parity_vs_1gpu"] = par1
     emit(line)
+    if line.get("parity") and not line["parity"]["ok"]:
+        raise SystemExit(f"parity outside the stated fp32 tolerance: {line['parity']}")
+    if par1 is not None and par1["max_abs"] != 0.0:
+        raise SystemExit(f"the partitioned run differs from the single-GPU run: {par1}")
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -391,6 +549,7 @@ def measure_roofline(eng, lib, layers, torch, dev) -> dict:
                        "algorithmic_bytes_per_launch": alg_bytes, "launches_timed": launches_timed,
                        "noop_launches_skipped": noop, "peak_source": peak_src}
     out["bp_msg_updates_per_s"] = degree * B / (mean_ms * 1e-3)
+    out["replay_sweeps_per_step"] = float(np.sum(eng.stats["bp_sweeps"][n_runs0:])) / nsteps
     return out
 
 
@@ -449,7 +608,7 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-steps", type=int, default=3, help="steps of the cpu_baseline leg (N=1 only)")
+    ap.add_argument("--cpu-steps", type=int, default=1, help="steps of the cpu_baseline / parity leg (N=1 only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -60,8 +60,11 @@ DEFAULT_SCHEDULE = {
 
 # Backend names accepted by the syntax check.  The reference validates against its registry dict
 # (config_syntax.py:63-70) and defaults to "numpy"; this package provides exactly one backend, "b200",
-# which is therefore also the default.  There is no CPU backend here: "numpy" / "cupy" configs belong to bqa.
+# which is therefore also the default.  The reference's own names "numpy" / "cupy" are accepted so that its examples
+# and benchmark configs (every one of them sets "backend" explicitly) run unmodified -- with a warning, because
+# execution is on the b200 kernels all the same: there is no CPU backend here.
 KNOWN_BACKENDS = {"b200"}
+REFERENCE_BACKENDS = {"numpy", "cupy"}
 
 
 def register_backend_name(name: str) -> None:
@@ -344,8 +347,13 @@ def analyse_config(config) -> dict:
         backend = vals["backend"]
         if not isinstance(backend, str):
             raise ConfigSyntaxError(f"Invalid backend \"{backend}\"")
-        if backend not in KNOWN_BACKENDS:
-            raise ConfigSyntaxError(f"Unknown backend \"{backend}\", available backends {sorted(KNOWN_BACKENDS)}")
+        if backend in REFERENCE_BACKENDS:
+            log.warning(f"Backend \"{backend}\" is a backend of the reference package; bqa_b200 executes the config on "
+                        "its \"b200\" backend (CUDA kernels, complex64 unless BQA_PRECISION=double)")
+            backend = "b200"
+        elif backend not in KNOWN_BACKENDS:
+            raise ConfigSyntaxError(f"Unknown backend \"{backend}\", available backends "
+                                    f"{sorted(KNOWN_BACKENDS | REFERENCE_BACKENDS)} (all executed on b200)")
         E, J = _analyse_edges(edges)
         return {
             "nodes": _analyse_nodes(nodes),

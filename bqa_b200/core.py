@@ -14,7 +14,24 @@ from .engine import Engine
 
 log = logging.getLogger(__name__)
 
-CHECKPOINT_VERSION = 1
+CHECKPOINT_VERSION = 2
+
+
+def engine_fingerprint(engine) -> str:
+    """Hash of what a checkpoint is only valid for: the compiled layouts (graph, slot numbering, amplitudes) and the
+    numerical parameters -- a config of the same sizes but other couplings would load silently otherwise."""
+    import hashlib
+    h = hashlib.sha256()
+    for c in engine.classes:
+        h.update(repr((c.degree, c.B)).encode())
+        h.update(np.ascontiguousarray(c.node_ids_host).tobytes())
+        for t in (c.in_pos, c.out_pos, c.node_ampls, c.edge_ampls):
+            h.update(t.cpu().numpy().tobytes())
+    ctx = engine.ctx
+    for name in ("nodes_number", "edges_number", "max_bond_dim", "max_bp_iters_number", "bp_eps", "pinv_eps", "damping",
+                 "measurement_threshold", "seed"):
+        h.update(repr((name, getattr(ctx, name, None))).encode())
+    return h.hexdigest()
 
 
 def save_checkpoint(path: str, engine, next_instruction: int, n_instructions: int, results: list) -> None:
@@ -25,7 +42,7 @@ def save_checkpoint(path: str, engine, next_instruction: int, n_instructions: in
     arrays.update(msgs=snap["msgs"], lmbds=snap["lmbds"])
     meta = {"version": CHECKPOINT_VERSION, "D": int(snap["D"]), "next": int(next_instruction), "n": int(n_instructions),
             "precision": engine.precision, "rng": engine.rng.bit_generator.state, "results": results,
-            "degrees": sorted(int(d) for d in snap["tensors"])}
+            "degrees": sorted(int(d) for d in snap["tensors"]), "fingerprint": engine_fingerprint(engine)}
     path = engine.checkpoint_file(path)
     tmp = f"{path}.tmp.{os.getpid()}"
     with open(tmp, "wb") as f:
@@ -42,6 +59,8 @@ def load_checkpoint(path: str, engine, n_instructions: int):
             raise ValueError(f"{path}: checkpoint version {meta.get('version')} is not {CHECKPOINT_VERSION}")
         if meta["n"] != n_instructions:
             raise ValueError(f"{path}: written for a schedule of {meta['n']} instructions, this one has {n_instructions}")
+        if meta.get("fingerprint") != engine_fingerprint(engine):
+            raise ValueError(f"{path}: written for another config (graph, amplitudes or parameters differ)")
         if meta["precision"] != engine.precision:
             raise ValueError(f"{path}: written in {meta['precision']} precision, the engine runs in {engine.precision}")
         snap = {"D": meta["D"], "tensors": {d: z[f"tensors_{d}"] for d in meta["degrees"]}, "msgs": z["msgs"],

@@ -197,7 +197,11 @@ BQA_HDN void emit_bp_msg(G g, int D, const cx<R>* g0, const cx<R>* g1, const cx<
   for (int o = g.rank(); o < D * D; o += g.size()) {
     const cx<R> nw = itr * (g0[o] + g1[o]);
     const cx<R> od = old[o];
-    const R a = norm2(nw - od), b = norm2(nw + od);
+    // a NaN entry must not drop out of the maxima (the reference's np.abs().max() propagates it, state.py:113): it
+    // becomes +inf, which survives max() and the bit-pattern atomic max, and makes the residual non-finite on the host
+    R a = norm2(nw - od), b = norm2(nw + od);
+    if (!(a == a)) a = R(INFINITY);
+    if (!(b == b)) b = R(INFINITY);
     mnum = a > mnum ? a : mnum;
     mden = b > mden ? b : mden;
     const cx<R> w = write_undamped ? nw : (damping * od + (R(1) - damping) * nw);

@@ -432,6 +432,9 @@ __device__ __forceinline__ void sweep(const Args& a, const float2* msgs_cur, flo
         // (explicit fused / unfused operations: the result must not depend on how an instantiation was contracted)
         mnum = fmaxf(mnum, fmaxf(abs2_rn(na.x - ov.x, na.y - ov.y), abs2_rn(nb.x - ov.z, nb.y - ov.w)));
         mden = fmaxf(mden, fmaxf(abs2_rn(na.x + ov.x, na.y + ov.y), abs2_rn(nb.x + ov.z, nb.y + ov.w)));
+        // fmaxf drops NaN operands.  Any non-finite entry of the node tensor or of an incoming message reaches the trace
+        // (a sum over every contracted entry), so a non-finite trace poisons the residual like np.abs().max() would
+        if (!(fabsf(tr[k]) < INFINITY)) { mnum = INFINITY; mden = INFINITY; }
         float4 w;
         if (write_undamped) {
           w = make_float4(na.x, na.y, nb.x, nb.y);

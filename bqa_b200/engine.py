@@ -40,6 +40,21 @@ def default_precision() -> str:
     return p
 
 
+def _on_device(method):
+    """Runs a public Engine method with the engine's GPU as the current CUDA device: the raw kernel launches behind the
+    C ABI (cooperative launches, function attributes, the SM count) act on cudaGetDevice(), not on the device of the
+    pointers they are given."""
+    import functools
+
+    @functools.wraps(method)
+    def call(self, *args, **kwargs):
+        if not self.cuda:
+            return method(self, *args, **kwargs)
+        with torch.cuda.device(self.dev):
+            return method(self, *args, **kwargs)
+    return call
+
+
 def _np(x) -> np.ndarray:
     """numpy view of a layout field: ours are arrays, bqa's are Tensor wrappers (.numpy) or lists of them."""
     if isinstance(x, (list, tuple)):
@@ -147,7 +162,9 @@ class Engine:
         cbytes = (2 * Dm * rsize + 15) // 16 * 16
         self._ctrl = self._alloc_shared(rbytes + 16 + cbytes, torch.uint8, "ctrl")
         self._ctrl_rbytes = rbytes
-        self._ctrl_bp = self._ctrl[: rbytes + 16]            # the part a BP run resets
+        # the part a BP run resets: residuals + status[0..2]; status[3] (a grid / peer barrier timed out) is sticky, so a
+        # timeout in any exchange of the step is still there at the step's host read
+        self._ctrl_bp = self._ctrl[: rbytes + 12]
         self._resid = self._ctrl[:rbytes].view(self.rdtype)
         self._status = self._ctrl[rbytes: rbytes + 16].view(torch.int32)
         self._colmax = self._ctrl[rbytes + 16:].view(self.rdtype)[: 2 * Dm]
@@ -246,6 +263,7 @@ class Engine:
         s = self._lmbd_stride
         return self._to_host(self._lmbds[: self.L * s]).reshape(self.L, s)[:, : self.D].copy()
 
+    @_on_device
     def state_to_host(self, pinned: bool = False) -> dict:
         """Checkpoint of the run-time state (the reference has none).  With ``pinned`` the
         arrays are views of page-locked host buffers (listed under "_pinned"), which ``load_state`` uploads
@@ -275,6 +293,7 @@ class Engine:
         """The value every rank holds (single process: the value); raises when the ranks disagree."""
         return int(value)
 
+    @_on_device
     def load_state(self, snap: dict) -> None:
         """Uploads a checkpoint / an oracle state: tensors {degree: (B, 2, D..)}, msgs (2L, D, D), lmbds (L, D)."""
         D = int(snap["D"])
@@ -291,11 +310,15 @@ class Engine:
             return torch.from_numpy(np.ascontiguousarray(np.asarray(arr), dtype=np_c).reshape(-1))
         for c in self.classes:
             t = host(("tensors", c.degree), snap["tensors"][c.degree])
-            assert t.shape[0] == c.B * 2 * D ** c.degree, "tensor batch has the wrong shape"
+            if t.shape[0] != c.B * 2 * D ** c.degree:
+                raise ValueError(f"degree-{c.degree} tensor batch has {t.shape[0]} elements, expected {c.B * 2 * D ** c.degree}")
             c.cur = 0
             c.T[0][: t.shape[0]].copy_(t, non_blocking=True)
         m = host("msgs", snap["msgs"])
-        assert m.shape[0] == self.E2 * D * D
+        if m.shape[0] != self.E2 * D * D:
+            raise ValueError(f"message array has {m.shape[0]} elements, expected {self.E2 * D * D}")
+        if np.asarray(snap["lmbds"]).shape != (self.L, D):
+            raise ValueError(f"lambda array has shape {np.asarray(snap['lmbds']).shape}, expected {(self.L, D)}")
         self._msgs_cur = 0
         self._msgs[0][: m.shape[0]].copy_(m, non_blocking=True)
         lm = np.zeros((self.L, 2 * D), self.np_rdtype)
@@ -370,6 +393,7 @@ class Engine:
         self._bp_run_done(int(status[1]))
         return bool(status[0]), int(status[1]), resid
 
+    @_on_device
     def run_bp(self) -> int:
         max_it = self.max_iters
         assert max_it > 0, "max_bp_iter_number must be positive"      # reference: assert best_msgs is not None
@@ -407,6 +431,10 @@ class Engine:
         num, den = resid[sweeps - 1]
         with np.errstate(divide="ignore", invalid="ignore"):
             dist = float(np.sqrt(num / den))
+        if not np.isfinite(dist):
+            # the reference fails loudly here too: np.abs().max() propagates NaN, `dist < best_dist` never holds and
+            # `assert best_msgs is not None` fires (state.py:113-123)
+            raise FloatingPointError(f"BP residual is not finite ({dist}) after {sweeps} sweeps: the state holds NaN/Inf")
         if done:
             # converged: keep the *input* of the converging sweep (state.py:118-120)
             self._msgs_cur = (self._msgs_cur + sweeps - 1) % 2
@@ -427,6 +455,7 @@ class Engine:
     def _reduce_colmax(self, colmax: torch.Tensor) -> None:
         """Hook for the partitioned engine (all-reduce max); no-op on one GPU."""
 
+    @_on_device
     def run_layer(self, xtime: float, ztime: float) -> None:
         D = self.D
         st = self._stream()
@@ -518,6 +547,7 @@ class Engine:
                              c.in_pos.data_ptr(), c.node_ids.data_ptr(), self._bloch.data_ptr(),
                              self._ws.data_ptr(), self._ws.numel(), st)
 
+    @_on_device
     def bloch_vectors(self) -> np.ndarray:
         """(N, 3) array of (x, y, z) per qubit in node-id order."""
         self._compute_bloch()
@@ -527,7 +557,7 @@ class Engine:
     def density_matrices(self) -> np.ndarray:
         """(N, 2, 2) trace-normalised single-qubit density matrices (state.py:77-94)."""
         b = self.bloch_vectors()
-        rho = np.empty((self.N, 2, 2), np.complex128)
+        rho = np.empty((b.shape[0], 2, 2), np.complex128)       # global node count on a partitioned engine
         rho[:, 0, 0] = 0.5 * (1 + b[:, 2])
         rho[:, 1, 1] = 0.5 * (1 - b[:, 2])
         rho[:, 0, 1] = 0.5 * (b[:, 0] - 1j * b[:, 1])
@@ -537,6 +567,7 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     # sampling  (state.py:250-312)
     # ------------------------------------------------------------------------------------------
+    @_on_device
     def measure(self) -> list:
         st = self._stream()
         outcomes = torch.zeros(self.N, dtype=torch.int32, device=self.dev)

@@ -29,7 +29,7 @@ import torch
 import torch.distributed as dist
 
 from .config import Context, Layout
-from .engine import Engine, _np
+from .engine import Engine, _np, _on_device
 
 log = logging.getLogger(__name__)
 
@@ -464,12 +464,14 @@ class PartitionedEngine(Engine):
         dist.all_reduce(full, op=dist.ReduceOp.SUM, group=self.group)
         return full
 
+    @_on_device
     def bloch_vectors(self) -> np.ndarray:
         self._compute_bloch()
         full = self._gather_rows(self._bloch, 4)
         log.info("Density matrices have been computed")
         return full.cpu().numpy()[:, :3].astype(np.float64)
 
+    @_on_device
     def measure(self) -> list:
         """reference state.py:250-312 with the candidate search and the projections done by the owners."""
         st = self._stream()

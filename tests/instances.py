@@ -139,3 +139,27 @@ def isolated_qubit_bloch(cfg, node=3):
             psi = rx @ rz @ psi
     rho = np.outer(psi, psi.conj())
     return np.array([(rho[0, 1] + rho[1, 0]).real, (rho[1, 0] - rho[0, 1]).imag, (rho[0, 0] - rho[1, 1]).real])
+
+
+def instance_fingerprint(nodes: dict, edges: dict) -> str:
+    """sha256 over node ids / fields / edges / couplings in dict order: the golden generators store it, the GPU tests
+    compare it before trusting a fixture (the random graph comes from networkx and must be rebuilt identically)."""
+    import hashlib
+    h = hashlib.sha256()
+    h.update(np.asarray(list(nodes.keys()), np.int64).tobytes())
+    h.update(np.asarray(list(nodes.values()), np.float64).tobytes())
+    h.update(np.asarray(list(edges.keys()), np.int64).tobytes())
+    h.update(np.asarray(list(edges.values()), np.float64).tobytes())
+    return h.hexdigest()
+
+
+def bench_config(n: int, total_steps: int = 100, dt: float = 0.2) -> dict:
+    """bench.py's workload (BASELINE.json configs[3] at n = 100 000): random 3-regular QUBO, max_bond_dim 4, defaults of
+    reference benchmarks_against_mqlib/random_3_regular_qubo_100000.py:10-34, schedule total_time = dt * S, S steps."""
+    from bqa_b200.benchmarking import generate_qubo_on_random_regular_graph
+    nodes, edges = generate_qubo_on_random_regular_graph(n, 3, seed=42)
+    return {"nodes": nodes, "edges": edges, "max_bond_dim": 4, "bp_eps": 1e-6, "pinv_eps": 1e-6, "damping": 0.0,
+            "max_bp_iter_number": 75, "seed": 42, "default_field": 0.0, "measurement_threshold": 0.95,
+            "schedule": {"total_time": dt * total_steps, "starting_mixing": 1.0,
+                         "actions": [{"type": "real_time_evolution", "weight": 1.0, "steps_number": total_steps,
+                                      "final_mixing": 0.0}]}}

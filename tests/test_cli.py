@@ -96,13 +96,27 @@ def test_failures_print_the_cause_chain(tmp_path, monkeypatch, capsys):
 
 
 def test_unknown_backend_is_rejected_not_silently_replaced(tmp_path, monkeypatch, capsys):
-    """A config that asks for the reference's numpy backend must fail loudly: this engine has no CPU path."""
+    """An unknown backend name fails loudly; the reference's own names are accepted with a warning (see below)."""
     monkeypatch.chdir(tmp_path)
     cfg = json_config(instances.cfg_ring24())
-    cfg["backend"] = "numpy"
+    cfg["backend"] = "tpu"
     (tmp_path / "cfg.json").write_text(json.dumps(cfg))
     assert cli.main(["prog", "-i", "cfg.json", "-l", "ERROR"]) == 1
     assert "backend" in capsys.readouterr().err
+
+
+def test_reference_backend_names_compile_with_a_warning(caplog):
+    """Every reference example / benchmark config sets "backend": "numpy" or "cupy" explicitly: they compile
+    unmodified, are executed on b200, and say so (there is no CPU path to fall back to)."""
+    import logging
+    from bqa_b200.config import config_to_context
+    for name in ("numpy", "cupy"):
+        cfg = dict(instances.cfg_ring24(), backend=name)
+        with caplog.at_level(logging.WARNING, logger="bqa_b200.config"):
+            ctx = config_to_context(cfg)
+        assert ctx.backend == "b200"
+        assert any("b200" in r.message and name in r.message for r in caplog.records)
+        caplog.clear()
 
 
 @pytest.mark.gpu

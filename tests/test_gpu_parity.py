@@ -340,6 +340,111 @@ def test_fast_apply_update_matches_generic(lib, B):
     assert np.array_equal(out[0][1], out[1][1])
 
 
+@pytest.mark.parametrize("B", [1, 3, 5, 6, 2003])
+def test_apply_update_kernels_match_oracle(lib, B):
+    """Kernel-level oracle vector for the simple-update application: both the specialised
+    degree-3 / D = 4 kernel (bqa_fast_apply.cu) and the generic one against the oracle's restatement of
+    apply_canonicalizers_with_extensions (reference backends.py:416-432) -> Rz layer (state.py:142-150) -> Rx layer
+    (:153-156) -> symmetric gauge sqrt(lambda) per leg + L2 normalisation (:219-227, backends.py:450-462) in
+    complex128 on the same complex64 inputs; the re-initialised messages are diag(lambda) / trace (state.py:56-57)."""
+    import torch
+    from bqa_b200 import _lib
+    from oracle import bqa_oracle as O
+    d, D = 3, 4
+    rng = np.random.default_rng(150 + B)
+    L = (3 * B + 1) // 2 + 3
+    t, _, thetas = instances.random_node_batch(B, d, D, seed=11 + B)
+    t32 = t.astype(np.complex64)
+    canon = (rng.normal(size=(2 * L, 8, 8)) + 1j * rng.normal(size=(2 * L, 8, 8))).astype(np.complex64)
+    lm = np.sort(rng.uniform(0.01, 1.0, size=(L, 8)), axis=1)[:, ::-1].astype(np.float32).copy()
+    in_pos = rng.permutation(2 * L)[: d * B].reshape(d, B).astype(np.int32)
+    out_pos = ((in_pos + L) % (2 * L)).astype(np.int32)
+    lpos = (in_pos % L).astype(np.int32)
+    h = rng.uniform(-1, 1, size=B).astype(np.float32)
+    J = np.stack(thetas).astype(np.float32)
+    zt, xt = 0.13, 0.07
+    # oracle: complex couplings like the reference's edge_ampls (principal roots of negative sines)
+    c128 = np.complex128
+    want = O.apply_canonicalizers_ext(t32.astype(c128), [canon[in_pos[j]][:, :, :D].astype(c128) for j in range(d)],
+                                      [(np.float64(np.float32(zt)) * J[j].astype(np.float64)).astype(c128) for j in range(d)])
+    phi = (zt * h.astype(np.float64)).reshape(-1, 1, 1, 1)
+    zz = want.copy()
+    zz[:, 1] *= -1.0
+    want = want * np.cos(phi) - 1j * zz * np.sin(phi)
+    want = np.cos(xt) * want - 1j * np.sin(xt) * want[:, ::-1]
+    for j in range(d):
+        shp = [B, 1, 1, 1, 1]
+        shp[2 + j] = D
+        want = want * np.sqrt(lm[lpos[j]][:, :D].astype(np.float64)).reshape(shp)
+    want = want / np.linalg.norm(want.reshape(B, -1), axis=1).reshape(-1, 1, 1, 1, 1)
+    lam = lm[lpos.reshape(-1)][:, :D].astype(np.float64)
+    want_msgs = (lam / lam.sum(1, keepdims=True))[:, :, None] * np.eye(D)
+    dev = torch.device("cuda:0")
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    T, Cn, Lm = up(t32.reshape(-1)), up(canon.reshape(-1)), up(lm.reshape(-1))
+    ip, op, lp, na, ea = up(in_pos), up(out_pos), up(lpos), up(h), up(J)
+    ws = torch.zeros(lib.workspace_bytes(_lib.C64, d, D, D), dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    for mode in (1, 0):
+        lib.set_kernel_mode(mode)
+        try:
+            Tout = torch.zeros_like(T)
+            msgs = torch.zeros(2 * L * D * D, dtype=torch.complex64, device=dev)
+            lib.apply_update(_lib.C64, d, D, D, B, T.data_ptr(), Tout.data_ptr(), Cn.data_ptr(), Lm.data_ptr(),
+                             msgs.data_ptr(), ip.data_ptr(), op.data_ptr(), lp.data_ptr(), na.data_ptr(), ea.data_ptr(),
+                             zt, xt, ws.data_ptr(), ws.numel(), st)
+        finally:
+            lib.set_kernel_mode(0)
+        got = Tout.cpu().numpy().reshape(want.shape)
+        assert np.abs(got - want).max() < 2e-6, mode
+        got_msgs = msgs.cpu().numpy().reshape(2 * L, D, D)[out_pos.reshape(-1)]
+        assert np.abs(got_msgs - want_msgs).max() < 1e-6, mode
+
+
+def test_rr100k_window_vs_reference_golden(golden_dir, lib):
+    """The benchmarked instance at full size against the UNMODIFIED reference (tests/golden/make_golden_100k.py: numpy
+    backend, complex128): the 30 ramp steps (bond dimension 1 -> 4) plus 3 steady-state steps of bench.py's schedule.
+    complex64 (the benchmarked precision) within the stated fp32 tolerance; complex128 to rounding."""
+    from bqa_b200.benchmarking import ising_energy
+    from bqa_b200.config import config_to_context
+    from bqa_b200.engine import Engine
+    g = np.load(os.path.join(golden_dir, "rr100k_window.npz"))
+    cfg = instances.bench_config(100_000)
+    assert instances.instance_fingerprint(cfg["nodes"], cfg["edges"]) == str(g["fingerprint"]), \
+        "this box rebuilt a different random graph than the one the golden was computed on"
+    ctx = config_to_context(cfg)
+    layers = [i for i in ctx.instructions if isinstance(i, dict)]
+    n_ramp, n_all = 30, len(g["bp_sweeps"])
+    stride = 8
+    for precision in ("single", "double"):
+        eng = Engine(ctx, precision=precision)
+        for ins in layers[:n_ramp]:
+            eng.run_layer(ins["xtime"], ins["ztime"])
+        b_ramp = eng.bloch_vectors()
+        for ins in layers[n_ramp:n_all]:
+            eng.run_layer(ins["xtime"], ins["ztime"])
+        b = eng.bloch_vectors()
+        lm = np.sort(eng.lmbds_numpy(), axis=1)[:, ::-1]
+        assert eng.stats["bond_dims"] == g["bond_dims"].tolist()
+        sw = np.abs(np.array(eng.stats["bp_sweeps"]) - g["bp_sweeps"])
+        e_ref = float(g["energy"])
+        e = ising_energy(cfg["edges"], cfg["nodes"], np.where(b[:, 2] > 0, 1.0, -1.0))
+        if precision == "single":
+            for got, want in ((b_ramp, g["bloch_ramp"]), (b, g["bloch"])):
+                diff = np.abs(got - want)
+                assert diff.max() < 5e-3 and diff.mean() < 1e-4                 # stated fp32 tolerance
+            assert sw.max() <= 1
+            assert np.abs(lm[::stride] - g["lmbds_sorted_strided"]).max() < 1e-4
+            assert abs(e - e_ref) <= 1e-4 * abs(e_ref)
+        else:
+            assert np.abs(b_ramp - g["bloch_ramp"]).max() < 1e-7 and np.abs(b - g["bloch"]).max() < 1e-7
+            assert sw.max() == 0
+            assert np.abs(lm[::stride] - g["lmbds_sorted_strided"]).max() < 1e-9
+            assert np.abs(lm.max(0) - g["lmbds_colmax"]).max() < 1e-9
+            assert e == e_ref
+        del eng
+
+
 # ---- BASELINE.json configs[0..2] as parity cases (SURVEY.md section 8d) ------------------------------------
 def _oracle_vs_gpu(cfg, lib, bloch_tol, check_outcomes=True):
     from oracle import bqa_oracle as O

@@ -367,7 +367,7 @@ def test_apply_update_kernels_match_oracle(lib, B):
     c128 = np.complex128
     want = O.apply_canonicalizers_ext(t32.astype(c128), [canon[in_pos[j]][:, :, :D].astype(c128) for j in range(d)],
                                       [(np.float64(np.float32(zt)) * J[j].astype(np.float64)).astype(c128) for j in range(d)])
-    phi = (zt * h.astype(np.float64)).reshape(-1, 1, 1, 1)
+    phi = (zt * h.astype(np.float64)).reshape(-1, 1, 1, 1, 1)
     zz = want.copy()
     zz[:, 1] *= -1.0
     want = want * np.cos(phi) - 1j * zz * np.sin(phi)

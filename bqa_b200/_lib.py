@@ -29,9 +29,24 @@ SIGNATURES = {
     "bqa_b200_argmax_unmeasured": [_i, _ll, _vp, _vp, _vp, _vp, _vp],
     "bqa_b200_project_node": [_i, _i, _i, _vp, _ll, _i, _vp],
     "bqa_b200_threshold_project": [_i, _i, _i, _ll, _vp, _vp, _vp, _vp, _d, _vp, _vp],
+    # raw operations of the backend interface (bqa_tensor_ops.cu)
+    "bqa_b200_t_unary": [_i, _i, _ll, _vp, _vp, _vp],
+    "bqa_b200_t_binary": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "bqa_b200_t_copy": [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
+    "bqa_b200_t_rows": [_i, _i, _ll, _ll, _vp, _vp, _vp, _vp],
+    "bqa_b200_t_fill": [_i, _ll, _vp, _d, _d, _vp],
+    "bqa_b200_t_axpby": [_i, _ll, _vp, _vp, _d, _d, _vp],
+    "bqa_b200_t_max_abs": [_i, _ll, _vp, _vp, _vp],
+    "bqa_b200_t_col_max": [_i, _ll, _ll, _vp, _vp, _vp],
+    "bqa_b200_t_batch_reduce": [_i, _i, _ll, _ll, _i, _vp, _vp, _vp],
+    "bqa_b200_t_diag": [_i, _ll, _i, _vp, _vp, _vp],
+    "bqa_b200_t_matmul": [_i, _ll, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "bqa_b200_t_svd": [_i, _ll, _i, _vp, _vp, _vp, _vp, _d, _vp, _sz, _vp],
+    "bqa_b200_t_bloch_to_rho": [_i, _ll, _vp, _vp, _vp],
 }
 EXPORTS = list(SIGNATURES) + ["bqa_b200_last_error", "bqa_b200_version", "bqa_b200_launch_count",
-                              "bqa_b200_workspace_bytes", "bqa_b200_set_kernel_mode", "bqa_b200_canon_stats"]
+                              "bqa_b200_workspace_bytes", "bqa_b200_set_kernel_mode", "bqa_b200_canon_stats",
+                              "bqa_b200_t_svd_scratch_bytes"]
 
 
 class Library:
@@ -41,7 +56,12 @@ class Library:
         self.path = path
         self._dll = C.CDLL(path)
         for name, argtypes in SIGNATURES.items():
-            fn = getattr(self._dll, name)
+            try:
+                fn = getattr(self._dll, name)
+            except AttributeError:
+                if name.startswith("bqa_b200_t_"):      # the test-only host emulation covers the fused entry points only
+                    continue
+                raise
             fn.argtypes = argtypes
             fn.restype = _i
             setattr(self, name[len("bqa_b200_"):], self._checked(name, fn))
@@ -50,6 +70,9 @@ class Library:
         self._dll.bqa_b200_launch_count.restype = _ll
         self._dll.bqa_b200_workspace_bytes.argtypes = [_i, _i, _i, _i]
         self._dll.bqa_b200_workspace_bytes.restype = _sz
+        if hasattr(self._dll, "bqa_b200_t_svd_scratch_bytes"):
+            self._dll.bqa_b200_t_svd_scratch_bytes.argtypes = [_i, _i]
+            self._dll.bqa_b200_t_svd_scratch_bytes.restype = _sz
 
     def _checked(self, name, fn):
         def call(*args):
@@ -69,7 +92,8 @@ class Library:
         return int(self._dll.bqa_b200_launch_count())
 
     def set_kernel_mode(self, mode: int) -> None:
-        """0: specialised kernels where they exist (default); 1: generic kernels only."""
+        """0: specialised kernels where they exist (default); 1: generic kernels only; 2: like 0 with the first-design
+        n = 8 canonicalizer (side-by-side measurements)."""
         if self._dll.bqa_b200_set_kernel_mode(int(mode)) != 0:
             raise RuntimeError(self._dll.bqa_b200_last_error().decode())
 
@@ -77,6 +101,9 @@ class Library:
         out = (C.c_ulonglong * 3)()
         self._dll.bqa_b200_canon_stats(out)
         return int(out[0]), int(out[1]), int(out[2])
+
+    def svd_scratch_bytes(self, prec: int, n: int) -> int:
+        return int(self._dll.bqa_b200_t_svd_scratch_bytes(prec, n))
 
     def workspace_bytes(self, prec: int, degree: int, D: int, D_new: int) -> int:
         return int(self._dll.bqa_b200_workspace_bytes(prec, degree, D, D_new))

@@ -2,51 +2,15 @@
 ``bqa.backends.BACKEND_STR_TO_BACKEND`` validated by ``config_syntax.py:63-70`` and resolved into
 ``Context.backend`` by ``config_canonicalization.py:211``).
 
-bqa's compile step only needs the backend to build index tensors (``make_from_list`` / ``make_from_iter``,
-``config_canonicalization.py:109-126, :205``); those stay host arrays, so ``B200Backend`` derives from bqa's
-``NumPyBackend`` for them.  Execution does not go through the per-op ``Tensor`` methods: ``bqa.run_qa`` is
-dispatched, for contexts whose backend is ``B200Backend``, to ``bqa_b200.run_context`` which drives the fused
-CUDA kernels behind the C ABI (include/bqa_b200.h) from the very same ``Context``.  INTEGRATION.md shows the
-three-line change a bqa maintainer would make instead of this monkey patch."""
+``B200Backend`` (bqa_b200/tensor_backend.py) is a real implementation of bqa's ``Tensor`` ABC on device arrays: all 36
+abstract raw operations are CUDA kernels behind the C ABI and the hot composites call the fused kernels, so the
+unmodified ``bqa.state`` engine runs with it op by op (``run_qa(config, fused=False)``).  The default dispatch for a
+whole config stays the fused engine: ``bqa.run_qa`` hands contexts whose backend is ``B200Backend`` to
+``bqa_b200.run_context``, which keeps the state resident in HBM, fuses across the ABC's op boundaries and runs the BP
+loop on the device.  INTEGRATION.md shows the change a bqa maintainer would make instead of the patch below."""
 from __future__ import annotations
 
 _registered = None
-
-# Tensor methods that do arithmetic on tensor data (reference src/bqa/backends.py:28-572): everything the engine in
-# src/bqa/state.py calls.  Constructors, shape queries and ``numpy`` stay: the compile step needs them for index tensors.
-NUMERICAL_METHODS = (
-    "pass_msgs", "get_density_matrices", "get_dist", "make_inplace_damping_update", "apply_x_gates", "apply_z_gates",
-    "apply_canonicalizers", "apply_canonicalizers_with_extensions", "apply_conditional_z_gates", "mul_by_lmbds",
-    "decompose_iden_using_msgs", "truncate_lmbds", "batch_truncate_all_but", "batch_tensordot", "batch_matmul",
-    "get_batch_svd", "batch_trace_normalize", "batch_normalize", "batched_diag", "measure", "sqrt", "pinv", "inv",
-    "batched_svd", "batched_matmul", "batched_trace", "batched_l2_norm", "max_norm",
-    "measure_raw_tensor_by_position_in_place", "apply_x_to_phys_dim_raw", "apply_z_to_phys_dim_raw",
-    "make_inplace_damping_update_raw",
-)
-
-
-def make_backend_class(numpy_backend_cls):
-    """The marker class a bqa maintainer would register as "b200" (INTEGRATION.md): bqa's own numpy backend for
-    the index tensors of the compile step; execution is dispatched on ``context.backend is B200Backend``."""
-
-    class B200Backend(numpy_backend_cls):
-        """numpy index tensors for the compile step, bqa_b200.Engine for execution.
-
-        The numerical methods of the Tensor interface are NOT inherited: calling one (e.g. by driving ``bqa.state``
-        by hand with this backend) would silently compute on the host under the name "b200".  They raise instead."""
-
-    def _refuse(name):
-        def method(self, *args, **kwargs):
-            raise RuntimeError(
-                f"B200Backend.{name}: the b200 backend has no per-op host path; it executes a compiled Context on the "
-                "GPU through bqa.run_qa (after bqa_b200.register_with_bqa()) or bqa_b200.run_context")
-        method.__name__ = name
-        return method
-
-    for name in NUMERICAL_METHODS:
-        if hasattr(numpy_backend_cls, name):
-            setattr(B200Backend, name, _refuse(name))
-    return B200Backend
 
 
 def register_with_bqa():
@@ -59,18 +23,21 @@ def register_with_bqa():
     import bqa.core as core
 
     from .core import run_context
+    from .tensor_backend import make_backend_class
 
-    B200Backend = make_backend_class(backends.NumPyBackend)
+    B200Backend = make_backend_class(backends.Tensor)
     backends.BACKEND_STR_TO_BACKEND["b200"] = B200Backend
     reference_run_qa = core.run_qa
 
-    def run_qa(config, **engine_kwargs) -> list:
+    def run_qa(config, fused: bool = True, **engine_kwargs) -> list:
+        """``fused=True``: the compiled Context is executed by bqa_b200.Engine (fused kernels, device-resident BP loop);
+        ``fused=False``: by the reference's own engine (src/bqa/state.py) through the Tensor methods of B200Backend."""
         context = core.config_to_context(config)
-        if context.backend is B200Backend:
+        if fused and context.backend is B200Backend:
             return run_context(context, **engine_kwargs)
         return reference_run_qa(config)
 
-    run_qa.__doc__ = reference_run_qa.__doc__
+    run_qa.__doc__ = (reference_run_qa.__doc__ or "") + (run_qa.__doc__ or "")
     core.run_qa = run_qa
     bqa.run_qa = run_qa
     _registered = B200Backend

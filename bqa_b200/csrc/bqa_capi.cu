@@ -14,7 +14,8 @@ namespace bqa {
 
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
-static std::atomic<int> g_kernel_mode{0};       // 0: specialised kernels where they exist, 1: generic kernels only
+// 0: specialised kernels where they exist, 1: generic kernels only, 2: like 0 but the first-design n = 8 canonicalizer
+static std::atomic<int> g_kernel_mode{0};
 
 int set_error(const char* fmt, ...) {
   va_list ap;
@@ -49,11 +50,12 @@ int bqa_b200_version(void) { return 1; }
 long long bqa_b200_launch_count(void) { return g_launches.load(); }
 /* profiling aid, see include/bqa_b200.h */
 int bqa_b200_canon_stats(unsigned long long* out3) {
-  canon8_stats(out3);
+  if (g_kernel_mode.load() == 2) canon8_stats(out3); else canon8v2_stats(out3);
   return 0;
 }
 int bqa_b200_set_kernel_mode(int mode) {
-  if (mode != 0 && mode != 1) return set_error("kernel mode must be 0 (auto) or 1 (generic only), got %d", mode);
+  if (mode < 0 || mode > 2)
+    return set_error("kernel mode must be 0 (auto), 1 (generic only) or 2 (auto with the first-design canonicalizer), got %d", mode);
   g_kernel_mode.store(mode);
   return 0;
 }
@@ -69,7 +71,7 @@ int bqa_b200_bp_sweep_p2p(int prec, int degree, int D, long long B, const void* 
                           size_t workspace_bytes, const int32_t* remote_pos, void* const* peers, void* stream) {
   if (int rc = check_shape(prec, degree, D)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (g_kernel_mode.load() == 0 && fast_d3D4_available(prec, degree, D, B))
+  if (g_kernel_mode.load() != 1 && fast_d3D4_available(prec, degree, D, B))
     return launch_fast_msgs_d3D4(false, B, T, msgs_cur, msgs_nxt, in_pos, out_pos, nullptr, 0.0, damping, write_undamped,
                                  bp_eps, it, resid, status, remote_pos, peers, st);
   if (prec == BQA_C64)
@@ -95,7 +97,7 @@ int bqa_b200_ext_msgs_p2p(int prec, int degree, int D, long long B, const void* 
                           void* stream) {
   if (int rc = check_shape(prec, degree, D)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (g_kernel_mode.load() == 0 && fast_d3D4_available(prec, degree, D, B))
+  if (g_kernel_mode.load() != 1 && fast_d3D4_available(prec, degree, D, B))
     return launch_fast_msgs_d3D4(true, B, T, msgs_cur, ext, in_pos, out_pos, edge_ampls, ztime, 0.0, 0, 0.0, 0, nullptr,
                                  nullptr, remote_pos, peers, st);
   if (prec == BQA_C64)
@@ -119,7 +121,7 @@ int bqa_b200_bp_run(int prec, int degree, int D, long long B, const void* T, voi
                     void* stream) {
   if (int rc = check_shape(prec, degree, D)) return rc;
   if (max_iters < 1) return set_error("max_iters must be positive, got %d", max_iters);
-  if (g_kernel_mode.load() != 0 || !fast_d3D4_available(prec, degree, D, B)) {
+  if (g_kernel_mode.load() == 1 || !fast_d3D4_available(prec, degree, D, B)) {
     set_error("bp_run: no single-launch kernel for precision %d, degree %d, D = %d", prec, degree, D);
     return 2;                                              /* not an error: the caller enqueues bqa_b200_bp_sweep calls */
   }
@@ -148,6 +150,8 @@ int bqa_b200_canonicalize(int prec, int D, long long L, const void* ext, void* c
   if (n_cols < 1 || n_cols > 2 * D) return set_error("n_cols %d outside [1, %d]", n_cols, 2 * D);
   cudaStream_t st = (cudaStream_t)stream;
   if (g_kernel_mode.load() == 0 && prec == BQA_C64 && D == 4)
+    return launch_fast_canon8v2(L, ext, canon, lmbds, colmax, pinv_eps, n_cols, st);
+  if (g_kernel_mode.load() == 2 && prec == BQA_C64 && D == 4)
     return launch_fast_canon8(L, ext, canon, lmbds, colmax, pinv_eps, n_cols, st);
   if (prec == BQA_C64) return launch_canonicalize<float>(D, L, ext, canon, lmbds, colmax, pinv_eps, st);
   return launch_canonicalize<double>(D, L, ext, canon, lmbds, colmax, pinv_eps, st);
@@ -161,7 +165,7 @@ int bqa_b200_apply_update(int prec, int degree, int D, int D_new, long long B, c
   if (int rc = check_shape(prec, degree, D)) return rc;
   if (D_new < 1 || D_new > 2 * D || D_new > BQA_MAX_D) return set_error("new bond dimension %d invalid for D = %d", D_new, D);
   cudaStream_t st = (cudaStream_t)stream;
-  if (g_kernel_mode.load() == 0 && fast_apply_available(prec, degree, D, D_new, B)) {
+  if (g_kernel_mode.load() != 1 && fast_apply_available(prec, degree, D, D_new, B)) {
     // the specialised kernel leaves the re-initialised messages to bqa_b200_gauge_msgs: write this class's slots here
     // so that the entry point keeps its contract (msgs_out[out_pos] = diag(lambda) / trace)
     if (int rc = launch_fast_apply_d3D4(B, T_in, T_out, canon, lmbds, in_pos, lmbd_pos, node_ampls, edge_ampls, ztime,

@@ -1,0 +1,567 @@
+// bqa_fast_canon8v2.cu -- canonicalizers of bond dimension 4 (extended dimension n = 8) in complex64, second design.
+//
+// replaces _get_canonicalizers (src/bqa/state.py:171-200) for the headline shape: per undirected edge
+//   m_f = V_f L_f V_f^H, m_b = V_b L_b V_b^H        masked eigendecompositions   (backends.py:483-490, 709-727)
+//   ker = L_f^1/2 V_f^H conj(V_b) L_b^1/2            (state.py:186-187)
+//   ker = U S W^H                                    masked SVD                   (state.py:189)
+//   C_f = V_f L_f^-1/2 U (slot e + L),  C_b = V_b L_b^-1/2 conj(W) (slot e),  lambda = S / |S|   (state.py:196-200)
+//
+// What changed against bqa_fast_canon8.cu (three one-sided Jacobi SVDs per edge, V accumulated in all of them, four
+// lanes per matrix) -- each point measured first in a complex64 numpy emulation on extended messages of real anneals
+// (scratch/canon_proto*.py, numbers in DESIGN.md section 3.2):
+//   * The two eigenproblems run on the CHOLESKY FACTOR.  A message is Hermitian positive semi-definite: m = G G^H with G
+//     lower triangular (diagonal pre-sorted, non-positive pivots give zero columns), and one-sided Jacobi on the columns
+//     of G gives G J = Q diag(sigma) with m = Q diag(sigma^2) Q^H (Veselic-Hari).  The eigenvectors are the normalised
+//     columns -- NO accumulation of the rotations, half the rotation work -- and because the columns of G are already
+//     nearly orthogonal and graded the sweep count drops from 5.8 to 3.9 per problem with a very narrow spread (the
+//     slowest of 32 matrices: 4.0 instead of 6.9).  The emulated end-to-end Bloch error against the complex128
+//     reference is 6 times SMALLER than with Jacobi on the message itself (7.8e-6 vs 4.9e-5 mean).
+//   * lu = L^1/2 V^H is simply (G J)^H and ul = V L^-1/2 is (G J) diag(1 / sigma^2): no square roots, no normalisation.
+//   * The SVD of ker rotates a STACKED matrix [ker ; conj(ul_b)]: the lower block arrives as conj(C_b) = conj(ul_b) W,
+//     no accumulated W and no product afterwards; C_f = ul_f (ker W) diag(1 / S).
+//   * ONE lane owns a whole 8 x 8 matrix (128 registers as packed row pairs), so a rotation of columns (p, q) needs no
+//     shuffle, no reduce-scatter and no broadcast; the four pairs of a round are independent instruction streams.  A
+//     warp works on 16 edges: in the eigen phase lane 2i takes m_f and lane 2i + 1 takes m_b of edge i, in the SVD phase
+//     lane 2i holds ker ("leader": computes the rotations) and lane 2i + 1 the stacked block ("follower": receives the
+//     four rotation scalars by shuffle).
+// Results do not depend on which edges share a warp (a converged matrix is frozen: its later rotations are exact
+// column exchanges), so single-GPU and partitioned runs stay bit-identical.
+#include <cuda_runtime.h>
+
+#include "bqa_core.cuh"
+#include "bqa_f32x2.cuh"
+#include "bqa_launch.cuh"
+
+namespace bqa {
+namespace canon8v2 {
+
+using x2::p2;
+
+constexpr int kWarps = 8;                  // one persistent CTA per SM, 2 warps per sub-partition (the kernel lives on
+                                           // ~250 registers: a whole 8 x 8 complex matrix per lane)
+constexpr int kEdges = 16;                 // edges per warp iteration (2 lanes each)
+constexpr int kMat = 528;                  // 8 rows x 64 bytes + 16: an odd number of 16-byte units, so the 8 lanes of a
+                                           // quarter warp hit 8 different bank groups with 128-bit accesses
+constexpr int kPad = 512;                  // offset of the 16 spare bytes of a matrix slot (row permutation of the owner)
+constexpr int kPair = 3 * kMat;            // per edge: F (A_f sorted, lives to the epilogue) | B (input m_f, then A_b) | Q (input m_b)
+constexpr int kWarpBytes = kEdges * kPair;
+constexpr int kSmem = kWarps * kWarpBytes; // 202 752 bytes
+static_assert(kSmem <= 227 * 1024, "shared memory budget");
+
+// statistics: [0] warp-level Jacobi runs (32 or 16 matrices at a time), [1] sweeps summed over them (a warp sweeps until
+// its slowest matrix has converged), [2] the part of [1] spent on the SVD of ker
+__device__ unsigned long long g_stats[3];
+
+struct Mat {                               // column j, row pair k = (rows 2k, 2k + 1): X = real parts, Y = imaginary parts
+  p2 X[8][4], Y[8][4];
+};
+
+__device__ __forceinline__ float rsqrt_nr(float x) {       // MUFU.RSQ + one Newton step (see bqa_fast_canon8.cu)
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y * (1.5f - 0.5f * x * y * y);
+}
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(unsigned dst, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+struct Rot {
+  float c, s, phx, phy, dw;                // cos, sin, unimodular phase conj(g) / |g|, norm transfer t |g|
+};
+// rotation of one column pair from its inner product (gr, gi) and squared norms (same arithmetic as bqa_fast_canon8.cu)
+__device__ __forceinline__ Rot rot_params(float al, float be, float gr, float gi, float nul, float tol2, bool frozen,
+                                          float& mxg2, float& mxs2) {
+  const float g2 = gr * gr + gi * gi;
+  const float ab = al * be;
+  const bool act = !frozen && !(al <= nul || be <= nul || g2 <= tol2 * ab);
+  const float ig = rsqrt_nr(g2 * 0x1p60f) * 0x1p30f;
+  const float ag = g2 * ig;
+  const float zeta = 0.5f * (be - al) * ig;
+  const float z2 = 1.f + zeta * zeta;
+  const float t0 = __fdividef(1.f, fabsf(zeta) + z2 * rsqrt_nr(z2));
+  const float t = act ? copysignf(t0, zeta) : 0.f;
+  Rot r;
+  r.c = rsqrt_nr(1.f + t * t);
+  r.s = r.c * t;
+  r.phx = act ? gr * ig : 1.f;
+  r.phy = act ? -gi * ig : 0.f;
+  r.dw = act ? t * ag : 0.f;
+  mxg2 = fmaxf(mxg2, act ? __fdividef(g2, ab) : 0.f);
+  mxs2 = fmaxf(mxs2, r.s * r.s);
+  return r;
+}
+
+// conj(a_p) . a_q over the 8 rows
+template <int P, int Q>
+__device__ __forceinline__ void gamma(const Mat& A, float& re, float& im) {
+  p2 r = x2::mul2(A.X[P][0], A.X[Q][0]);
+  p2 i = x2::mul2(A.X[P][0], A.Y[Q][0]);
+  r = x2::fma2(A.Y[P][0], A.Y[Q][0], r);
+  i = x2::fnma2(A.Y[P][0], A.X[Q][0], i);
+#pragma unroll
+  for (int k = 1; k < 4; ++k) {
+    r = x2::fma2(A.X[P][k], A.X[Q][k], r);
+    i = x2::fma2(A.X[P][k], A.Y[Q][k], i);
+    r = x2::fma2(A.Y[P][k], A.Y[Q][k], r);
+    i = x2::fnma2(A.Y[P][k], A.X[Q][k], i);
+  }
+  re = x2::hsum(r);
+  im = x2::hsum(i);
+}
+
+// a_q <- phase a_q, then (a_p, a_q) <- (s a_p + c a_q, c a_p - s a_q): rotation AND exchange of the two columns
+template <int P, int Q>
+__device__ __forceinline__ void rot_cols(Mat& A, const Rot& r) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const p2 qx = x2::fnma2s(r.phy, A.Y[Q][k], x2::mul2s(r.phx, A.X[Q][k]));
+    const p2 qy = x2::fma2s(r.phy, A.X[Q][k], x2::mul2s(r.phx, A.Y[Q][k]));
+    const p2 px = A.X[P][k], py = A.Y[P][k];
+    A.X[Q][k] = x2::fnma2s(r.s, qx, x2::mul2s(r.c, px));
+    A.Y[Q][k] = x2::fnma2s(r.s, qy, x2::mul2s(r.c, py));
+    A.X[P][k] = x2::fma2s(r.c, qx, x2::mul2s(r.s, px));
+    A.Y[P][k] = x2::fma2s(r.c, qy, x2::mul2s(r.s, py));
+  }
+}
+
+// one pair: the leader derives the rotation from its own columns; in the SVD phase (PAIRED) the follower lane takes the
+// four rotation scalars of its leader (lane - 1) instead
+template <bool PAIRED, int P, int Q>
+__device__ __forceinline__ void pair_step(Mat& A, float (&w)[8], float nul, float tol2, bool frozen, float& mxg2,
+                                          float& mxs2, int src_lane) {
+  float gr, gi;
+  gamma<P, Q>(A, gr, gi);
+  Rot r = rot_params(w[P], w[Q], gr, gi, nul, tol2, frozen, mxg2, mxs2);
+  if (PAIRED) {
+    r.c = __shfl_sync(0xffffffffu, r.c, src_lane);
+    r.s = __shfl_sync(0xffffffffu, r.s, src_lane);
+    r.phx = __shfl_sync(0xffffffffu, r.phx, src_lane);
+    r.phy = __shfl_sync(0xffffffffu, r.phy, src_lane);
+  }
+  rot_cols<P, Q>(A, r);
+  const float al = w[P], be = w[Q];
+  w[Q] = al - r.dw;
+  w[P] = be + r.dw;
+}
+
+__device__ __forceinline__ void col_norms(const Mat& A, float (&w)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    p2 s = x2::mul2(A.X[j][0], A.X[j][0]);
+    s = x2::fma2(A.Y[j][0], A.Y[j][0], s);
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      s = x2::fma2(A.X[j][k], A.X[j][k], s);
+      s = x2::fma2(A.Y[j][k], A.Y[j][k], s);
+    }
+    w[j] = x2::hsum(s);
+  }
+}
+
+// One-sided Jacobi on the columns of A, odd-even (transposition) ordering with column exchange as in
+// bqa_fast_canon8.cu: a sweep is 4 x [pairs (0,1) (2,3) (4,5) (6,7) | pairs (1,2) (3,4) (5,6)] by position; after a sweep
+// the column order is reversed, an odd number of sweeps is undone at the end.  On exit the columns are orthogonal and
+// w[j] is the squared norm of column j.  PAIRED: lanes 2i (leader) and 2i + 1 (follower, see pair_step).
+template <bool PAIRED>
+__device__ __forceinline__ void jacobi8(Mat& A, float (&w)[8], int& sweeps) {
+  const int lane = threadIdx.x & 31;
+  const int src_lane = lane & ~1;
+  const float eps = 1.1920929e-07f;
+  const float tol = eps * 2.f * 2.8284271f;                 // eps * 2 * sqrt(n), like the generic kernel
+  const float tol2 = tol * tol;
+  col_norms(A, w);
+  const float fro2 = ((w[0] + w[1]) + (w[2] + w[3])) + ((w[4] + w[5]) + (w[6] + w[7]));
+  const float nul = eps * eps * fro2;                       // columns below eps |A|_F are numerically zero
+  bool frozen = false;
+  int done = 0;
+#pragma unroll 1
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    float mxg2 = 0.f, mxs2 = 0.f;
+#pragma unroll 1
+    for (int rr = 0; rr < 4; ++rr) {
+      pair_step<PAIRED, 0, 1>(A, w, nul, tol2, frozen, mxg2, mxs2, src_lane);
+      pair_step<PAIRED, 2, 3>(A, w, nul, tol2, frozen, mxg2, mxs2, src_lane);
+      pair_step<PAIRED, 4, 5>(A, w, nul, tol2, frozen, mxg2, mxs2, src_lane);
+      pair_step<PAIRED, 6, 7>(A, w, nul, tol2, frozen, mxg2, mxs2, src_lane);
+      pair_step<PAIRED, 1, 2>(A, w, nul, tol2, frozen, mxg2, mxs2, src_lane);
+      pair_step<PAIRED, 3, 4>(A, w, nul, tol2, frozen, mxg2, mxs2, src_lane);
+      pair_step<PAIRED, 5, 6>(A, w, nul, tol2, frozen, mxg2, mxs2, src_lane);
+    }
+    col_norms(A, w);                                        // exact norms once per sweep
+    ++done;
+    // LAPACK xGESVJ's quadratic-convergence test: the next sweep's rotations would be below the tolerance
+    bool fin = frozen || 64.f * mxg2 * mxs2 < tol2;
+    if (PAIRED) fin = __shfl_sync(0xffffffffu, fin ? 1 : 0, src_lane) != 0;
+    frozen = fin;
+    if (!__any_sync(0xffffffffu, !frozen)) break;
+  }
+  sweeps += done;
+  if (done & 1) {                                           // warp-uniform: restore the original column order
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const p2 ax = A.X[j][k], ay = A.Y[j][k];
+        A.X[j][k] = A.X[7 - j][k]; A.Y[j][k] = A.Y[7 - j][k];
+        A.X[7 - j][k] = ax; A.Y[7 - j][k] = ay;
+      }
+      const float wj = w[j];
+      w[j] = w[7 - j];
+      w[7 - j] = wj;
+    }
+  }
+}
+
+// rank of every entry in the descending, stable order of v[0..7]
+__device__ __forceinline__ void ranks_desc(const float (&v)[8], int (&rank)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int r = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r += (v[i] > v[j] || (v[i] == v[j] && i < j)) ? 1 : 0;
+    rank[j] = r;
+  }
+}
+
+// ---- phase 1: eigendecomposition of one Hermitian PSD message through its Cholesky factor --------------------------
+// in : the 8 x 8 message in `src` (row-major, 64-byte rows)
+// out: dst[row][c] = (G J)[row][col of rank c], columns sorted by eigenvalue (descending), columns with eigenvalue
+//      <= pinv_eps (or below the pinv_raw cut) zeroed: dst^H is lu, dst diag(1 / |column|^2) is ul of
+//      decompose_iden_using_msgs (backends.py:483-490)
+__device__ __forceinline__ void eig_phase(const unsigned char* src, unsigned char* pad, unsigned char* dst, float pinv_eps,
+                                          int& sweeps) {
+  // --- diagonal pre-sort: rows / columns are visited in the order of decreasing diagonal (a static stand-in for
+  // diagonal pivoting; perm[pos] = original index, kept in the spare bytes of the owner's input slot)
+  float d[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) d[i] = *reinterpret_cast<const float*>(src + i * 64 + i * 8);
+  {
+    int rk[8];
+    ranks_desc(d, rk);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pad[rk[i]] = (unsigned char)i;
+  }
+  const uint2 pw = *reinterpret_cast<const uint2*>(pad);
+  int roff[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) roff[i] = (int)(((i < 4 ? pw.x : pw.y) >> (8 * (i & 3))) & 0xffu);
+  // --- lower triangle of the permuted matrix and its Cholesky factor, in place (right-looking, fully unrolled)
+  float2 G[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j <= i; ++j) G[i][j] = *reinterpret_cast<const float2*>(src + roff[i] * 64 + roff[j] * 8);
+  __syncwarp();                                             // every lane holds its input: the slots may be overwritten
+  const float thr = G[0][0].x * 0x1p-22f;                   // pivots at the rounding level of the largest one: zero column
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float dk = G[k][k].x;
+    const float r = dk > thr ? rsqrt_nr(dk) : 0.f;
+    G[k][k] = make_float2(dk * r, 0.f);
+#pragma unroll
+    for (int i = k + 1; i < 8; ++i) { G[i][k].x *= r; G[i][k].y *= r; }
+#pragma unroll
+    for (int j = k + 1; j < 8; ++j) {
+      const float2 b = G[j][k];
+#pragma unroll
+      for (int i = j; i < 8; ++i) {                          // G[i][j] -= G[i][k] conj(G[j][k])
+        const float2 a = G[i][k];
+        G[i][j].x -= a.x * b.x + a.y * b.y;
+        G[i][j].y -= a.y * b.x - a.x * b.y;
+      }
+    }
+  }
+  Mat A;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i0 = 2 * k, i1 = 2 * k + 1;
+      A.X[j][k] = x2::pk(i0 >= j ? G[i0][j].x : 0.f, i1 >= j ? G[i1][j].x : 0.f);
+      A.Y[j][k] = x2::pk(i0 >= j ? G[i0][j].y : 0.f, i1 >= j ? G[i1][j].y : 0.f);
+    }
+  float w[8];
+  jacobi8<false>(A, w, sweeps);
+  // --- publish: rows back in the original order, columns by descending eigenvalue w = sigma^2, masked
+  int rk[8];
+  ranks_desc(w, rk);
+  const uint2 pw2 = *reinterpret_cast<const uint2*>(pad);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const bool keep = w[j] > pinv_eps && w[j] > 1.4210855e-14f;    // batched_svd mask; pinv_raw: sqrt(lambda) > eps
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 xr = x2::unpk(A.X[j][k]), yi = x2::unpk(A.Y[j][k]);
+      const int r0 = (int)(((k < 2 ? pw2.x : pw2.y) >> (8 * ((2 * k) & 3))) & 0xffu);
+      const int r1 = (int)(((k < 2 ? pw2.x : pw2.y) >> (8 * ((2 * k + 1) & 3))) & 0xffu);
+      *reinterpret_cast<float2*>(dst + r0 * 64 + rk[j] * 8) = keep ? make_float2(xr.x, yi.x) : make_float2(0.f, 0.f);
+      *reinterpret_cast<float2*>(dst + r1 * 64 + rk[j] * 8) = keep ? make_float2(xr.y, yi.y) : make_float2(0.f, 0.f);
+    }
+  }
+}
+
+__device__ __forceinline__ void lds_row(float2 (&r)[8], const unsigned char* p) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 v = *reinterpret_cast<const float4*>(p + 16 * i);
+    r[2 * i] = make_float2(v.x, v.y);
+    r[2 * i + 1] = make_float2(v.z, v.w);
+  }
+}
+
+// 1 / |column|^2 of a published matrix (0 for the masked, zeroed columns)
+__device__ __forceinline__ void inv_col_norms(const unsigned char* m, float (&inv)[8]) {
+  float w[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) w[j] = 0.f;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    float2 row[8];
+    lds_row(row, m + r * 64);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[j] += row[j].x * row[j].x + row[j].y * row[j].y;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) inv[j] = w[j] > 0.f ? 1.f / w[j] : 0.f;
+}
+
+__global__ void __launch_bounds__(kWarps * 32, 1) k_canon8v2(long long L, const float2* __restrict__ ext,
+                                                             float2* __restrict__ canon, float* __restrict__ lmbds,
+                                                             float* __restrict__ colmax, float pinv_eps, int ncols) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int pair = lane >> 1;
+  const bool leader = (lane & 1) == 0;
+  unsigned char* wbase = smem + wib * kWarpBytes;
+  unsigned char* F = wbase + pair * kPair;                  // A_f (published), needed until the epilogue
+  unsigned char* Bm = F + kMat;                             // input m_f, then A_b (published)
+  unsigned char* Qm = Bm + kMat;                            // input m_b
+  const long long groups = (L + kEdges - 1) / kEdges;
+  const long long nwarps = (long long)gridDim.x * kWarps;
+  const unsigned char* gext = reinterpret_cast<const unsigned char*>(ext);
+  float cm[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) cm[j] = 0.f;
+  int n_sweeps = 0, n_ker = 0, n_jac = 0;
+
+  // copies of one group's 32 input matrices: edge t of the group by one warp-wide 512-byte copy per matrix
+  auto prefetch = [&](long long g) {
+    const unsigned dst = smem_u32(wbase) + lane * 16;
+#pragma unroll 4
+    for (int t = 0; t < kEdges; ++t) {
+      long long e = g * kEdges + t;
+      e = e < L ? e : L - 1;
+      cp_async16(dst + t * kPair + kMat, gext + (size_t)e * 512 + lane * 16);
+      cp_async16(dst + t * kPair + 2 * kMat, gext + (size_t)(e + L) * 512 + lane * 16);
+    }
+    cp_async_commit();
+  };
+  long long g = (long long)blockIdx.x * kWarps + wib;
+  if (g < groups) prefetch(g);
+#pragma unroll 1
+  for (; g < groups; g += nwarps) {
+    long long e = g * kEdges + pair;
+    const bool live = e < L;
+    e = live ? e : L - 1;
+    cp_async_wait_all();
+    __syncwarp();
+    // ---- phase 1: lane 2i decomposes m_f (slot B -> F), lane 2i + 1 decomposes m_b (slot Q -> B)
+    // (the follower publishes into B, which the leader reads its input from: eig_phase loads the whole input into
+    // registers and passes a __syncwarp before anything is stored)
+    eig_phase(leader ? Bm : Qm, (leader ? Bm : Qm) + kPad, leader ? F : Bm, pinv_eps, n_sweeps);
+    n_jac += 1;
+    __syncwarp();
+    // ---- ker = A_f^H conj(A_b) on the leader; the follower loads the stacked block conj(ul_b) = conj(A_b) / |col|^2
+    Mat A;
+    if (leader) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { A.X[j][k] = x2::pk(0.f, 0.f); A.Y[j][k] = x2::pk(0.f, 0.f); }
+#pragma unroll 2
+      for (int r = 0; r < 8; ++r) {
+        float2 f[8], b[8];
+        lds_row(f, F + r * 64);
+        lds_row(b, Bm + r * 64);
+        p2 FX[4], FY[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { FX[k] = x2::pk(f[2 * k].x, f[2 * k + 1].x); FY[k] = x2::pk(f[2 * k].y, f[2 * k + 1].y); }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {                      // ker[i][j] = conj(sum_r A_f[r][i] A_b[r][j])
+            A.X[j][k] = x2::fma2s(b[j].x, FX[k], A.X[j][k]);
+            A.X[j][k] = x2::fnma2s(b[j].y, FY[k], A.X[j][k]);
+            A.Y[j][k] = x2::fnma2s(b[j].y, FX[k], A.Y[j][k]);
+            A.Y[j][k] = x2::fnma2s(b[j].x, FY[k], A.Y[j][k]);
+          }
+      }
+    } else {
+      float inv[8];
+      inv_col_norms(Bm, inv);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float2 r0[8], r1[8];
+        lds_row(r0, Bm + (2 * k) * 64);
+        lds_row(r1, Bm + (2 * k + 1) * 64);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          A.X[j][k] = x2::pk(r0[j].x * inv[j], r1[j].x * inv[j]);
+          A.Y[j][k] = x2::pk(-r0[j].y * inv[j], -r1[j].y * inv[j]);
+        }
+      }
+    }
+    __syncwarp();
+    // slots B and Q are free: the next group's inputs stream in behind the SVD phase
+    if (g + nwarps < groups) prefetch(g + nwarps);
+    // ---- phase 2: one-sided Jacobi on [ker ; conj(ul_b)]
+    float w[8];
+    {
+      const int before = n_sweeps;
+      jacobi8<true>(A, w, n_sweeps);
+      n_ker += n_sweeps - before;
+    }
+    n_jac += 1;
+    // ---- epilogue.  Leader: w = S^2 per column
+    int rk[8];
+    ranks_desc(w, rk);
+    unsigned packed = 0;
+    float sig[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sig[j] = sqrtf(w[j]);
+      packed |= (unsigned)rk[j] << (3 * j);
+      packed |= (sig[j] > pinv_eps ? 1u : 0u) << (24 + j);
+    }
+    packed = __shfl_sync(0xffffffffu, packed, lane & ~1);     // ranks and masks of the leader
+    if (leader) {
+      float nrm2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) nrm2 += sig[j] > pinv_eps ? w[j] : 0.f;
+      const float inrm = 1.f / sqrtf(nrm2);
+      float lam[8], sorted[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) lam[j] = sig[j] > pinv_eps ? sig[j] * inrm : 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float v = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v = rk[j] == c ? lam[j] : v;
+        sorted[c] = v;
+      }
+      if (live) {
+        float4* lo = reinterpret_cast<float4*>(lmbds + (size_t)e * 8);
+        lo[0] = make_float4(sorted[0], sorted[1], sorted[2], sorted[3]);
+        lo[1] = make_float4(sorted[4], sorted[5], sorted[6], sorted[7]);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) cm[c] = fmaxf(cm[c], sorted[c]);
+      }
+      // G[i][j] = (ker W)[i][j] / (S_j |A_f col i|^2) for the kept columns;  C_f[r][j] = sum_i A_f[r][i] G[i][j]
+      float invf[8];
+      inv_col_norms(F, invf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float is = sig[j] > pinv_eps ? 1.f / sig[j] : 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const p2 sc = x2::pk(invf[2 * k] * is, invf[2 * k + 1] * is);
+          A.X[j][k] = x2::mul2(A.X[j][k], sc);
+          A.Y[j][k] = x2::mul2(A.Y[j][k], sc);
+        }
+      }
+      float2* cf = canon + (size_t)(e + L) * 64;
+#pragma unroll 2
+      for (int r = 0; r < 8; ++r) {
+        float2 f[8];
+        lds_row(f, F + r * 64);
+        p2 FX[4], FY[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { FX[k] = x2::pk(f[2 * k].x, f[2 * k + 1].x); FY[k] = x2::pk(f[2 * k].y, f[2 * k + 1].y); }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          p2 re = x2::mul2(FX[0], A.X[j][0]);
+          p2 im = x2::mul2(FX[0], A.Y[j][0]);
+          re = x2::fnma2(FY[0], A.Y[j][0], re);
+          im = x2::fma2(FY[0], A.X[j][0], im);
+#pragma unroll
+          for (int k = 1; k < 4; ++k) {
+            re = x2::fma2(FX[k], A.X[j][k], re);
+            im = x2::fma2(FX[k], A.Y[j][k], im);
+            re = x2::fnma2(FY[k], A.Y[j][k], re);
+            im = x2::fma2(FY[k], A.X[j][k], im);
+          }
+          if (live && rk[j] < ncols) cf[r * 8 + rk[j]] = make_float2(x2::hsum(re), x2::hsum(im));
+        }
+      }
+    } else {
+      // follower: column j holds conj(C_b)[:, j]; slot e, column position = the leader's rank of j
+      float2* cb = canon + (size_t)e * 64;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = (int)((packed >> (3 * j)) & 7u);
+        const bool keep = (packed >> (24 + j)) & 1u;
+        if (live && c < ncols) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 xr = x2::unpk(A.X[j][k]), yi = x2::unpk(A.Y[j][k]);
+            cb[(2 * k) * 8 + c] = keep ? make_float2(xr.x, -yi.x) : make_float2(0.f, 0.f);
+            cb[(2 * k + 1) * 8 + c] = keep ? make_float2(xr.y, -yi.y) : make_float2(0.f, 0.f);
+          }
+        }
+      }
+    }
+    __syncwarp();                                           // F is rewritten by the next iteration's phase 1
+  }
+  // column-wise max of lambda over all edges (truncate_lmbds, backends.py:297-299); only leaders hold values
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) cm[c] = fmaxf(cm[c], __shfl_xor_sync(0xffffffffu, cm[c], o));
+  }
+  if (lane < 8) {
+    float v = cm[0];
+#pragma unroll
+    for (int c = 1; c < 8; ++c) v = lane == c ? cm[c] : v;
+    atomicMax(reinterpret_cast<unsigned int*>(colmax + lane), __float_as_uint(v));
+  }
+  if (lane == 0) {
+    atomicAdd(&g_stats[0], (unsigned long long)n_jac);
+    atomicAdd(&g_stats[1], (unsigned long long)n_sweeps);
+    atomicAdd(&g_stats[2], (unsigned long long)n_ker);
+  }
+}
+
+}  // namespace canon8v2
+
+void canon8v2_stats(unsigned long long* out3) {
+  cudaMemcpyFromSymbol(out3, canon8v2::g_stats, sizeof(unsigned long long) * 3);
+}
+
+int launch_fast_canon8v2(long long L, const void* ext, void* canon, void* lmbds, void* colmax, double pinv_eps,
+                         int ncols, cudaStream_t st) {
+  using namespace canon8v2;
+  if (L == 0) return 0;
+  if (ncols < 1 || ncols > 8) return set_error("canonicalize: %d canonicalizer columns requested for n = 8", ncols);
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(k_canon8v2, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(k_canon8v2): %s", cudaGetErrorString(e));
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sms <= 0) sms = 148;
+  const long long groups = (L + kEdges - 1) / kEdges;
+  long long grid = (groups + kWarps - 1) / kWarps;
+  if (grid > sms) grid = sms;
+  k_canon8v2<<<(int)grid, kWarps * 32, kSmem, st>>>(L, (const float2*)ext, (float2*)canon, (float*)lmbds, (float*)colmax,
+                                                   (float)pinv_eps, ncols);
+  return after_launch("canonicalize(n=8, v2)");
+}
+
+}  // namespace bqa

@@ -82,5 +82,9 @@ int launch_fast_canon8(long long L, const void* ext, void* canon, void* lmbds, v
                        int ncols, cudaStream_t st);
 
 void canon8_stats(unsigned long long* out3);
+// second design (bqa_fast_canon8v2.cu): Cholesky factor + column Jacobi for the eigenproblems, stacked SVD of ker
+int launch_fast_canon8v2(long long L, const void* ext, void* canon, void* lmbds, void* colmax, double pinv_eps,
+                         int ncols, cudaStream_t st);
+void canon8v2_stats(unsigned long long* out3);
 
 }  // namespace bqa

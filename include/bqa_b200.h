@@ -38,7 +38,9 @@ int bqa_b200_version(void);
 long long bqa_b200_launch_count(void);
 
 /* 0 (default): specialised kernels where one exists for (precision, degree, D), generic kernels otherwise;
- * 1: generic kernels only (used by the tests to check the specialised kernels against the generic ones) */
+ * 1: generic kernels only (used by the tests to check the specialised kernels against the generic ones);
+ * 2: like 0 with the first-design n = 8 canonicalizer (bqa_fast_canon8.cu) instead of the current one
+ *    (bqa_fast_canon8v2.cu): kept for side-by-side measurements */
 int bqa_b200_set_kernel_mode(int mode);
 
 /* profiling aid: out3[0] = warp-level Jacobi problems (4 matrices each) solved by the n = 8 canonicalizer kernel
@@ -162,6 +164,48 @@ int bqa_b200_project_node(int prec, int degree, int D, void* T, long long pos, i
 int bqa_b200_threshold_project(int prec, int degree, int D, long long B, void* T, const int32_t* node_ids,
                                const void* bloch, int32_t* outcomes, double thr, int32_t* n_projected,
                                void* stream);
+
+/* ---- raw operations of the backend interface on device arrays (bqa_tensor_ops.cu) ----------------------------
+ * The reference's plugin boundary is the ABC bqa.backends.Tensor (src/bqa/backends.py:28-252): 36 abstract raw
+ * operations from which it builds every composite.  bqa_b200.tensor_backend.B200Backend implements them with the
+ * entry points below (dense row-major device arrays; complex64 / complex128 by `prec`; index arrays int64), so the
+ * unmodified engine src/bqa/state.py runs op by op on the GPU.  Each comment names the raw op it serves.           */
+
+/* op: 0 inv_raw (:638), 1 pinv_raw (:719-727; cut at machine epsilon of the precision), 2 sqrt_raw (:683, principal
+ * branch), 3 sin_raw, 4 cos_raw (:741-746), 5 conj_raw (:663) */
+int bqa_b200_t_unary(int prec, int op, long long n, const void* a, void* out, void* stream);
+/* op: 0 mul_raw, 1 sum_raw, 2 sub_raw, 3 div_raw (:694-706, :757) with numpy broadcasting expressed as element
+ * strides (0 on a broadcast axis); out is dense, rank <= 8 */
+int bqa_b200_t_binary(int prec, int op, int rank, const long long* shape, const long long* strides_a,
+                      const long long* strides_b, const void* a, const void* b, void* out, void* stream);
+/* strided copy of 4-, 8- or 16-byte elements: transpose_raw (:676), truncate_raw_tensor (:737), take_batch_slice (:688),
+ * concatenate (:749), apply_x_to_phys_dim_raw (:632, a negative stride on the physical axis) */
+int bqa_b200_t_copy(int elem_bytes, int rank, const long long* shape, const long long* strides_in,
+                    const long long* strides_out, const void* in, void* out, void* stream);
+/* batched_gather (:607, scatter = 0: out[i] = in[idx[i]]) and assign_at_batch_indices_raw (:646-650, scatter = 1:
+ * out[idx[i]] = in[i], in place on `out`); rows of row_elems elements */
+int bqa_b200_t_rows(int elem_bytes, int scatter, long long n_idx, long long row_elems, const long long* idx,
+                    const void* in, void* out, void* stream);
+int bqa_b200_t_fill(int prec, long long n, void* out, double re, double im, void* stream);
+/* make_inplace_damping_update_raw (:761-764): dst = alpha dst + beta src */
+int bqa_b200_t_axpby(int prec, long long n, void* dst, const void* src, double alpha, double beta, void* stream);
+/* max_norm (:621-625): is_full -> one complex element holding max |a|; otherwise |max over the batch axis| per column */
+int bqa_b200_t_max_abs(int prec, long long n, const void* a, void* out1, void* stream);
+int bqa_b200_t_col_max(int prec, long long batch, long long inner, const void* a, void* out, void* stream);
+/* mode 0: batched_l2_norm (:610-618); mode 1: batched_trace (:628) of (batch, n, n) */
+int bqa_b200_t_batch_reduce(int prec, int mode, long long batch, long long inner, int n, const void* a, void* out,
+                            void* stream);
+/* batched_diag (:657-660): out[..., i, j] = a[..., i] (i == j) */
+int bqa_b200_t_diag(int prec, long long rows, int n, const void* a, void* out, void* stream);
+/* batched_matmul (:666-670): (batch, m, k) @ (batch, k, n) */
+int bqa_b200_t_matmul(int prec, long long batch, int m, int k, int n, const void* a, const void* b, void* out,
+                      void* stream);
+/* batched_svd (:709-717) of square matrices n <= 32: u, s (stored complex), vh, descending, masked at pinv_eps */
+size_t bqa_b200_t_svd_scratch_bytes(int prec, int n);
+int bqa_b200_t_svd(int prec, long long batch, int n, const void* a, void* u, void* s, void* vh, double pinv_eps,
+                   void* scratch, size_t scratch_bytes, void* stream);
+/* (B, 2, 2) density matrices from the (x, y, z, p0) rows bqa_b200_density writes (utils.py:23-27 inverted) */
+int bqa_b200_t_bloch_to_rho(int prec, long long B, const void* bloch, void* rho, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,79 @@
+"""Times bqa_b200_canonicalize on the extended messages of the benchmarked instance (100k-qubit 3-regular QUBO after
+`--steps` annealing steps) for the current n = 8 kernel (mode 0) and the first design (mode 2); prints one JSON line.
+
+    python scripts/time_canon.py [--qubits 100000] [--steps 40] [--reps 20]
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--qubits", type=int, default=100_000)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--reps", type=int, default=20)
+    args = ap.parse_args()
+    import instances
+    from bqa_b200 import _lib
+    from bqa_b200.config import config_to_context
+    from bqa_b200.engine import Engine
+    lib = _lib.load_library()
+    ctx = config_to_context(instances.bench_config(args.qubits))
+    eng = Engine(ctx, precision="single")
+    layers = [i for i in ctx.instructions if isinstance(i, dict)]
+    for ins in layers[:args.steps]:
+        eng.run_layer(ins["xtime"], ins["ztime"])
+    # the extended messages of the next step, as the canonicalizer would see them
+    ins = layers[args.steps]
+    st = torch.cuda.current_stream().cuda_stream
+    c = eng.classes[0]
+    lib.ext_msgs(eng.prec, c.degree, eng.D, c.B, c.T[c.cur].data_ptr(), eng.msgs_buffer.data_ptr(), eng._ext.data_ptr(),
+                 c.in_pos.data_ptr(), c.out_pos.data_ptr(), c.edge_ampls.data_ptr(), float(ins["ztime"]),
+                 eng._ws.data_ptr(), eng._ws.numel(), st)
+    out = {"qubits": args.qubits, "edges": eng.L, "D": eng.D, "after_steps": args.steps}
+    res = {}
+    for mode in (2, 0):
+        lib.set_kernel_mode(mode)
+        canon = torch.zeros_like(eng._canon)
+        lm = torch.zeros_like(eng._lmbds)
+        colmax = torch.zeros(8, dtype=torch.float32, device=eng.dev)
+        call = lambda: lib.canonicalize(eng.prec, eng.D, eng.L, eng._ext.data_ptr(), canon.data_ptr(), lm.data_ptr(),
+                                        colmax.data_ptr(), eng.pinv_eps, 4, st)
+        for _ in range(3):
+            call()
+        torch.cuda.synchronize()
+        s0 = lib.canon_stats()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.reps):
+            call()
+        e1.record()
+        torch.cuda.synchronize()
+        s1 = lib.canon_stats()
+        ms = e0.elapsed_time(e1) / args.reps
+        res[mode] = (canon.cpu().numpy().reshape(2 * eng.L, 8, 8), lm.cpu().numpy().reshape(eng.L, 8), colmax.cpu().numpy())
+        out[f"mode{mode}"] = {"ms": ms, "edges_per_s": eng.L / (ms * 1e-3),
+                              "sweeps_per_warp_run": (s1[1] - s0[1]) / max(s1[0] - s0[0], 1),
+                              "ker_share_of_sweeps": (s1[2] - s0[2]) / max(s1[1] - s0[1], 1)}
+    lib.set_kernel_mode(0)
+    out["lambda_max_abs_diff"] = float(np.abs(res[0][1] - res[2][1]).max())
+    out["colmax"] = [res[0][2].tolist(), res[2][2].tolist()]
+    # gauge-invariant comparison of the canonicalizers: the projectors C_f C_b^T restricted to the kept columns agree
+    pf = res[0][0][eng.L:, :, :4] @ np.swapaxes(res[0][0][:eng.L, :, :4], 1, 2)
+    pf2 = res[2][0][eng.L:, :, :4] @ np.swapaxes(res[2][0][:eng.L, :, :4], 1, 2)
+    out["CfCbT_max_abs_diff"] = float(np.abs(pf - pf2).max())
+    out["CfCbT_scale"] = float(np.abs(pf2).max())
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

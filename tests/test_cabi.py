@@ -47,7 +47,10 @@ def test_cuda_sources_target_sm_100a_only():
 
 
 def test_host_emulation_exports_the_same_abi():
+    """the fused entry points (what the engine calls); the raw-op entry points bqa_b200_t_* of the backend class exist
+    in the CUDA library only"""
     from hostemu.build import build as build_hostemu
     dll = ctypes.CDLL(build_hostemu())
     for name in declared_symbols():
-        assert hasattr(dll, name), name
+        if not name.startswith("bqa_b200_t_"):
+            assert hasattr(dll, name), name

@@ -242,9 +242,10 @@ def _graded_ext_msgs(rng, L, n=8):
     return np.concatenate([psd(), psd()], 0)
 
 
-@pytest.mark.parametrize("L", [1, 5, 3001])
+@pytest.mark.parametrize("L", [1, 5, 16, 17, 3001])
 def test_fast_canon8_matches_oracle(lib, L):
-    """Specialised n = 8 complex64 canonicalizer kernel (bqa_fast_canon8.cu) against the oracle's
+    """Specialised n = 8 complex64 canonicalizer kernels (bqa_fast_canon8v2.cu, the current one: mode 0; bqa_fast_canon8.cu,
+    the first design: mode 2) and the generic kernel (mode 1) against the oracle's
     _get_canonicalizers restatement (reference state.py:171-200) in complex128.  Gauge-invariant checks: the lambdas,
     their column maxima, and the defining property of the canonicalizers -- with the oracle's square-root factors
     lu_f, lu_b of the masked messages (backends.py:483-490) and ker = lu_f lu_b^T (state.py:186-187),
@@ -266,7 +267,7 @@ def test_fast_canon8_matches_oracle(lib, L):
     dev = torch.device("cuda:0")
     e = torch.from_numpy(ext.reshape(-1)).to(dev)
     st = torch.cuda.current_stream().cuda_stream
-    for mode in (1, 0):
+    for mode in (1, 2, 0):
         lib.set_kernel_mode(mode)
         try:
             canon = torch.zeros_like(e)

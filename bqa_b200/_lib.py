@@ -29,6 +29,10 @@ SIGNATURES = {
     "bqa_b200_argmax_unmeasured": [_i, _ll, _vp, _vp, _vp, _vp, _vp],
     "bqa_b200_project_node": [_i, _i, _i, _vp, _ll, _i, _vp],
     "bqa_b200_threshold_project": [_i, _i, _i, _ll, _vp, _vp, _vp, _vp, _d, _vp, _vp],
+    # all degree classes in one launch (bqa_multiclass.cuh); the class table is a host array of ClassDesc
+    "bqa_b200_ext_msgs_classes": [_i, _i, _vp, _i, _vp, _vp, _d, _vp, _sz, _vp],
+    "bqa_b200_apply_update_classes": [_i, _i, _vp, _i, _i, _vp, _vp, _vp, _d, _d, _vp, _sz, _vp],
+    "bqa_b200_bp_run_classes": [_i, _i, _vp, _i, _vp, _vp, _i, _d, _d, _i, _vp, _vp, _vp, _sz, _vp],
     # raw operations of the backend interface (bqa_tensor_ops.cu)
     "bqa_b200_t_unary": [_i, _i, _ll, _vp, _vp, _vp],
     "bqa_b200_t_binary": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
@@ -49,6 +53,12 @@ EXPORTS = list(SIGNATURES) + ["bqa_b200_last_error", "bqa_b200_version", "bqa_b2
                               "bqa_b200_t_svd_scratch_bytes"]
 
 
+class ClassDesc(C.Structure):
+    """bqa_b200_class of include/bqa_b200.h: one row of the degree-class table of the *_classes entry points"""
+    _fields_ = [("degree", _i), ("B", _ll), ("T_in", _vp), ("T_out", _vp), ("in_pos", _vp), ("out_pos", _vp),
+                ("lmbd_pos", _vp), ("node_ampls", _vp), ("edge_ampls", _vp)]
+
+
 class Library:
     """Thin checked wrapper: every entry point returns 0 or raises RuntimeError(last_error)."""
 
@@ -59,7 +69,8 @@ class Library:
             try:
                 fn = getattr(self._dll, name)
             except AttributeError:
-                if name.startswith("bqa_b200_t_"):      # the test-only host emulation covers the fused entry points only
+                # the test-only host emulation covers the per-class fused entry points only
+                if name.startswith("bqa_b200_t_") or name.endswith("_classes"):
                     continue
                 raise
             fn.argtypes = argtypes

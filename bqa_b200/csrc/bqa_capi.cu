@@ -130,6 +130,46 @@ int bqa_b200_bp_run(int prec, int degree, int D, long long B, const void* T, voi
                                  (cudaStream_t)stream);
 }
 
+int bqa_b200_ext_msgs_classes(int prec, int n_classes, const bqa_b200_class* cls, int D, const void* msgs_cur, void* ext,
+                              double ztime, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = check_shape(prec, 0, D)) return rc;
+  if (!cls) return set_error("ext_msgs_classes: no class table");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (prec == BQA_C64)
+    return launch_multiclass<float>(0, n_classes, cls, D, D, (void*)msgs_cur, ext, 0, nullptr, nullptr, ztime, 0.0, 0.0, 0.0,
+                                    0, nullptr, nullptr, workspace, workspace_bytes, st);
+  return launch_multiclass<double>(0, n_classes, cls, D, D, (void*)msgs_cur, ext, 0, nullptr, nullptr, ztime, 0.0, 0.0, 0.0,
+                                   0, nullptr, nullptr, workspace, workspace_bytes, st);
+}
+
+int bqa_b200_apply_update_classes(int prec, int n_classes, const bqa_b200_class* cls, int D, int D_new, const void* canon,
+                                  const void* lmbds, void* msgs_out, double ztime, double xtime, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  if (int rc = check_shape(prec, 0, D)) return rc;
+  if (D_new < 1 || D_new > 2 * D || D_new > BQA_MAX_D) return set_error("new bond dimension %d invalid for D = %d", D_new, D);
+  if (!cls) return set_error("apply_update_classes: no class table");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (prec == BQA_C64)
+    return launch_multiclass<float>(1, n_classes, cls, D, D_new, nullptr, msgs_out, 0, canon, lmbds, ztime, xtime, 0.0, 0.0,
+                                    0, nullptr, nullptr, workspace, workspace_bytes, st);
+  return launch_multiclass<double>(1, n_classes, cls, D, D_new, nullptr, msgs_out, 0, canon, lmbds, ztime, xtime, 0.0, 0.0,
+                                   0, nullptr, nullptr, workspace, workspace_bytes, st);
+}
+
+int bqa_b200_bp_run_classes(int prec, int n_classes, const bqa_b200_class* cls, int D, void* msgs0, void* msgs1, int parity,
+                            double damping, double bp_eps, int max_iters, void* resid, int32_t* status, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  if (int rc = check_shape(prec, 0, D)) return rc;
+  if (max_iters < 1) return set_error("max_iters must be positive, got %d", max_iters);
+  if (!cls) return set_error("bp_run_classes: no class table");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (prec == BQA_C64)
+    return launch_multiclass<float>(2, n_classes, cls, D, D, msgs0, msgs1, parity, nullptr, nullptr, 0.0, 0.0, damping,
+                                    bp_eps, max_iters, resid, status, workspace, workspace_bytes, st);
+  return launch_multiclass<double>(2, n_classes, cls, D, D, msgs0, msgs1, parity, nullptr, nullptr, 0.0, 0.0, damping,
+                                   bp_eps, max_iters, resid, status, workspace, workspace_bytes, st);
+}
+
 int bqa_b200_gauge_msgs(int prec, int D_old, int D_new, long long L, const void* lmbds, void* msgs_out, void* stream) {
   if (int rc = check_shape(prec, 0, D_old)) return rc;
   if (D_new < 1 || D_new > 2 * D_old || D_new > BQA_MAX_D) return set_error("new bond dimension %d invalid for D = %d", D_new, D_old);

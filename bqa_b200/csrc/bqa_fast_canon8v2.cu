@@ -127,24 +127,41 @@ __device__ __forceinline__ void rot_cols(Mat& A, const Rot& r) {
   }
 }
 
-// one pair: the leader derives the rotation from its own columns; in the SVD phase (PAIRED) the follower lane takes the
-// four rotation scalars of its leader (lane - 1) instead
-template <bool PAIRED, int P, int Q>
-__device__ __forceinline__ void pair_step(Mat& A, float (&w)[8], float nul, float tol2, bool frozen, float& mxg2,
-                                          float& mxs2, int src_lane) {
-  float gr, gi;
-  gamma<P, Q>(A, gr, gi);
-  Rot r = rot_params(w[P], w[Q], gr, gi, nul, tol2, frozen, mxg2, mxs2);
-  if (PAIRED) {
-    r.c = __shfl_sync(0xffffffffu, r.c, src_lane);
-    r.s = __shfl_sync(0xffffffffu, r.s, src_lane);
-    r.phx = __shfl_sync(0xffffffffu, r.phx, src_lane);
-    r.phy = __shfl_sync(0xffffffffu, r.phy, src_lane);
+// One round = NP (4 or 3) disjoint pairs of neighbouring columns.  Every lane derives the rotations from its own columns
+// and then takes the four rotation scalars of lane `src_lane`: itself in the eigen phase, its leader (lane - 1) for the
+// follower lanes of the SVD phase.  The four inner products, then the four parameter chains, then the rotations: the
+// independent chains sit next to each other for the scheduler.  (ONE code body for both phases: with two instantiations
+// warps in different phases evicted each other's 16 KB loop from the 32 KB instruction cache -- 14 % misses, "no
+// instruction" the second largest stall in the first ncu capture.)
+template <int NP, int P0, int Q0, int P1, int Q1, int P2, int Q2, int P3, int Q3>
+__device__ __forceinline__ void round_step(Mat& A, float (&w)[8], float nul, float tol2, bool frozen, float& mxg2,
+                                           float& mxs2, int src_lane) {
+  float gr[4], gi[4];
+  gamma<P0, Q0>(A, gr[0], gi[0]);
+  gamma<P1, Q1>(A, gr[1], gi[1]);
+  gamma<P2, Q2>(A, gr[2], gi[2]);
+  if (NP == 4) gamma<P3, Q3>(A, gr[3], gi[3]);
+  Rot r[4];
+  r[0] = rot_params(w[P0], w[Q0], gr[0], gi[0], nul, tol2, frozen, mxg2, mxs2);
+  r[1] = rot_params(w[P1], w[Q1], gr[1], gi[1], nul, tol2, frozen, mxg2, mxs2);
+  r[2] = rot_params(w[P2], w[Q2], gr[2], gi[2], nul, tol2, frozen, mxg2, mxs2);
+  if (NP == 4) r[3] = rot_params(w[P3], w[Q3], gr[3], gi[3], nul, tol2, frozen, mxg2, mxs2);
+#pragma unroll
+  for (int k = 0; k < NP; ++k) {
+    r[k].c = __shfl_sync(0xffffffffu, r[k].c, src_lane);
+    r[k].s = __shfl_sync(0xffffffffu, r[k].s, src_lane);
+    r[k].phx = __shfl_sync(0xffffffffu, r[k].phx, src_lane);
+    r[k].phy = __shfl_sync(0xffffffffu, r[k].phy, src_lane);
   }
-  rot_cols<P, Q>(A, r);
-  const float al = w[P], be = w[Q];
-  w[Q] = al - r.dw;
-  w[P] = be + r.dw;
+  rot_cols<P0, Q0>(A, r[0]);
+  rot_cols<P1, Q1>(A, r[1]);
+  rot_cols<P2, Q2>(A, r[2]);
+  if (NP == 4) rot_cols<P3, Q3>(A, r[3]);
+  float t;
+  t = w[P0]; w[P0] = w[Q0] + r[0].dw; w[Q0] = t - r[0].dw;
+  t = w[P1]; w[P1] = w[Q1] + r[1].dw; w[Q1] = t - r[1].dw;
+  t = w[P2]; w[P2] = w[Q2] + r[2].dw; w[Q2] = t - r[2].dw;
+  if (NP == 4) { t = w[P3]; w[P3] = w[Q3] + r[3].dw; w[Q3] = t - r[3].dw; }
 }
 
 __device__ __forceinline__ void col_norms(const Mat& A, float (&w)[8]) {
@@ -164,11 +181,10 @@ __device__ __forceinline__ void col_norms(const Mat& A, float (&w)[8]) {
 // One-sided Jacobi on the columns of A, odd-even (transposition) ordering with column exchange as in
 // bqa_fast_canon8.cu: a sweep is 4 x [pairs (0,1) (2,3) (4,5) (6,7) | pairs (1,2) (3,4) (5,6)] by position; after a sweep
 // the column order is reversed, an odd number of sweeps is undone at the end.  On exit the columns are orthogonal and
-// w[j] is the squared norm of column j.  PAIRED: lanes 2i (leader) and 2i + 1 (follower, see pair_step).
-template <bool PAIRED>
-__device__ __forceinline__ void jacobi8(Mat& A, float (&w)[8], int& sweeps) {
+// w[j] is the squared norm of column j.  paired: lanes 2i (leader) and 2i + 1 (follower, see pair_step).
+__device__ __forceinline__ void jacobi8(Mat& A, float (&w)[8], int& sweeps, bool paired) {
   const int lane = threadIdx.x & 31;
-  const int src_lane = lane & ~1;
+  const int src_lane = paired ? (lane & ~1) : lane;
   const float eps = 1.1920929e-07f;
   const float tol = eps * 2.f * 2.8284271f;                 // eps * 2 * sqrt(n), like the generic kernel
   const float tol2 = tol * tol;
@@ -182,20 +198,14 @@ __device__ __forceinline__ void jacobi8(Mat& A, float (&w)[8], int& sweeps) {
     float mxg2 = 0.f, mxs2 = 0.f;
 #pragma unroll 1
     for (int rr = 0; rr < 4; ++rr) {
-      pair_step<PAIRED, 0, 1>(A, w, nul, tol2, frozen, mxg2, mxs2, src_lane);
-      pair_step<PAIRED, 2, 3>(A, w, nul, tol2, frozen, mxg2, mxs2, src_lane);
-      pair_step<PAIRED, 4, 5>(A, w, nul, tol2, frozen, mxg2, mxs2, src_lane);
-      pair_step<PAIRED, 6, 7>(A, w, nul, tol2, frozen, mxg2, mxs2, src_lane);
-      pair_step<PAIRED, 1, 2>(A, w, nul, tol2, frozen, mxg2, mxs2, src_lane);
-      pair_step<PAIRED, 3, 4>(A, w, nul, tol2, frozen, mxg2, mxs2, src_lane);
-      pair_step<PAIRED, 5, 6>(A, w, nul, tol2, frozen, mxg2, mxs2, src_lane);
+      round_step<4, 0, 1, 2, 3, 4, 5, 6, 7>(A, w, nul, tol2, frozen, mxg2, mxs2, src_lane);
+      round_step<3, 1, 2, 3, 4, 5, 6, 0, 0>(A, w, nul, tol2, frozen, mxg2, mxs2, src_lane);
     }
     col_norms(A, w);                                        // exact norms once per sweep
     ++done;
     // LAPACK xGESVJ's quadratic-convergence test: the next sweep's rotations would be below the tolerance
-    bool fin = frozen || 64.f * mxg2 * mxs2 < tol2;
-    if (PAIRED) fin = __shfl_sync(0xffffffffu, fin ? 1 : 0, src_lane) != 0;
-    frozen = fin;
+    const bool fin = frozen || 64.f * mxg2 * mxs2 < tol2;
+    frozen = __shfl_sync(0xffffffffu, fin ? 1 : 0, src_lane) != 0;
     if (!__any_sync(0xffffffffu, !frozen)) break;
   }
   sweeps += done;
@@ -227,14 +237,10 @@ __device__ __forceinline__ void ranks_desc(const float (&v)[8], int (&rank)[8]) 
 }
 
 // ---- phase 1: eigendecomposition of one Hermitian PSD message through its Cholesky factor --------------------------
-// in : the 8 x 8 message in `src` (row-major, 64-byte rows)
-// out: dst[row][c] = (G J)[row][col of rank c], columns sorted by eigenvalue (descending), columns with eigenvalue
-//      <= pinv_eps (or below the pinv_raw cut) zeroed: dst^H is lu, dst diag(1 / |column|^2) is ul of
-//      decompose_iden_using_msgs (backends.py:483-490)
-__device__ __forceinline__ void eig_phase(const unsigned char* src, unsigned char* pad, unsigned char* dst, float pinv_eps,
-                                          int& sweeps) {
-  // --- diagonal pre-sort: rows / columns are visited in the order of decreasing diagonal (a static stand-in for
-  // diagonal pivoting; perm[pos] = original index, kept in the spare bytes of the owner's input slot)
+// eig_load: the 8 x 8 message in `src` (row-major, 64-byte rows) -> columns of its Cholesky factor G (m = G G^H) in A.
+// Rows / columns are visited in the order of decreasing diagonal (a static stand-in for diagonal pivoting); the
+// permutation perm[pos] = original index is kept in the spare bytes of the owner's input slot.
+__device__ __forceinline__ void eig_load(const unsigned char* src, unsigned char* pad, Mat& A) {
   float d[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) d[i] = *reinterpret_cast<const float*>(src + i * 64 + i * 8);
@@ -248,7 +254,7 @@ __device__ __forceinline__ void eig_phase(const unsigned char* src, unsigned cha
   int roff[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) roff[i] = (int)(((i < 4 ? pw.x : pw.y) >> (8 * (i & 3))) & 0xffu);
-  // --- lower triangle of the permuted matrix and its Cholesky factor, in place (right-looking, fully unrolled)
+  // lower triangle of the permuted matrix and its Cholesky factor, in place (right-looking, fully unrolled)
   float2 G[8][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -274,7 +280,6 @@ __device__ __forceinline__ void eig_phase(const unsigned char* src, unsigned cha
       }
     }
   }
-  Mat A;
 #pragma unroll
   for (int j = 0; j < 8; ++j)
 #pragma unroll
@@ -283,9 +288,14 @@ __device__ __forceinline__ void eig_phase(const unsigned char* src, unsigned cha
       A.X[j][k] = x2::pk(i0 >= j ? G[i0][j].x : 0.f, i1 >= j ? G[i1][j].x : 0.f);
       A.Y[j][k] = x2::pk(i0 >= j ? G[i0][j].y : 0.f, i1 >= j ? G[i1][j].y : 0.f);
     }
-  float w[8];
-  jacobi8<false>(A, w, sweeps);
-  // --- publish: rows back in the original order, columns by descending eigenvalue w = sigma^2, masked
+}
+
+// eig_publish: after the Jacobi sweeps the columns of A are Q diag(sigma), w = sigma^2 = the eigenvalues.
+// dst[row][c] = A[row][column of rank c]: rows back in the original order, columns by descending eigenvalue, columns
+// with eigenvalue <= pinv_eps (or below the pinv_raw cut) zeroed: dst^H is lu, dst diag(1 / |column|^2) is ul of
+// decompose_iden_using_msgs (backends.py:483-490)
+__device__ __forceinline__ void eig_publish(const Mat& A, const float (&w)[8], const unsigned char* pad, unsigned char* dst,
+                                            float pinv_eps) {
   int rk[8];
   ranks_desc(w, rk);
   const uint2 pw2 = *reinterpret_cast<const uint2*>(pad);
@@ -330,7 +340,7 @@ __device__ __forceinline__ void inv_col_norms(const unsigned char* m, float (&in
 
 __global__ void __launch_bounds__(kWarps * 32, 1) k_canon8v2(long long L, const float2* __restrict__ ext,
                                                              float2* __restrict__ canon, float* __restrict__ lmbds,
-                                                             float* __restrict__ colmax, float pinv_eps, int ncols) {
+                                                             float* __restrict__ colmax, float pinv_eps, int ncols, int nphases) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int pair = lane >> 1;
@@ -368,63 +378,70 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_canon8v2(long long L, const 
     e = live ? e : L - 1;
     cp_async_wait_all();
     __syncwarp();
-    // ---- phase 1: lane 2i decomposes m_f (slot B -> F), lane 2i + 1 decomposes m_b (slot Q -> B)
-    // (the follower publishes into B, which the leader reads its input from: eig_phase loads the whole input into
-    // registers and passes a __syncwarp before anything is stored)
-    eig_phase(leader ? Bm : Qm, (leader ? Bm : Qm) + kPad, leader ? F : Bm, pinv_eps, n_sweeps);
-    n_jac += 1;
-    __syncwarp();
-    // ---- ker = A_f^H conj(A_b) on the leader; the follower loads the stacked block conj(ul_b) = conj(A_b) / |col|^2
+    // Two Jacobi runs per iteration through ONE copy of the sweep code (a rolled loop over the phases):
+    //   phase 0: lane 2i decomposes m_f (slot B -> F), lane 2i + 1 decomposes m_b (slot Q -> B)
+    //   phase 1: lane 2i holds ker = A_f^H conj(A_b), lane 2i + 1 the stacked block conj(ul_b) = conj(A_b) / |col|^2
     Mat A;
-    if (leader) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { A.X[j][k] = x2::pk(0.f, 0.f); A.Y[j][k] = x2::pk(0.f, 0.f); }
-#pragma unroll 2
-      for (int r = 0; r < 8; ++r) {
-        float2 f[8], b[8];
-        lds_row(f, F + r * 64);
-        lds_row(b, Bm + r * 64);
-        p2 FX[4], FY[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { FX[k] = x2::pk(f[2 * k].x, f[2 * k + 1].x); FY[k] = x2::pk(f[2 * k].y, f[2 * k + 1].y); }
+    float w[8];
+#pragma unroll 1
+    for (int phase = 0; phase < nphases; ++phase) {
+      if (phase == 0) {
+        // (the follower publishes into B, which the leader reads its input from: eig_load holds the whole input in
+        // registers and passes a __syncwarp before anything is stored)
+        eig_load(leader ? Bm : Qm, (leader ? Bm : Qm) + kPad, A);
+      } else if (leader) {
 #pragma unroll
         for (int j = 0; j < 8; ++j)
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {                      // ker[i][j] = conj(sum_r A_f[r][i] A_b[r][j])
-            A.X[j][k] = x2::fma2s(b[j].x, FX[k], A.X[j][k]);
-            A.X[j][k] = x2::fnma2s(b[j].y, FY[k], A.X[j][k]);
-            A.Y[j][k] = x2::fnma2s(b[j].y, FX[k], A.Y[j][k]);
-            A.Y[j][k] = x2::fnma2s(b[j].x, FY[k], A.Y[j][k]);
+          for (int k = 0; k < 4; ++k) { A.X[j][k] = x2::pk(0.f, 0.f); A.Y[j][k] = x2::pk(0.f, 0.f); }
+#pragma unroll 2
+        for (int r = 0; r < 8; ++r) {
+          float2 f[8], b[8];
+          lds_row(f, F + r * 64);
+          lds_row(b, Bm + r * 64);
+          p2 FX[4], FY[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { FX[k] = x2::pk(f[2 * k].x, f[2 * k + 1].x); FY[k] = x2::pk(f[2 * k].y, f[2 * k + 1].y); }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {                    // ker[i][j] = conj(sum_r A_f[r][i] A_b[r][j])
+              A.X[j][k] = x2::fma2s(b[j].x, FX[k], A.X[j][k]);
+              A.X[j][k] = x2::fnma2s(b[j].y, FY[k], A.X[j][k]);
+              A.Y[j][k] = x2::fnma2s(b[j].y, FX[k], A.Y[j][k]);
+              A.Y[j][k] = x2::fnma2s(b[j].x, FY[k], A.Y[j][k]);
+            }
+        }
+      } else {
+        float inv[8];
+        inv_col_norms(Bm, inv);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float2 r0[8], r1[8];
+          lds_row(r0, Bm + (2 * k) * 64);
+          lds_row(r1, Bm + (2 * k + 1) * 64);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            A.X[j][k] = x2::pk(r0[j].x * inv[j], r1[j].x * inv[j]);
+            A.Y[j][k] = x2::pk(-r0[j].y * inv[j], -r1[j].y * inv[j]);
           }
-      }
-    } else {
-      float inv[8];
-      inv_col_norms(Bm, inv);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float2 r0[8], r1[8];
-        lds_row(r0, Bm + (2 * k) * 64);
-        lds_row(r1, Bm + (2 * k + 1) * 64);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          A.X[j][k] = x2::pk(r0[j].x * inv[j], r1[j].x * inv[j]);
-          A.Y[j][k] = x2::pk(-r0[j].y * inv[j], -r1[j].y * inv[j]);
         }
       }
-    }
-    __syncwarp();
-    // slots B and Q are free: the next group's inputs stream in behind the SVD phase
-    if (g + nwarps < groups) prefetch(g + nwarps);
-    // ---- phase 2: one-sided Jacobi on [ker ; conj(ul_b)]
-    float w[8];
-    {
+      if (phase == 1) {
+        __syncwarp();
+        // slots B and Q are free: the next group's inputs stream in behind the SVD phase
+        if (g + nwarps < groups) prefetch(g + nwarps);
+      }
       const int before = n_sweeps;
-      jacobi8<true>(A, w, n_sweeps);
-      n_ker += n_sweeps - before;
+      jacobi8(A, w, n_sweeps, phase == 1);
+      n_jac += 1;
+      if (phase == 0) {
+        eig_publish(A, w, (leader ? Bm : Qm) + kPad, leader ? F : Bm, pinv_eps);
+        __syncwarp();
+      } else {
+        n_ker += n_sweeps - before;
+      }
     }
-    n_jac += 1;
     // ---- epilogue.  Leader: w = S^2 per column
     int rk[8];
     ranks_desc(w, rk);
@@ -560,7 +577,7 @@ int launch_fast_canon8v2(long long L, const void* ext, void* canon, void* lmbds,
   long long grid = (groups + kWarps - 1) / kWarps;
   if (grid > sms) grid = sms;
   k_canon8v2<<<(int)grid, kWarps * 32, kSmem, st>>>(L, (const float2*)ext, (float2*)canon, (float*)lmbds, (float*)colmax,
-                                                   (float)pinv_eps, ncols);
+                                                   (float)pinv_eps, ncols, 2);
   return after_launch("canonicalize(n=8, v2)");
 }
 

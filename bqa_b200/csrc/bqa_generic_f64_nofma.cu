@@ -5,6 +5,8 @@
 // the arithmetic.  Separately rounded multiply and add (what numpy/LAPACK on the host do) keeps them, fused
 // multiply-add does not -- so this translation unit must not contract.
 #include "bqa_generic.cuh"
+#include "bqa_multiclass.cuh"
 namespace bqa {
 BQA_INSTANTIATE(double)
+BQA_INSTANTIATE_MULTICLASS(double)
 }

@@ -9,6 +9,8 @@
 #define BQA_GENERIC_MAX_WARPS (148 * 32)
 #define BQA_MAX_PEERS 8
 
+struct bqa_b200_class;          // include/bqa_b200.h
+
 namespace bqa {
 
 int set_error(const char* fmt, ...);
@@ -48,6 +50,13 @@ int launch_project(int d, int D, void* T, long long pos, int bit, cudaStream_t s
 template <typename R>
 int launch_threshold(int d, int D, long long B, void* T, const int32_t* node_ids, const void* bloch,
                      int32_t* outcomes, double thr, int32_t* n_proj, cudaStream_t st);
+
+// all degree classes in one launch (bqa_multiclass.cuh); kind: 0 extended messages, 1 apply update, 2 whole BP run
+template <typename R>
+int launch_multiclass(int kind, int n_classes, const bqa_b200_class* cls, int D, int Dn, void* msgs0, void* msgs1,
+                      int parity, const void* canon, const void* lmbds, double ztime, double xtime, double damping,
+                      double bp_eps, int max_iters, void* resid, int32_t* status, void* ws, size_t ws_bytes,
+                      cudaStream_t st);
 
 // specialised kernels (bqa_fast_d3D4.cu): degree 3, D = 4, complex64
 bool fast_d3D4_available(int prec, int degree, int D, long long B);

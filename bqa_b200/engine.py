@@ -16,6 +16,7 @@ sweep kernels test the previous sweep's residual on the device and turn into no-
 """
 from __future__ import annotations
 
+import ctypes as C
 import logging
 import os
 from dataclasses import dataclass
@@ -120,6 +121,9 @@ class Engine:
         self._bp_chunk = 4
         self._single_launch_ok = self.cuda and os.environ.get("BQA_B200_SINGLE_LAUNCH_BP", "1") != "0"
         self._no_bp_run = {}         # bond dimension -> True once bqa_b200_bp_run reported "no kernel for this shape"
+        # all degree classes in one launch (bqa_multiclass.cuh): single GPU, CUDA library only
+        self._multiclass = (self.cuda and hasattr(self.lib, "bp_run_classes")
+                            and os.environ.get("BQA_B200_MULTICLASS", "1") != "0")
 
         self.classes: list[_DegreeClass] = []
         self._node_class = np.zeros(self.N, np.int64)
@@ -330,6 +334,27 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     # BP  (state.py:97-124)
     # ------------------------------------------------------------------------------------------
+    def _class_table(self, out_side: bool = False):
+        """(ctypes array of bqa_b200_class, n): the degree classes as the *_classes entry points take them; with
+        ``out_side`` the tensors' other ping-pong buffer is the output (apply update)"""
+        rows = (_lib.ClassDesc * len(self.classes))()
+        for r, c in zip(rows, self.classes):
+            r.degree, r.B = c.degree, c.B
+            r.T_in = c.T[c.cur].data_ptr()
+            r.T_out = c.T[1 - c.cur].data_ptr() if out_side else None
+            r.in_pos, r.out_pos, r.lmbd_pos = c.in_pos.data_ptr(), c.out_pos.data_ptr(), c.lmbd_pos.data_ptr()
+            r.node_ampls, r.edge_ampls = c.node_ampls.data_ptr(), c.edge_ampls.data_ptr()
+        return rows, len(self.classes)
+
+    def _use_multiclass(self) -> bool:
+        """Several degree classes (or a shape without a specialised kernel) on one GPU: table-driven launches."""
+        return self._multiclass and self._peer_targets("msgs") is None and not self._fast_single_class()
+
+    def _fast_single_class(self) -> bool:
+        active = [c for c in self.classes if c.B > 0]
+        return (len(active) == 1 and self.precision == "single" and active[0].degree == 3 and self.D == 4
+                and active[0].B >= 4 and self.Dmax >= 4)
+
     def _enqueue_sweep(self, it: int, write_undamped: bool) -> None:
         D = self.D
         cur = self._msgs[(self._msgs_cur + it) % 2]
@@ -371,7 +396,15 @@ class Engine:
         """The whole BP run in one cooperative launch (bqa_b200_bp_run) when every BP-active node sits in one degree
         class with a specialised kernel; returns (converged, sweeps, resid) or None."""
         active = [c for c in self.classes if c.degree > 0 and c.B > 0]
-        if len(active) != 1 or not self._single_launch_ok or self._no_bp_run.get(self.D):
+        if not self._single_launch_ok:
+            return None
+        if active and self._use_multiclass():
+            rows, n = self._class_table()
+            self.lib.bp_run_classes(self.prec, n, C.byref(rows), self.D, self._msgs[0].data_ptr(), self._msgs[1].data_ptr(),
+                                    self._msgs_cur, self.damping, self.bp_eps, self.max_iters, self._resid.data_ptr(),
+                                    self._status.data_ptr(), self._ws.data_ptr(), self._ws.numel(), self._stream())
+            return self._read_bp_run()
+        if len(active) != 1 or self._no_bp_run.get(self.D):
             return None
         c = active[0]
         peers = self._bp_run_peers()
@@ -385,6 +418,10 @@ class Engine:
         if not ok:
             self._no_bp_run[self.D] = True
             return None
+        return self._read_bp_run()
+
+    def _read_bp_run(self):
+        """(converged, sweeps, residuals) of a single-launch BP run: the step's one read of the control block"""
         ctrl = self._read_ctrl()
         resid = ctrl[: self._ctrl_rbytes].view(self.np_rdtype).reshape(-1, 2)
         status = ctrl[self._ctrl_rbytes: self._ctrl_rbytes + 16].view(np.int32)
@@ -463,8 +500,13 @@ class Engine:
         self._ensure_edge_buffers(D)
         cur = self.msgs_buffer
         peers = self._peer_targets("ext")
+        multi = self._use_multiclass()
+        if multi:
+            rows, n = self._class_table()
+            self.lib.ext_msgs_classes(self.prec, n, C.byref(rows), D, cur.data_ptr(), self._ext.data_ptr(), float(ztime),
+                                      self._ws.data_ptr(), self._ws.numel(), st)
         for c in self.classes:
-            if c.degree == 0:
+            if c.degree == 0 or multi:
                 continue
             args = (self.prec, c.degree, D, c.B, c.T[c.cur].data_ptr(), cur.data_ptr(),
                     self._ext.data_ptr(), c.in_pos.data_ptr(), c.out_pos.data_ptr(),
@@ -515,7 +557,16 @@ class Engine:
         """Truncated simple update D -> Dn of every class + Rz/Rx layers + symmetric gauge, then BP to convergence."""
         st = self._stream()
         msgs_out = self._msgs[0]
+        multi = self._use_multiclass()
+        if multi:
+            rows, n = self._class_table(out_side=True)
+            self.lib.apply_update_classes(self.prec, n, C.byref(rows), D, Dn, self._canon.data_ptr(), self._lmbds.data_ptr(),
+                                          msgs_out.data_ptr(), float(ztime), float(xtime), self._ws.data_ptr(),
+                                          self._ws.numel(), st)
         for c in self.classes:
+            if multi:
+                c.cur = 1 - c.cur
+                continue
             self.lib.apply_update(self.prec, c.degree, D, Dn, c.B, c.T[c.cur].data_ptr(), c.T[1 - c.cur].data_ptr(),
                                   self._canon.data_ptr(), self._lmbds.data_ptr(), msgs_out.data_ptr(),
                                   c.in_pos.data_ptr(), c.out_pos.data_ptr(), c.lmbd_pos.data_ptr(),

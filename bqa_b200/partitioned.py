@@ -327,6 +327,7 @@ class PartitionedEngine(Engine):
         self._seq = 0
         super().__init__(local, precision=precision, device=device, _testing_lib=_testing_lib)
         self.rng = np.random.default_rng(int(context.seed))              # same stream on every rank
+        self._multiclass = False          # the table-driven launches have no halo stores / no exchange between sweeps
         dev = self.dev
         self._peers = sorted(plan.send_slots)
         self._send_idx = {q: torch.from_numpy(plan.send_slots[q]).to(dev) for q in self._peers}

@@ -165,6 +165,33 @@ int bqa_b200_threshold_project(int prec, int degree, int D, long long B, void* T
                                const void* bloch, int32_t* outcomes, double thr, int32_t* n_projected,
                                void* stream);
 
+/* ---- all degree classes of a graph in one launch (bqa_multiclass.cuh) -----------------------------------------
+ * The reference loops over the degree classes on the host (state.py:106-112, :127-139, :238-246).  These entry points
+ * take the classes as a table (host array, copied into the kernel parameters): a step on a graph with several degree
+ * classes is ext_msgs_classes + canonicalize + apply_update_classes + bp_run_classes = 4 launches, and the whole BP run
+ * of _run_bp (state.py:97-124) is one cooperative launch with the convergence test on the device (status[0] =
+ * converged, status[1] = sweeps executed, status[2] = barrier counter -- zeroed by the caller --, status[3] = abort).
+ * Results equal the per-class entry points bit for bit.  Single GPU only (no halo stores). */
+typedef struct bqa_b200_class {
+  int degree;
+  long long B;
+  const void* T_in;            /* (B, 2, D, ..., D) */
+  void* T_out;                 /* apply_update_classes only */
+  const int32_t* in_pos;       /* (degree, B) */
+  const int32_t* out_pos;
+  const int32_t* lmbd_pos;     /* apply_update_classes only */
+  const void* node_ampls;      /* (B) reals, apply_update_classes only */
+  const void* edge_ampls;      /* (degree, B) reals */
+} bqa_b200_class;
+int bqa_b200_ext_msgs_classes(int prec, int n_classes, const bqa_b200_class* classes_host, int D, const void* msgs_cur,
+                              void* ext, double ztime, void* workspace, size_t workspace_bytes, void* stream);
+int bqa_b200_apply_update_classes(int prec, int n_classes, const bqa_b200_class* classes_host, int D, int D_new,
+                                  const void* canon, const void* lmbds, void* msgs_out, double ztime, double xtime,
+                                  void* workspace, size_t workspace_bytes, void* stream);
+int bqa_b200_bp_run_classes(int prec, int n_classes, const bqa_b200_class* classes_host, int D, void* msgs0, void* msgs1,
+                            int parity, double damping, double bp_eps, int max_iters, void* resid, int32_t* status,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- raw operations of the backend interface on device arrays (bqa_tensor_ops.cu) ----------------------------
  * The reference's plugin boundary is the ABC bqa.backends.Tensor (src/bqa/backends.py:28-252): 36 abstract raw
  * operations from which it builds every composite.  bqa_b200.tensor_backend.B200Backend implements them with the

@@ -50,7 +50,7 @@ SIGNATURES = {
 }
 EXPORTS = list(SIGNATURES) + ["bqa_b200_last_error", "bqa_b200_version", "bqa_b200_launch_count",
                               "bqa_b200_workspace_bytes", "bqa_b200_set_kernel_mode", "bqa_b200_canon_stats",
-                              "bqa_b200_t_svd_scratch_bytes"]
+                              "bqa_b200_t_svd_scratch_bytes", "bqa_b200_canon_stats_detail"]
 
 
 class ClassDesc(C.Structure):
@@ -115,6 +115,11 @@ class Library:
 
     def svd_scratch_bytes(self, prec: int, n: int) -> int:
         return int(self._dll.bqa_b200_t_svd_scratch_bytes(prec, n))
+
+    def canon_stats_detail(self) -> list[int]:
+        out = (C.c_ulonglong * 7)()
+        self._dll.bqa_b200_canon_stats_detail(out)
+        return [int(v) for v in out]
 
     def workspace_bytes(self, prec: int, degree: int, D: int, D_new: int) -> int:
         return int(self._dll.bqa_b200_workspace_bytes(prec, degree, D, D_new))

@@ -53,6 +53,10 @@ int bqa_b200_canon_stats(unsigned long long* out3) {
   if (g_kernel_mode.load() == 2) canon8_stats(out3); else canon8v2_stats(out3);
   return 0;
 }
+int bqa_b200_canon_stats_detail(unsigned long long* out7) {
+  canon8v2_stats_detail(out7);
+  return 0;
+}
 int bqa_b200_set_kernel_mode(int mode) {
   if (mode < 0 || mode > 2)
     return set_error("kernel mode must be 0 (auto), 1 (generic only) or 2 (auto with the first-design canonicalizer), got %d", mode);

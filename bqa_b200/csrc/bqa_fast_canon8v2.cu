@@ -50,7 +50,8 @@ static_assert(kSmem <= 227 * 1024, "shared memory budget");
 
 // statistics: [0] warp-level Jacobi runs (32 or 16 matrices at a time), [1] sweeps summed over them (a warp sweeps until
 // its slowest matrix has converged), [2] the part of [1] spent on the SVD of ker
-__device__ unsigned long long g_stats[3];
+// [3] / [4]: sweeps summed over the single matrices until each one froze, eigen phase / SVD phase ([5] / [6]: matrices)
+__device__ unsigned long long g_stats[7];
 
 struct Mat {                               // column j, row pair k = (rows 2k, 2k + 1): X = real parts, Y = imaginary parts
   p2 X[8][4], Y[8][4];
@@ -182,7 +183,7 @@ __device__ __forceinline__ void col_norms(const Mat& A, float (&w)[8]) {
 // bqa_fast_canon8.cu: a sweep is 4 x [pairs (0,1) (2,3) (4,5) (6,7) | pairs (1,2) (3,4) (5,6)] by position; after a sweep
 // the column order is reversed, an odd number of sweeps is undone at the end.  On exit the columns are orthogonal and
 // w[j] is the squared norm of column j.  paired: lanes 2i (leader) and 2i + 1 (follower, see pair_step).
-__device__ __forceinline__ void jacobi8(Mat& A, float (&w)[8], int& sweeps, bool paired) {
+__device__ __forceinline__ void jacobi8(Mat& A, float (&w)[8], int& sweeps, bool paired, int& own_sweeps) {
   const int lane = threadIdx.x & 31;
   const int src_lane = paired ? (lane & ~1) : lane;
   const float eps = 1.1920929e-07f;
@@ -203,6 +204,7 @@ __device__ __forceinline__ void jacobi8(Mat& A, float (&w)[8], int& sweeps, bool
     }
     col_norms(A, w);                                        // exact norms once per sweep
     ++done;
+    own_sweeps += frozen ? 0 : 1;
     // LAPACK xGESVJ's quadratic-convergence test: the next sweep's rotations would be below the tolerance
     const bool fin = frozen || 64.f * mxg2 * mxs2 < tol2;
     frozen = __shfl_sync(0xffffffffu, fin ? 1 : 0, src_lane) != 0;
@@ -355,7 +357,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_canon8v2(long long L, const 
   float cm[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) cm[j] = 0.f;
-  int n_sweeps = 0, n_ker = 0, n_jac = 0;
+  int n_sweeps = 0, n_ker = 0, n_jac = 0, own_eig = 0, own_ker = 0, n_iter = 0;
 
   // copies of one group's 32 input matrices: edge t of the group by one warp-wide 512-byte copy per matrix
   auto prefetch = [&](long long g) {
@@ -433,7 +435,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_canon8v2(long long L, const 
         if (g + nwarps < groups) prefetch(g + nwarps);
       }
       const int before = n_sweeps;
-      jacobi8(A, w, n_sweeps, phase == 1);
+      jacobi8(A, w, n_sweeps, phase == 1, phase == 0 ? own_eig : own_ker);
       n_jac += 1;
       if (phase == 0) {
         eig_publish(A, w, (leader ? Bm : Qm) + kPad, leader ? F : Bm, pinv_eps);
@@ -530,6 +532,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_canon8v2(long long L, const 
         }
       }
     }
+    n_iter += live ? 1 : 0;
     __syncwarp();                                           // F is rewritten by the next iteration's phase 1
   }
   // column-wise max of lambda over all edges (truncate_lmbds, backends.py:297-299); only leaders hold values
@@ -544,6 +547,18 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_canon8v2(long long L, const 
     for (int c = 1; c < 8; ++c) v = lane == c ? cm[c] : v;
     atomicMax(reinterpret_cast<unsigned int*>(colmax + lane), __float_as_uint(v));
   }
+  {
+    unsigned long long se = (unsigned long long)own_eig * (n_iter ? 1 : 0), sk = leader ? (unsigned long long)own_ker : 0ull;
+    unsigned long long ne = (unsigned long long)n_iter, nk = leader ? (unsigned long long)n_iter : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      se += __shfl_xor_sync(0xffffffffu, se, o); sk += __shfl_xor_sync(0xffffffffu, sk, o);
+      ne += __shfl_xor_sync(0xffffffffu, ne, o); nk += __shfl_xor_sync(0xffffffffu, nk, o);
+    }
+    if (lane == 0) {
+      atomicAdd(&g_stats[3], se); atomicAdd(&g_stats[4], sk); atomicAdd(&g_stats[5], ne); atomicAdd(&g_stats[6], nk);
+    }
+  }
   if (lane == 0) {
     atomicAdd(&g_stats[0], (unsigned long long)n_jac);
     atomicAdd(&g_stats[1], (unsigned long long)n_sweeps);
@@ -555,6 +570,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_canon8v2(long long L, const 
 
 void canon8v2_stats(unsigned long long* out3) {
   cudaMemcpyFromSymbol(out3, canon8v2::g_stats, sizeof(unsigned long long) * 3);
+}
+void canon8v2_stats_detail(unsigned long long* out7) {
+  cudaMemcpyFromSymbol(out7, canon8v2::g_stats, sizeof(unsigned long long) * 7);
 }
 
 int launch_fast_canon8v2(long long L, const void* ext, void* canon, void* lmbds, void* colmax, double pinv_eps,

@@ -95,5 +95,6 @@ void canon8_stats(unsigned long long* out3);
 int launch_fast_canon8v2(long long L, const void* ext, void* canon, void* lmbds, void* colmax, double pinv_eps,
                          int ncols, cudaStream_t st);
 void canon8v2_stats(unsigned long long* out3);
+void canon8v2_stats_detail(unsigned long long* out7);
 
 }  // namespace bqa

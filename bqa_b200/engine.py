@@ -118,6 +118,7 @@ class Engine:
         self.rng = np.random.default_rng(int(ctx.seed))
         self.D = 1
         self.stats = {"bp_sweeps": [], "bp_dist": [], "bond_dims": [], "trunc_err": []}
+        self.host_reads = 0          # blocking device -> host reads so far (control block, column maxima, results)
         self._bp_chunk = 4
         self._single_launch_ok = self.cuda and os.environ.get("BQA_B200_SINGLE_LAUNCH_BP", "1") != "0"
         self._no_bp_run = {}         # bond dimension -> True once bqa_b200_bp_run reported "no kernel for this shape"
@@ -180,8 +181,10 @@ class Engine:
         self.speculate = os.environ.get("BQA_B200_SPECULATE", "1") != "0"
         self._bloch = torch.zeros(self.N * 4, dtype=self.rdtype, device=self.dev)
         self._ws = torch.zeros(16, dtype=torch.uint8, device=self.dev)
-        self._argmax_i = torch.zeros(2, dtype=torch.int32, device=self.dev)
-        self._argmax_p = torch.zeros(1, dtype=self.rdtype, device=self.dev)
+        # candidate of a sampling pass: (node, unmeasured count) int32 x2 | p0 real -- one buffer, one host read per pass
+        self._argmax = torch.zeros(16, dtype=torch.uint8, device=self.dev)
+        self._argmax_i = self._argmax[:8].view(torch.int32)
+        self._argmax_p = self._argmax[8:8 + (4 if self.precision == "single" else 8)].view(self.rdtype)
         self._nproj = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self._init_state()
 
@@ -192,6 +195,7 @@ class Engine:
         return torch.cuda.current_stream(self.dev).cuda_stream if self.cuda else 0
 
     def _to_host(self, t: torch.Tensor) -> np.ndarray:
+        self.host_reads += 1
         return t.cpu().numpy()          # synchronises the current stream
 
     def _read_ctrl(self) -> np.ndarray:
@@ -199,6 +203,7 @@ class Engine:
         if self._ctrl_host is None:
             ctrl = self._to_host(self._ctrl)
         else:
+            self.host_reads += 1
             self._ctrl_host.copy_(self._ctrl, non_blocking=True)
             torch.cuda.current_stream(self.dev).synchronize()
             ctrl = self._ctrl_host.numpy().copy()
@@ -347,13 +352,15 @@ class Engine:
         return rows, len(self.classes)
 
     def _use_multiclass(self) -> bool:
-        """Several degree classes (or a shape without a specialised kernel) on one GPU: table-driven launches."""
-        return self._multiclass and self._peer_targets("msgs") is None and not self._fast_single_class()
-
-    def _fast_single_class(self) -> bool:
-        active = [c for c in self.classes if c.B > 0]
-        return (len(active) == 1 and self.precision == "single" and active[0].degree == 3 and self.D == 4
-                and active[0].B >= 4 and self.Dmax >= 4)
+        """Table-driven launches over all degree classes (one GPU): always for shapes without a specialised kernel;
+        when a class has one (degree 3, D = 4, complex64), only while that class is small enough for the launches
+        saved to outweigh the faster kernel."""
+        if not self._multiclass or self._peer_targets("msgs") is not None:
+            return False
+        fast = [c for c in self.classes if self.precision == "single" and c.degree == 3 and self.D == 4 and c.B >= 4]
+        if not fast:
+            return True
+        return len([c for c in self.classes if c.B > 0]) > 1 and max(c.B for c in fast) <= 8192
 
     def _enqueue_sweep(self, it: int, write_undamped: bool) -> None:
         D = self.D
@@ -627,10 +634,11 @@ class Engine:
             self._compute_bloch()
             self.lib.argmax_unmeasured(self.prec, self.N, self._bloch.data_ptr(), outcomes.data_ptr(),
                                        self._argmax_i.data_ptr(), self._argmax_p.data_ptr(), st)
-            node, left = (int(v) for v in self._to_host(self._argmax_i))
+            cand = self._to_host(self._argmax)
+            node, left = (int(v) for v in cand[:8].view(np.int32))
             if left == 0:
                 break
-            p0 = float(self._to_host(self._argmax_p)[0])
+            p0 = float(cand[8:8 + self._argmax_p.element_size()].view(self.np_rdtype)[0])
             u = self.rng.uniform(0.0, 1.0)                  # one draw per pass, same stream as the reference
             bit = 0 if p0 > u else 1
             log.debug(f"Node {node} the most determined (spin-up probability {p0} and spin-down probability {1 - p0}) and has been measured")

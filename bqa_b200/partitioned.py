@@ -482,8 +482,9 @@ class PartitionedEngine(Engine):
             self._compute_bloch()
             self.lib.argmax_unmeasured(self.prec, self.N, self._bloch.data_ptr(), outcomes.data_ptr(),
                                        self._argmax_i.data_ptr(), self._argmax_p.data_ptr(), st)
-            node, left = (int(v) for v in self._to_host(self._argmax_i))
-            p0 = float(self._to_host(self._argmax_p)[0])
+            mine = self._to_host(self._argmax)
+            node, left = (int(v) for v in mine[:8].view(np.int32))
+            p0 = float(mine[8:8 + self._argmax_p.element_size()].view(self.np_rdtype)[0])
             cand = torch.tensor([abs(2.0 * p0 - 1.0) if left else -1.0, float(owned[node]) if left else -1.0, p0,
                                  float(left)], dtype=torch.float64, device=self.dev)
             allc = [torch.zeros_like(cand) for _ in range(self.world)]

@@ -47,6 +47,10 @@ int bqa_b200_set_kernel_mode(int mode);
  * since load, out3[1] = Jacobi sweeps summed over them, out3[2] = the part of out3[1] spent on the SVD of ker
  * (synchronises the device) */
 int bqa_b200_canon_stats(unsigned long long* out3);
+/* current n = 8 kernel only: out7[0..2] as above, out7[3] / out7[4] = sweeps summed over the single matrices until each
+ * one had converged (eigen phase / SVD phase), out7[5] / out7[6] = matrices: what a warp loses by sweeping until its
+ * slowest matrix is done */
+int bqa_b200_canon_stats_detail(unsigned long long* out7);
 
 /* bytes of device scratch the node kernels need for a degree class (pass the max over classes) */
 size_t bqa_b200_workspace_bytes(int prec, int degree, int D, int D_new);

@@ -42,6 +42,31 @@ def main():
             torch.cuda.synchronize()
             out[f"gpu_{prec}_s"] = time.perf_counter() - t0
             out[f"res_{prec}"] = res
+            # the annealing steps alone: launches and blocking host reads per step
+            from bqa_b200 import _lib
+            from bqa_b200.config import config_to_context
+            from bqa_b200.engine import Engine
+            lib = _lib.load_library()
+            ctx = config_to_context(cfg)
+            layers = [i for i in ctx.instructions if isinstance(i, dict)]
+            for multi in (True, False):
+                eng = Engine(ctx, precision=prec)
+                eng._multiclass = multi
+                l0 = lib.launch_count()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for ins in layers:
+                    eng.run_layer(ins["xtime"], ins["ztime"])
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                tag = f"{prec}_{'one_launch_for_all_classes' if multi else 'per_class_launches'}"
+                out[f"steps_per_s_{tag}"] = len(layers) / dt
+                out[f"launches_per_step_{tag}"] = (lib.launch_count() - l0) / len(layers)
+                out[f"host_reads_per_step_{tag}"] = eng.host_reads / len(layers)
+                t0 = time.perf_counter()
+                if "measure" in cfg["schedule"]["actions"]:
+                    eng.measure()
+                    out[f"measure_s_{tag}"] = time.perf_counter() - t0
         if with_oracle:
             t0 = time.perf_counter()
             want = dict(O.run_qa(cfg))

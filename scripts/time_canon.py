@@ -59,6 +59,7 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         s1 = lib.canon_stats()
+        det = lib.canon_stats_detail() if mode == 0 else None
         ms = e0.elapsed_time(e1) / args.reps
         # every launch on its own: does the duration drift under back-to-back load (clocks)?
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.reps)]
@@ -72,6 +73,8 @@ def main():
         out[f"mode{mode}"] = {"ms": ms, "ms_first": each[0], "ms_min": min(each), "ms_last": each[-1], "edges_per_s": eng.L / (ms * 1e-3),
                               "sweeps_per_warp_run": (s1[1] - s0[1]) / max(s1[0] - s0[0], 1),
                               "ker_share_of_sweeps": (s1[2] - s0[2]) / max(s1[1] - s0[1], 1)}
+        if det:
+            out["mode0"]["mean_sweeps_per_matrix"] = {"eigen": det[3] / max(det[5], 1), "svd": det[4] / max(det[6], 1)}
     lib.set_kernel_mode(0)
     out["lambda_max_abs_diff"] = float(np.abs(res[0][1] - res[2][1]).max())
     out["colmax"] = [res[0][2].tolist(), res[2][2].tolist()]

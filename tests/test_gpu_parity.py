@@ -447,7 +447,7 @@ def test_rr100k_window_vs_reference_golden(golden_dir, lib):
             assert sw.max() == 0
             assert np.abs(lm[::stride] - g["lmbds_sorted_strided"]).max() < 1e-9
             assert np.abs(lm.max(0) - g["lmbds_colmax"]).max() < 1e-9
-            assert e == e_ref
+            assert abs(e - e_ref) <= 1e-12 * abs(e_ref)                         # same spins, another summation order
         del eng
 
 
@@ -566,11 +566,17 @@ def test_multiclass_launches_equal_per_class_launches(lib, name, precision):
         eng._multiclass = multi
         before = lib.launch_count()
         layers = [i for i in ctx.instructions if isinstance(i, dict)]
-        for ins in layers:
-            eng.run_layer(ins["xtime"], ins["ztime"])
-        launches = lib.launch_count() - before
-        bloch = eng.bloch_vectors()
-        outcomes = eng.measure()
+        # (generic kernels on both sides: per-class launches would give a degree-3 class at D = 4 in complex64 to the
+        # specialised kernels, whose arithmetic is ordered differently)
+        lib.set_kernel_mode(1)
+        try:
+            for ins in layers:
+                eng.run_layer(ins["xtime"], ins["ztime"])
+            launches = lib.launch_count() - before
+            bloch = eng.bloch_vectors()
+            outcomes = eng.measure()
+        finally:
+            lib.set_kernel_mode(0)
         out[multi] = (bloch, outcomes, eng.stats["bp_sweeps"], eng.stats["bp_dist"], eng.stats["bond_dims"], launches / len(layers))
     assert np.array_equal(out[True][0], out[False][0])
     assert out[True][1:5] == out[False][1:5]

@@ -50,7 +50,8 @@ SIGNATURES = {
 }
 EXPORTS = list(SIGNATURES) + ["bqa_b200_last_error", "bqa_b200_version", "bqa_b200_launch_count",
                               "bqa_b200_workspace_bytes", "bqa_b200_set_kernel_mode", "bqa_b200_canon_stats",
-                              "bqa_b200_t_svd_scratch_bytes", "bqa_b200_canon_stats_detail"]
+                              "bqa_b200_t_svd_scratch_bytes", "bqa_b200_canon_stats_detail",
+                              "bqa_b200_set_barrier_timeout"]
 
 
 class ClassDesc(C.Structure):
@@ -106,6 +107,11 @@ class Library:
         """0: specialised kernels where they exist (default); 1: generic kernels only; 2: like 0 with the first-design
         n = 8 canonicalizer (side-by-side measurements)."""
         if self._dll.bqa_b200_set_kernel_mode(int(mode)) != 0:
+            raise RuntimeError(self._dll.bqa_b200_last_error().decode())
+
+    def set_barrier_timeout(self, seconds: float) -> None:
+        self._dll.bqa_b200_set_barrier_timeout.argtypes = [_d]
+        if self._dll.bqa_b200_set_barrier_timeout(float(seconds)) != 0:
             raise RuntimeError(self._dll.bqa_b200_last_error().decode())
 
     def canon_stats(self) -> tuple[int, int, int]:

@@ -57,6 +57,15 @@ int bqa_b200_canon_stats_detail(unsigned long long* out7) {
   canon8v2_stats_detail(out7);
   return 0;
 }
+int bqa_b200_set_barrier_timeout(double seconds) {
+  if (!(seconds > 0.0)) return set_error("barrier timeout must be positive, got %g s", seconds);
+  int dev = 0, khz = 0;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev) != cudaSuccess || khz <= 0) khz = 1965000;
+  cudaGetLastError();
+  fast::set_barrier_timeout_cycles((long long)(seconds * 1e3 * (double)khz));
+  return 0;
+}
 int bqa_b200_set_kernel_mode(int mode) {
   if (mode < 0 || mode > 2)
     return set_error("kernel mode must be 0 (auto), 1 (generic only) or 2 (auto with the first-design canonicalizer), got %d", mode);

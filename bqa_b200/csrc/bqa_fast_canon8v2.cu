@@ -45,7 +45,8 @@ constexpr int kMat = 528;                  // 8 rows x 64 bytes + 16: an odd num
 constexpr int kPad = 512;                  // offset of the 16 spare bytes of a matrix slot (row permutation of the owner)
 constexpr int kPair = 3 * kMat;            // per edge: F (A_f sorted, lives to the epilogue) | B (input m_f, then A_b) | Q (input m_b)
 constexpr int kWarpBytes = kEdges * kPair;
-constexpr int kSmem = kWarps * kWarpBytes; // 202 752 bytes
+constexpr int kBars = kWarps * kWarpBytes; // one mbarrier per warp behind the matrix slots
+constexpr int kSmem = kBars + kWarps * 8;  // 202 816 bytes
 static_assert(kSmem <= 227 * 1024, "shared memory budget");
 
 // statistics: [0] warp-level Jacobi runs (32 or 16 matrices at a time), [1] sweeps summed over them (a warp sweeps until
@@ -66,8 +67,25 @@ __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)_
 __device__ __forceinline__ void cp_async16(unsigned dst, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(gmem) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+// ---- TMA bulk copies (cp.async.bulk, SASS: UBLKCP) completed on an mbarrier -------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// generic-proxy accesses of this thread to shared memory are ordered before later async-proxy (TMA) accesses
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 struct Rot {
   float c, s, phx, phy, dw;                // cos, sin, unimodular phase conj(g) / |g|, norm transfer t |g|
@@ -359,17 +377,23 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_canon8v2(long long L, const 
   for (int j = 0; j < 8; ++j) cm[j] = 0.f;
   int n_sweeps = 0, n_ker = 0, n_jac = 0, own_eig = 0, own_ker = 0, n_iter = 0;
 
-  // copies of one group's 32 input matrices: edge t of the group by one warp-wide 512-byte copy per matrix
+  // The 32 input matrices of a group (m_f of its 16 edges, then m_b) arrive by TMA: every lane issues ONE 512-byte bulk
+  // copy (lane t < 16: m_f of edge t -> slot B of pair t; lane t >= 16: m_b of edge t - 16 -> slot Q) and the warp's
+  // mbarrier completes when all 16 KB have landed -- instead of 32 16-byte LDGSTS per lane.
+  const unsigned bar = smem_u32(smem + kBars + wib * 8);
+  if (lane == 0) mbar_init(bar, 1);
+  fence_proxy_async();
+  __syncwarp();
+  unsigned bar_parity = 0;
   auto prefetch = [&](long long g) {
-    const unsigned dst = smem_u32(wbase) + lane * 16;
-#pragma unroll 4
-    for (int t = 0; t < kEdges; ++t) {
-      long long e = g * kEdges + t;
-      e = e < L ? e : L - 1;
-      cp_async16(dst + t * kPair + kMat, gext + (size_t)e * 512 + lane * 16);
-      cp_async16(dst + t * kPair + 2 * kMat, gext + (size_t)(e + L) * 512 + lane * 16);
-    }
-    cp_async_commit();
+    long long e = g * kEdges + (lane & 15);
+    e = e < L ? e : L - 1;
+    const unsigned dst = smem_u32(wbase) + (lane & 15) * kPair + (lane < 16 ? kMat : 2 * kMat);
+    fence_proxy_async();                                    // this lane's earlier loads / stores of the slots come first
+    __syncwarp();
+    if (lane == 0) mbar_expect_tx(bar, 32 * 512);
+    __syncwarp();
+    bulk_g2s(dst, gext + (size_t)(lane < 16 ? e : e + L) * 512, 512, bar);
   };
   long long g = (long long)blockIdx.x * kWarps + wib;
   if (g < groups) prefetch(g);
@@ -378,8 +402,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_canon8v2(long long L, const 
     long long e = g * kEdges + pair;
     const bool live = e < L;
     e = live ? e : L - 1;
-    cp_async_wait_all();
-    __syncwarp();
+    mbar_wait(bar, bar_parity);
+    bar_parity ^= 1;
     // Two Jacobi runs per iteration through ONE copy of the sweep code (a rolled loop over the phases):
     //   phase 0: lane 2i decomposes m_f (slot B -> F), lane 2i + 1 decomposes m_b (slot Q -> B)
     //   phase 1: lane 2i holds ker = A_f^H conj(A_b), lane 2i + 1 the stacked block conj(ul_b) = conj(A_b) / |col|^2

@@ -509,9 +509,9 @@ struct RunArgs {
   unsigned char* peers[2][BQA_MAX_PEERS];
   int parity, max_iters;
   int rank, world;                 // world == 1: single GPU
-  float* peer_resid[BQA_MAX_PEERS];
-  unsigned* peer_flags[BQA_MAX_PEERS];
-  unsigned seq_base;               // cross-GPU barrier sequence numbers seq_base + 1, + 2, ... (one per sweep)
+  uint4* peer_xchg[BQA_MAX_PEERS]; // every rank's handshake lines [2][BQA_MAX_PEERS] (peer mapped): 64 bytes into its flag buffer
+  unsigned seq_base;               // cross-GPU sequence numbers seq_base + 1, + 2, ... (one per sweep)
+  long long timeout_cycles;        // a peer that stays silent this long aborts the run (status[3])
 };
 
 __device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
@@ -524,12 +524,18 @@ __device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_volatile_v4(uint4* p, uint4 v) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_volatile_v4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
 }
 
 // all CTAs of the grid; `counter` only grows (zeroed by the host before the launch); status[3] != 0 aborts everyone
-__device__ __forceinline__ bool grid_barrier(unsigned* counter, unsigned& generation, volatile int32_t* status) {
+__device__ __forceinline__ bool grid_barrier(unsigned* counter, unsigned& generation, volatile int32_t* status,
+                                             long long timeout_cycles) {
   __syncthreads();
   __shared__ int ok;
   if (threadIdx.x == 0) {
@@ -540,7 +546,7 @@ __device__ __forceinline__ bool grid_barrier(unsigned* counter, unsigned& genera
     const unsigned target = generation * gridDim.x;
     const long long t0 = clock64();
     while (ld_acquire_gpu_u32(counter) < target) {
-      if (status[3] != 0 || clock64() - t0 > 20000000000LL) { status[3] = 1; ok = 0; break; }
+      if (status[3] != 0 || clock64() - t0 > timeout_cycles) { status[3] = 1; ok = 0; break; }
     }
   }
   __syncthreads();
@@ -564,35 +570,56 @@ __global__ void __launch_bounds__(kThreads, 1) k_bp_run_d3D4(const __grid_consta
     const int cur = (r.parity + it) & 1;
     // cap reached: the undamped sweep is kept (state.py:122-123)
     sweep<false, MULTI>(a, r.msgs[cur], r.msgs[cur ^ 1], it, it == r.max_iters - 1, PeersOfRun{r, cur ^ 1}, smem);
-    if (!grid_barrier(counter, generation, a.status)) return;
+    if (!grid_barrier(counter, generation, a.status, r.timeout_cycles)) return;
+    float num = __ldcg(a.resid + 2 * it), den = __ldcg(a.resid + 2 * it + 1);     // local maxima (barrier above)
     if (MULTI && r.world > 1) {
-      // every local CTA has finished its stores (barrier above).  CTA 0 pushes the residual maxima to the peers and
-      // releases this rank's flag in their memory; EVERY CTA then waits for the peers' flags in local memory (no second
-      // grid barrier: the acquire of a peer's flag orders that peer's halo stores and maxima before this CTA's next sweep)
+      // Cross-GPU handshake of the sweep, one 16-byte line per peer (the layout of NCCL's low-latency protocol: two
+      // 8-byte words, each carrying data and the sequence number, because only 8-byte stores are atomic over NVLink):
+      //   {max |new - old|^2, seq, max |new + old|^2, seq}  ->  peer q's line [it & 1][rank]
+      // CTA 0 sends -- after one system-scope fence that orders every local CTA's halo stores (made visible to it by the
+      // grid barrier) before the line; EVERY CTA polls its own copy of the peers' lines in local memory and folds their
+      // maxima into the global residual (get_dist is a ratio of two GLOBAL maxima, backends.py:492-495).  No remote
+      // atomics, no second grid barrier, and nothing of a peer's control block is written, so a BP run needs no barrier
+      // in front of it.  (Two lines per peer: a rank can be at most one sweep ahead of the slowest reader.)
       const unsigned seq = r.seq_base + it + 1;
+      __shared__ unsigned s_max[2];
+      if (threadIdx.x == 0) { s_max[0] = __float_as_uint(num); s_max[1] = __float_as_uint(den); }
+      __syncthreads();
       if (threadIdx.x < r.world && (int)threadIdx.x != r.rank) {
         const int q = threadIdx.x;
+        const int slot = (it & 1) * BQA_MAX_PEERS;
         if (blockIdx.x == 0) {
-          const unsigned* mine = reinterpret_cast<const unsigned*>(a.resid) + 2 * it;
-          unsigned* theirs = reinterpret_cast<unsigned*>(r.peer_resid[q]) + 2 * it;
-          atomicMax_system(theirs, ld_acquire_gpu_u32(mine));
-          atomicMax_system(theirs + 1, ld_acquire_gpu_u32(mine + 1));
           __threadfence_system();
-          st_release_sys_u32(r.peer_flags[q] + r.rank, seq);
+          st_volatile_v4(r.peer_xchg[q] + slot + r.rank, make_uint4(__float_as_uint(num), seq, __float_as_uint(den), seq));
         }
+        const uint4* mine = r.peer_xchg[r.rank] + slot + q;
+        uint4 line = ld_volatile_v4(mine);
         const long long t0 = clock64();
-        while ((int)(ld_acquire_sys_u32(r.peer_flags[r.rank] + q) - seq) < 0) {
-          if (*((volatile int32_t*)a.status + 3) != 0 || clock64() - t0 > 20000000000LL) { a.status[3] = 1; break; }
+        while (line.y != seq || line.w != seq) {
+          if (*((volatile int32_t*)a.status + 3) != 0 || clock64() - t0 > r.timeout_cycles) { a.status[3] = 1; break; }
+          line = ld_volatile_v4(mine);
         }
+        __threadfence_system();                             // the peer's halo stores are ordered before its line
+        atomicMax(&s_max[0], line.x);                       // non-negative reals order like their bit patterns
+        atomicMax(&s_max[1], line.z);
       }
       __syncthreads();
       if (*((volatile int32_t*)a.status + 3) != 0) return;
+      num = __uint_as_float(s_max[0]);
+      den = __uint_as_float(s_max[1]);
+      if (blockIdx.x == 0 && threadIdx.x == 0) {            // the host reads the GLOBAL residual of the last sweep
+        a.resid[2 * it] = num;
+        a.resid[2 * it + 1] = den;
+      }
     }
-    const float num = __ldcg(a.resid + 2 * it), den = __ldcg(a.resid + 2 * it + 1);
     if (sqrtf(num / den) < a.bp_eps) { sweeps = it + 1; converged = 1; break; }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) { a.status[1] = sweeps; a.status[0] = converged; }
 }
+
+static long long g_timeout_cycles = 20000000000LL;          // ~10 s at 2 GHz
+long long barrier_timeout_cycles() { return g_timeout_cycles; }
+void set_barrier_timeout_cycles(long long c) { g_timeout_cycles = c > 0 ? c : 20000000000LL; }
 
 static int sm_count() {                     // of the current device (a process may drive several)
   int dev = 0, n = 0;
@@ -630,9 +657,10 @@ int launch_fast_bp_run_d3D4(long long B, const void* T, void* msgs0, void* msgs1
   for (int q = 0; q < BQA_MAX_PEERS; ++q) {
     r.peers[0][q] = (a.remote_pos && peers0) ? (unsigned char*)peers0[q] : nullptr;
     r.peers[1][q] = (a.remote_pos && peers1) ? (unsigned char*)peers1[q] : nullptr;
-    r.peer_resid[q] = (world > 1 && q < world) ? (float*)peer_resid[q] : nullptr;
-    r.peer_flags[q] = (world > 1 && q < world) ? (unsigned*)peer_flags[q] : nullptr;
+    r.peer_xchg[q] = (world > 1 && q < world) ? (uint4*)((unsigned char*)peer_flags[q] + 64) : nullptr;
   }
+  (void)peer_resid;
+  r.timeout_cycles = barrier_timeout_cycles();
   const long long groups = (B + 3) / 4;
   long long grid = (groups + kWarps - 1) / kWarps;
   if (grid > sm_count()) grid = sm_count();

@@ -86,6 +86,12 @@ int launch_fast_apply_d3D4(long long B, const void* T_in, void* T_out, const voi
 int launch_sweep_sync(int prec, int rank, int world, void* const* peer_resid, int it, void* const* peer_flags,
                       unsigned seq, int32_t* status, cudaStream_t st);
 
+// cycles a grid / peer barrier waits before it sets status[3] and gives up (bqa_b200_set_barrier_timeout)
+namespace fast {
+long long barrier_timeout_cycles();
+void set_barrier_timeout_cycles(long long cycles);
+}
+
 // specialised canonicalizer kernel (bqa_fast_canon8.cu): D = 4 (n = 8), complex64
 int launch_fast_canon8(long long L, const void* ext, void* canon, void* lmbds, void* colmax, double pinv_eps,
                        int ncols, cudaStream_t st);

@@ -41,6 +41,7 @@ struct MultiArgs {
   int32_t* status;
   cx<R>* ws;
   size_t ws_per_warp;
+  long long timeout_cycles;
 };
 
 template <typename R>
@@ -90,7 +91,8 @@ __device__ __forceinline__ unsigned mc_ld_acquire(const unsigned* p) {
   return v;
 }
 // all CTAs of a cooperative grid; `counter` only grows (zeroed by the host before the launch); status[3] != 0 aborts
-__device__ __forceinline__ bool mc_grid_barrier(unsigned* counter, unsigned& generation, volatile int32_t* status) {
+__device__ __forceinline__ bool mc_grid_barrier(unsigned* counter, unsigned& generation, volatile int32_t* status,
+                                                long long timeout_cycles) {
   __syncthreads();
   __shared__ int ok;
   if (threadIdx.x == 0) {
@@ -101,7 +103,7 @@ __device__ __forceinline__ bool mc_grid_barrier(unsigned* counter, unsigned& gen
     const unsigned target = generation * gridDim.x;
     const long long t0 = clock64();
     while (mc_ld_acquire(counter) < target) {
-      if (status[3] != 0 || clock64() - t0 > 20000000000LL) { status[3] = 1; ok = 0; break; }
+      if (status[3] != 0 || clock64() - t0 > timeout_cycles) { status[3] = 1; ok = 0; break; }
     }
   }
   __syncthreads();
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(128) k_mc_bp_run(const __grid_constant__ Multi
   for (int it = 0; it < a.max_iters; ++it) {
     const int cur = (a.parity + it) & 1;
     mc_sweep<R>(a, a.msgs[cur], a.msgs[cur ^ 1], it, it == a.max_iters - 1);    // cap: the undamped sweep is kept (:122-123)
-    if (!mc_grid_barrier(counter, generation, a.status)) return;
+    if (!mc_grid_barrier(counter, generation, a.status, a.timeout_cycles)) return;
     const R num = __ldcg(a.resid + 2 * it), den = __ldcg(a.resid + 2 * it + 1);
     if (msqrt(num / den) < a.bp_eps) { sweeps = it + 1; converged = 1; break; }
   }
@@ -212,6 +214,7 @@ int launch_multiclass(int kind, int n_classes, const bqa_b200_class* cls, int D,
   a.canon = (const cx<R>*)canon; a.lmbds = (const R*)lmbds;
   a.ztime = (R)ztime; a.xtime = (R)xtime; a.damping = (R)damping; a.bp_eps = (R)bp_eps;
   a.resid = (R*)resid; a.status = status; a.ws = (cx<R>*)ws; a.ws_per_warp = per_warp;
+  a.timeout_cycles = fast::barrier_timeout_cycles();
   long long blocks = (total + 3) / 4;
   const long long cap = (long long)BQA_GENERIC_MAX_WARPS / 4;
   if (blocks > cap) blocks = cap;

@@ -134,6 +134,7 @@ template int launch_gauge_slots<double>(int, int, long long, const int32_t*, con
 struct SyncArgs {
   int rank, world, it, dbl;
   unsigned seq;
+  long long timeout_cycles;
   void* resid[BQA_MAX_PEERS];              // base of every rank's residual array (peer mapped)
   unsigned* flags[BQA_MAX_PEERS];          // every rank's flag array: flags[q][src] is written by rank src
   int32_t* status;
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(32) k_sweep_sync(SyncArgs a) {
     st_release_sys(a.flags[q] + a.rank, a.seq);             // "rank has finished sweep seq" on peer q
     const long long t0 = clock64();
     while ((int)(ld_acquire_sys(a.flags[a.rank] + q) - a.seq) < 0) {
-      if (clock64() - t0 > 20000000000LL) {                 // ~10 s: a peer died; flag the error instead of hanging
+      if (clock64() - t0 > a.timeout_cycles) {              // a peer died: flag the error instead of hanging
         a.status[3] = 1;
         break;
       }
@@ -183,6 +184,7 @@ int launch_sweep_sync(int prec, int rank, int world, void* const* peer_resid, in
   if (world == 1) return 0;
   SyncArgs a{};
   a.rank = rank; a.world = world; a.it = it; a.dbl = prec == 1; a.seq = seq; a.status = status;
+  a.timeout_cycles = fast::barrier_timeout_cycles();
   for (int q = 0; q < world; ++q) { a.resid[q] = peer_resid ? peer_resid[q] : nullptr; a.flags[q] = (unsigned*)peer_flags[q]; }
   if (it >= 0 && !peer_resid) return set_error("sweep_sync: residual arrays missing");
   k_sweep_sync<<<1, 32, 0, st>>>(a);

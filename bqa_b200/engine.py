@@ -399,6 +399,12 @@ class Engine:
     def _bp_run_done(self, sweeps: int) -> None:
         """Hook for the partitioned engine (advances the cross-GPU barrier sequence)."""
 
+    def _single_launch_applies(self) -> bool:
+        """True when run_bp will take the one-launch kernel of the headline shape (bqa_b200_bp_run)."""
+        active = [c for c in self.classes if c.degree > 0 and c.B > 0]
+        return (self._single_launch_ok and len(active) == 1 and not self._no_bp_run.get(self.D)
+                and self.precision == "single" and active[0].degree == 3 and self.D == 4 and active[0].B >= 4)
+
     def _try_single_launch_bp(self):
         """The whole BP run in one cooperative launch (bqa_b200_bp_run) when every BP-active node sits in one degree
         class with a specialised kernel; returns (converged, sweeps, resid) or None."""

@@ -345,7 +345,8 @@ class PartitionedEngine(Engine):
         self._single_launch_ok = bool(int(flag[0])) and int(flag[1]) == -int(flag[2])   # same single class everywhere
         if self.p2p:
             self._ensure_edge_buffers(self.Dmax)              # symmetric allocations are collective: do them all now
-            self._flags = self._alloc_shared(64, torch.uint8, "flags")
+            # 64 bytes of per-peer barrier flags (bqa_b200_sweep_sync) + the handshake lines of the single-launch BP run
+            self._flags = self._alloc_shared(64 + 2 * 16 * 8, torch.uint8, "flags")
             ptrs = lambda tag: (C.c_void_p * 8)(*([int(x) for x in self._symm[tag][1].buffer_ptrs] + [0] * (8 - self.world)))
             self._peer_ptrs = {("msgs", 0): ptrs("msgs0"), ("msgs", 1): ptrs("msgs1"), ("ext", 0): ptrs("ext"),
                                "ctrl": ptrs("ctrl"), "flags": ptrs("flags")}
@@ -390,8 +391,10 @@ class PartitionedEngine(Engine):
         self._seq += sweeps            # one cross-GPU barrier per executed sweep, same count on every rank
 
     def _before_bp(self) -> None:
-        if self.p2p:
-            self._sync(-1)            # nobody pushes residuals of the new run before everybody has reset its block
+        # per-sweep launches: nobody pushes residuals of the new run before everybody has reset its control block.
+        # (The single-launch run writes nothing into a peer's control block -- handshake lines only: no barrier.)
+        if self.p2p and not self._single_launch_applies():
+            self._sync(-1)
 
     # -- boundary exchange of a (slots, elems) complex array held flat in `buf` ------------------------
     def _exchange(self, buf: torch.Tensor, elems: int) -> None:

@@ -43,6 +43,10 @@ long long bqa_b200_launch_count(void);
  *    (bqa_fast_canon8v2.cu): kept for side-by-side measurements */
 int bqa_b200_set_kernel_mode(int mode);
 
+/* how long an in-kernel grid barrier or cross-GPU handshake waits before it gives up, sets status[3] (sticky: the engine
+ * raises at its next read of the control block) and lets the kernel end; default about 10 s */
+int bqa_b200_set_barrier_timeout(double seconds);
+
 /* profiling aid: out3[0] = warp-level Jacobi problems (4 matrices each) solved by the n = 8 canonicalizer kernel
  * since load, out3[1] = Jacobi sweeps summed over them, out3[2] = the part of out3[1] spent on the SVD of ker
  * (synchronises the device) */
@@ -101,12 +105,17 @@ int bqa_b200_ext_msgs_p2p(int prec, int degree, int D, long long B, const void* 
 int bqa_b200_sweep_sync(int prec, int rank, int world, void* const* peer_resid, int it, void* const* peer_flags,
                         unsigned seq, int32_t* status, void* stream);
 /* The whole BP run of a degree class in ONE cooperative launch (reference _run_bp, state.py:97-124): persistent CTAs
- * iterate sweep -> grid barrier -> (world > 1: residual push + flag barrier with the peers) -> global residual test.
+ * iterate sweep -> grid barrier -> (world > 1: cross-GPU handshake, below) -> global residual test.
  * Sweep `it` reads msgs{(parity + it) & 1} and writes the other buffer; on return status[0] = converged (0 / 1),
  * status[1] = number of sweeps executed; status[2] (grid-barrier counter) and resid must be zero before the call.
  * Only for graphs whose nodes all sit in ONE degree class that has a specialised kernel; returns 2 (and changes
  * nothing) when there is none -- the caller then enqueues bqa_b200_bp_sweep[_p2p] calls.  peers0/peers1 = peer bases
- * of the two message buffers; cross-GPU barrier sequence numbers used: seq_base + 1 ... seq_base + status[1]. */
+ * of the two message buffers.  Cross-GPU handshake of a sweep: CTA 0 stores ONE 16-byte line {max |new - old|^2, seq,
+ * max |new + old|^2, seq} into every peer (after a system-scope fence behind the grid barrier: the halo stores come
+ * first), every CTA polls the peers' lines in local memory and folds their maxima into the global residual.  The
+ * lines live 64 bytes into each rank's flag buffer: peer_flags[q] must point to at least 64 + 2 * 16 *
+ * BQA_B200_MAX_PEERS zero-initialised bytes; sequence numbers used: seq_base + 1 ... seq_base + status[1].  Nothing of a
+ * peer's control block is written (peer_resid is unused), so no barrier is needed in front of a run. */
 int bqa_b200_bp_run(int prec, int degree, int D, long long B, const void* T, void* msgs0, void* msgs1, int parity,
                     const int32_t* in_pos, const int32_t* out_pos, double damping, double bp_eps, int max_iters,
                     void* resid, int32_t* status, const int32_t* remote_pos, void* const* peers0, void* const* peers1,

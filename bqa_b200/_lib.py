@@ -24,6 +24,8 @@ SIGNATURES = {
     "bqa_b200_bp_sweep": [_i, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp, _d, _i, _d, _i, _vp, _vp, _vp, _sz, _vp],
     "bqa_b200_ext_msgs": [_i, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _d, _vp, _sz, _vp],
     "bqa_b200_canonicalize": [_i, _i, _ll, _vp, _vp, _vp, _vp, _d, _i, _vp],
+    "bqa_b200_canonicalize_ordered": [_i, _i, _ll, _vp, _vp, _vp, _vp, _d, _i, _vp, _vp, _vp],
+    "bqa_b200_sort_edges_by_cost": [_ll, _vp, _vp, _vp],
     "bqa_b200_apply_update": [_i, _i, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _vp, _sz, _vp],
     "bqa_b200_density": [_i, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp],
     "bqa_b200_argmax_unmeasured": [_i, _ll, _vp, _vp, _vp, _vp, _vp],
@@ -54,6 +56,9 @@ EXPORTS = list(SIGNATURES) + ["bqa_b200_last_error", "bqa_b200_version", "bqa_b2
                               "bqa_b200_set_barrier_timeout"]
 
 
+_CUDA_ONLY = ("bqa_b200_canonicalize_ordered", "bqa_b200_sort_edges_by_cost")
+
+
 class ClassDesc(C.Structure):
     """bqa_b200_class of include/bqa_b200.h: one row of the degree-class table of the *_classes entry points"""
     _fields_ = [("degree", _i), ("B", _ll), ("T_in", _vp), ("T_out", _vp), ("in_pos", _vp), ("out_pos", _vp),
@@ -71,7 +76,7 @@ class Library:
                 fn = getattr(self._dll, name)
             except AttributeError:
                 # the test-only host emulation covers the per-class fused entry points only
-                if name.startswith("bqa_b200_t_") or name.endswith("_classes"):
+                if name.startswith("bqa_b200_t_") or name.endswith("_classes") or name in _CUDA_ONLY:
                     continue
                 raise
             fn.argtypes = argtypes

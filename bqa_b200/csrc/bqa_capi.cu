@@ -199,11 +199,20 @@ int bqa_b200_sweep_sync(int prec, int rank, int world, void* const* peer_resid, 
 
 int bqa_b200_canonicalize(int prec, int D, long long L, const void* ext, void* canon, void* lmbds, void* colmax,
                           double pinv_eps, int n_cols, void* stream) {
+  return bqa_b200_canonicalize_ordered(prec, D, L, ext, canon, lmbds, colmax, pinv_eps, n_cols, nullptr, nullptr, stream);
+}
+
+int bqa_b200_sort_edges_by_cost(long long L, const void* cost, int32_t* order, void* stream) {
+  return launch_sort_edges_by_cost(L, cost, order, (cudaStream_t)stream);
+}
+
+int bqa_b200_canonicalize_ordered(int prec, int D, long long L, const void* ext, void* canon, void* lmbds, void* colmax,
+                                  double pinv_eps, int n_cols, const int32_t* order, void* cost, void* stream) {
   if (int rc = check_shape(prec, 0, D)) return rc;
   if (n_cols < 1 || n_cols > 2 * D) return set_error("n_cols %d outside [1, %d]", n_cols, 2 * D);
   cudaStream_t st = (cudaStream_t)stream;
   if (g_kernel_mode.load() == 0 && prec == BQA_C64 && D == 4)
-    return launch_fast_canon8v2(L, ext, canon, lmbds, colmax, pinv_eps, n_cols, st);
+    return launch_fast_canon8v2(L, ext, canon, lmbds, colmax, pinv_eps, n_cols, order, cost, st);
   if (g_kernel_mode.load() == 2 && prec == BQA_C64 && D == 4)
     return launch_fast_canon8(L, ext, canon, lmbds, colmax, pinv_eps, n_cols, st);
   if (prec == BQA_C64) return launch_canonicalize<float>(D, L, ext, canon, lmbds, colmax, pinv_eps, st);

@@ -360,7 +360,8 @@ __device__ __forceinline__ void inv_col_norms(const unsigned char* m, float (&in
 
 __global__ void __launch_bounds__(kWarps * 32, 1) k_canon8v2(long long L, const float2* __restrict__ ext,
                                                              float2* __restrict__ canon, float* __restrict__ lmbds,
-                                                             float* __restrict__ colmax, float pinv_eps, int ncols, int nphases) {
+                                                             float* __restrict__ colmax, float pinv_eps, int ncols, int nphases,
+                                                             const int* __restrict__ order, unsigned char* __restrict__ cost) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int pair = lane >> 1;
@@ -388,6 +389,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_canon8v2(long long L, const 
   auto prefetch = [&](long long g) {
     long long e = g * kEdges + (lane & 15);
     e = e < L ? e : L - 1;
+    if (order) e = __ldg(order + e);
     const unsigned dst = smem_u32(wbase) + (lane & 15) * kPair + (lane < 16 ? kMat : 2 * kMat);
     fence_proxy_async();                                    // this lane's earlier loads / stores of the slots come first
     __syncwarp();
@@ -402,6 +404,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_canon8v2(long long L, const 
     long long e = g * kEdges + pair;
     const bool live = e < L;
     e = live ? e : L - 1;
+    if (order) e = __ldg(order + e);                        // edges grouped by the sweeps they needed last time (see `cost`)
+    int it_eig = 0, it_ker = 0;
     mbar_wait(bar, bar_parity);
     bar_parity ^= 1;
     // Two Jacobi runs per iteration through ONE copy of the sweep code (a rolled loop over the phases):
@@ -459,7 +463,15 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_canon8v2(long long L, const 
         if (g + nwarps < groups) prefetch(g + nwarps);
       }
       const int before = n_sweeps;
-      jacobi8(A, w, n_sweeps, phase == 1, phase == 0 ? own_eig : own_ker);
+      int own = 0;
+      jacobi8(A, w, n_sweeps, phase == 1, own);
+      if (phase == 0) {
+        own_eig += own;
+        it_eig = max(own, __shfl_xor_sync(0xffffffffu, own, 1));
+      } else {
+        own_ker += own;
+        it_ker = own;
+      }
       n_jac += 1;
       if (phase == 0) {
         eig_publish(A, w, (leader ? Bm : Qm) + kPad, leader ? F : Bm, pinv_eps);
@@ -495,6 +507,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_canon8v2(long long L, const 
         for (int j = 0; j < 8; ++j) v = rk[j] == c ? lam[j] : v;
         sorted[c] = v;
       }
+      // what this edge cost: the key bqa_b200_sort_edges_by_cost groups the edges by, so that the edges of a warp need
+      // about the same number of sweeps next time (a warp sweeps until its slowest matrix has converged)
+      if (live && cost) cost[e] = (unsigned char)(min(it_eig, 15) * 16 + min(it_ker, 15));
       if (live) {
         float4* lo = reinterpret_cast<float4*>(lmbds + (size_t)e * 8);
         lo[0] = make_float4(sorted[0], sorted[1], sorted[2], sorted[3]);
@@ -599,8 +614,46 @@ void canon8v2_stats_detail(unsigned long long* out7) {
   cudaMemcpyFromSymbol(out7, canon8v2::g_stats, sizeof(unsigned long long) * 7);
 }
 
+// ---- counting sort of the edges by cost, descending (one block; keys are bytes; warp-aggregated shared-memory atomics)
+__global__ void __launch_bounds__(1024) k_sort_by_cost(long long L, const unsigned char* __restrict__ cost, int* __restrict__ order) {
+  __shared__ unsigned hist[256];
+  const int lane = threadIdx.x & 31;
+  for (int k = threadIdx.x; k < 256; k += blockDim.x) hist[k] = 0;
+  __syncthreads();
+  const long long rounds = (L + blockDim.x - 1) / blockDim.x;
+  for (long long rnd = 0; rnd < rounds; ++rnd) {
+    const long long i = rnd * blockDim.x + threadIdx.x;
+    const unsigned key = i < L ? cost[i] : 256u;
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    if (key < 256u && lane == __ffs(peers) - 1) atomicAdd(&hist[key], __popc(peers));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {                                   // start of every key's run, largest key first
+    unsigned run = 0;
+    for (int k = 255; k >= 0; --k) { const unsigned c = hist[k]; hist[k] = run; run += c; }
+  }
+  __syncthreads();
+  for (long long rnd = 0; rnd < rounds; ++rnd) {
+    const long long i = rnd * blockDim.x + threadIdx.x;
+    const unsigned key = i < L ? cost[i] : 256u;
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    const int leader = __ffs(peers) - 1;
+    unsigned base = 0;
+    if (key < 256u && lane == leader) base = atomicAdd(&hist[key], __popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (key < 256u) order[base + __popc(peers & ((1u << lane) - 1u))] = (int)i;
+  }
+}
+
+int launch_sort_edges_by_cost(long long L, const void* cost, int32_t* order, cudaStream_t st) {
+  if (L <= 0) return 0;
+  if (L >= (1LL << 31)) return set_error("sort_edges_by_cost: %lld edges exceed the 32-bit index range", L);
+  k_sort_by_cost<<<1, 1024, 0, st>>>(L, (const unsigned char*)cost, order);
+  return after_launch("sort_edges_by_cost");
+}
+
 int launch_fast_canon8v2(long long L, const void* ext, void* canon, void* lmbds, void* colmax, double pinv_eps,
-                         int ncols, cudaStream_t st) {
+                         int ncols, const int32_t* order, void* cost, cudaStream_t st) {
   using namespace canon8v2;
   if (L == 0) return 0;
   if (ncols < 1 || ncols > 8) return set_error("canonicalize: %d canonicalizer columns requested for n = 8", ncols);
@@ -619,7 +672,7 @@ int launch_fast_canon8v2(long long L, const void* ext, void* canon, void* lmbds,
   long long grid = (groups + kWarps - 1) / kWarps;
   if (grid > sms) grid = sms;
   k_canon8v2<<<(int)grid, kWarps * 32, kSmem, st>>>(L, (const float2*)ext, (float2*)canon, (float*)lmbds, (float*)colmax,
-                                                   (float)pinv_eps, ncols, 2);
+                                                   (float)pinv_eps, ncols, 2, order, (unsigned char*)cost);
   return after_launch("canonicalize(n=8, v2)");
 }
 

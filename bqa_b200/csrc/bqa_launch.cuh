@@ -99,7 +99,8 @@ int launch_fast_canon8(long long L, const void* ext, void* canon, void* lmbds, v
 void canon8_stats(unsigned long long* out3);
 // second design (bqa_fast_canon8v2.cu): Cholesky factor + column Jacobi for the eigenproblems, stacked SVD of ker
 int launch_fast_canon8v2(long long L, const void* ext, void* canon, void* lmbds, void* colmax, double pinv_eps,
-                         int ncols, cudaStream_t st);
+                         int ncols, const int32_t* order, void* cost, cudaStream_t st);
+int launch_sort_edges_by_cost(long long L, const void* cost, int32_t* order, cudaStream_t st);
 void canon8v2_stats(unsigned long long* out3);
 void canon8v2_stats_detail(unsigned long long* out7);
 

@@ -179,6 +179,13 @@ class Engine:
         # collapses (backends.py:297-303), so the step is enqueued without waiting for the column maxima and they are
         # checked with the BP control block, in the step's only host read; a wrong guess redoes the update.
         self.speculate = os.environ.get("BQA_B200_SPECULATE", "1") != "0"
+        # edge order of the n = 8 canonicalizer kernel (bqa_b200_canonicalize_ordered): identity until costs exist
+        self._canon_order = self._canon_cost = None
+        self._canon_resort_every = int(os.environ.get("BQA_B200_CANON_RESORT", "8"))
+        self._canon_age = 1                                   # the first regrouping needs one step of recorded costs
+        if self.cuda and self._canon_resort_every > 0 and hasattr(self.lib, "canonicalize_ordered") and self.L > 0:
+            self._canon_order = torch.arange(self.L, dtype=torch.int32, device=self.dev)
+            self._canon_cost = torch.zeros(self.L, dtype=torch.uint8, device=self.dev)
         self._bloch = torch.zeros(self.N * 4, dtype=self.rdtype, device=self.dev)
         self._ws = torch.zeros(16, dtype=torch.uint8, device=self.dev)
         # candidate of a sampling pass: (node, unmeasured count) int32 x2 | p0 real -- one buffer, one host read per pass
@@ -530,9 +537,21 @@ class Engine:
                 self.lib.ext_msgs_p2p(*args, c.remote_pos.data_ptr(), peers, st)
         self._exchange_ext()
         self._colmax.zero_()
-        self.lib.canonicalize(self.prec, D, self.L, self._ext.data_ptr(), self._canon.data_ptr(),
-                              self._lmbds.data_ptr(), self._colmax.data_ptr(), self.pinv_eps,
-                              min(2 * D, self.Dmax), st)
+        if self._canon_order is not None and self.precision == "single" and D == 4:
+            # n = 8 kernel: edges grouped by the Jacobi sweeps they needed (regrouped every few steps from the costs the
+            # kernel records; a warp sweeps until its slowest matrix is done, results do not depend on the grouping)
+            if self._canon_age >= self._canon_resort_every:
+                self.lib.sort_edges_by_cost(self.L, self._canon_cost.data_ptr(), self._canon_order.data_ptr(), st)
+                self._canon_age = 0
+            self._canon_age += 1
+            self.lib.canonicalize_ordered(self.prec, D, self.L, self._ext.data_ptr(), self._canon.data_ptr(),
+                                          self._lmbds.data_ptr(), self._colmax.data_ptr(), self.pinv_eps,
+                                          min(2 * D, self.Dmax), self._canon_order.data_ptr(),
+                                          self._canon_cost.data_ptr(), st)
+        else:
+            self.lib.canonicalize(self.prec, D, self.L, self._ext.data_ptr(), self._canon.data_ptr(),
+                                  self._lmbds.data_ptr(), self._colmax.data_ptr(), self.pinv_eps,
+                                  min(2 * D, self.Dmax), st)
         self._lmbd_stride = 2 * D
         self._reduce_colmax(self._colmax)
         speculative = self.speculate and self.cuda and D == self.Dmax

@@ -141,6 +141,15 @@ int bqa_b200_ext_msgs(int prec, int degree, int D, long long B, const void* T, c
  * bond dimension the truncation can keep, state.py:233-235); columns >= n_cols of canon may be left unwritten. */
 int bqa_b200_canonicalize(int prec, int D, long long L, const void* ext, void* canon, void* lmbds,
                           void* colmax, double pinv_eps, int n_cols, void* stream);
+/* The same with the edges visited in the order `order` (int32 permutation of 0 .. L-1, NULL = identity) and the cost of
+ * every edge written to `cost` (one byte per edge, NULL = not wanted): 16 * sweeps of its slower eigenproblem + sweeps of
+ * its SVD.  A warp of the n = 8 kernel sweeps until the slowest of its matrices has converged (3.7 / 4.0 sweeps per
+ * matrix on average, 5.0 / 5.1 per warp on the 100k benchmark); grouping edges that needed the same number of sweeps
+ * last time -- bqa_b200_sort_edges_by_cost: order = edges by descending cost -- removes most of that loss.  Results do
+ * not depend on the order (a converged matrix is frozen).  Shapes without the specialised kernel ignore both arrays. */
+int bqa_b200_canonicalize_ordered(int prec, int D, long long L, const void* ext, void* canon, void* lmbds, void* colmax,
+                                  double pinv_eps, int n_cols, const int32_t* order, void* cost, void* stream);
+int bqa_b200_sort_edges_by_cost(long long L, const void* cost, int32_t* order, void* stream);
 
 /* ---- K3c + K4: apply the simple update to a degree class ---------------------------------------
  * replaces batch_truncate_all_but + apply_canonicalizers_with_extensions (state.py:235-246,

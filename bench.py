@@ -417,6 +417,13 @@ def run_ours(args) -> None:
                 "what": "Bloch vectors of the partitioned run after the timed region vs a single-GPU replay on rank 0"}
         del one
 
+    # ---- configs[4] (500k qubits) with the same kernels, at N = 8 only ------------------------------------------
+    cfg5 = None
+    if world == 8 and not args.no_config5:
+        del eng
+        torch.cuda.empty_cache()
+        cfg5 = config5_block(steps, warmup, torch, dist, dev, rank, world)
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -458,6 +465,8 @@ def run_ours(args) -> None:
         line["parity"] = parity_block(cfg, eng.bloch_vectors(), eng.lmbds_numpy(), eng.stats["bp_sweeps"][n1:], r)
     if par1 is not None:
         line["parity_vs_1gpu"] = par1
+    if cfg5 is not None:
+        line["config5_500k"] = cfg5
     emit(line)
     if line.get("parity") and not line["parity"]["ok"]:
         raise SystemExit(f"parity outside the stated fp32 tolerance: {line['parity']}")
@@ -466,6 +475,62 @@ def run_ours(args) -> None:
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def config5_block(steps: int, warmup: int, torch, dist, dev, rank: int, world: int) -> dict | None:
+    """BASELINE.json configs[4]: the 500 000-qubit random 3-regular QUBO (benchmarks_against_mqlib/
+    random_3_regular_qubo_500000.py shape, dt = 0.2) sharded over the 8 GPUs with the same kernels: steps/s of K timed
+    steps after the ramp, and the partitioned result against a single-GPU replay of the same steps on rank 0."""
+    from bqa_b200.config import config_to_context
+    from bqa_b200.engine import Engine
+    from bqa_b200.partitioned import PartitionedEngine
+    t0 = time.perf_counter()
+    cfg = make_config(500_000, schedule_len(steps, warmup))
+    ctx = config_to_context(cfg)
+    layers = [i for i in ctx.instructions if isinstance(i, dict)]
+    eng = PartitionedEngine(ctx, precision="single", device=dev)
+    k = RAMP + warmup
+    for ins in layers[:k]:
+        eng.run_layer(ins["xtime"], ins["ztime"])
+    assert eng.D == 4
+    dist.barrier()
+    torch.cuda.synchronize(dev)
+    n0 = len(eng.stats["bp_sweeps"])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for ins in layers[k:k + steps]:
+        eng.run_layer(ins["xtime"], ins["ztime"])
+    e1.record()
+    dist.barrier()
+    torch.cuda.synchronize(dev)
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    bloch = eng.bloch_vectors()
+    sweeps = eng.stats["bp_sweeps"][n0:]
+    out = None
+    if rank == 0:
+        one = Engine(ctx, precision="single", device=dev)
+        for ins in layers[:k + steps]:
+            one.run_layer(ins["xtime"], ins["ztime"])
+        d1 = np.abs(one.bloch_vectors() - bloch)
+        spins = np.where(bloch[:, 2] > 0, 1.0, -1.0)
+        from bqa_b200.benchmarking import ising_energy
+        out = {"workload": "random 3-regular QUBO, 500,000 qubits (BASELINE.json configs[4]), "
+                           "generate_qubo_on_random_regular_graph(500000, 3, seed=42), node-partitioned over 8 GPUs",
+               "value": steps / (ms * 1e-3), "unit": "steps/s", "ms_per_step": ms / steps, "steps": steps,
+               "sweeps_per_step": float(np.mean(sweeps)),
+               "bp_msg_updates_per_s": float(np.sum(sweeps)) * int(ctx.edges_number) / (ms * 1e-3),
+               "parity_vs_1gpu": {"max_abs": float(d1.max()), "expected": 0.0, "steps_compared": k + steps,
+                                  "sweeps_equal": one.stats["bp_sweeps"][:k + steps] == eng.stats["bp_sweeps"][:k + steps]},
+               "energy_of_sign_z": ising_energy(cfg["edges"], cfg["nodes"], spins),
+               "cut_fraction": None, "wall_s": None}
+        del one
+    del eng
+    dist.barrier()
+    if out is not None:
+        out["wall_s"] = time.perf_counter() - t0
+    return out
 
 
 def measure_roofline(eng, lib, layers, torch, dev) -> dict:
@@ -480,7 +545,8 @@ def measure_roofline(eng, lib, layers, torch, dev) -> dict:
         else (6650.0, "fallback (B200_PROFILING.md)")
     # entry point -> bucket (the partitioned engine calls the *_p2p variants)
     buckets = {"bp_sweep": "bp_sweep", "bp_sweep_p2p": "bp_sweep", "ext_msgs": "ext_msgs", "ext_msgs_p2p": "ext_msgs",
-               "canonicalize": "canonicalize", "apply_update": "apply_update", "sweep_sync": "sweep_sync",
+               "canonicalize": "canonicalize", "canonicalize_ordered": "canonicalize", "sort_edges_by_cost": "canonicalize",
+               "apply_update": "apply_update", "sweep_sync": "sweep_sync",
                "gauge_msgs": "gauge_msgs", "bp_run": "bp_run"}
     names = sorted(set(buckets.values()))
     events = {n: [] for n in names}
@@ -610,6 +676,7 @@ def main() -> None:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-steps", type=int, default=1, help="steps of the cpu_baseline / parity leg (N=1 only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-config5", action="store_true", help="N = 8: skip the 500k-qubit block")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -28,6 +28,8 @@
 // column exchanges), so single-GPU and partitioned runs stay bit-identical.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "bqa_core.cuh"
 #include "bqa_f32x2.cuh"
 #include "bqa_launch.cuh"
@@ -201,7 +203,7 @@ __device__ __forceinline__ void col_norms(const Mat& A, float (&w)[8]) {
 // bqa_fast_canon8.cu: a sweep is 4 x [pairs (0,1) (2,3) (4,5) (6,7) | pairs (1,2) (3,4) (5,6)] by position; after a sweep
 // the column order is reversed, an odd number of sweeps is undone at the end.  On exit the columns are orthogonal and
 // w[j] is the squared norm of column j.  paired: lanes 2i (leader) and 2i + 1 (follower, see pair_step).
-__device__ __forceinline__ void jacobi8(Mat& A, float (&w)[8], int& sweeps, bool paired, int& own_sweeps) {
+__device__ __forceinline__ void jacobi8(Mat& A, float (&w)[8], int& sweeps, bool paired, int& own_sweeps, float conv) {
   const int lane = threadIdx.x & 31;
   const int src_lane = paired ? (lane & ~1) : lane;
   const float eps = 1.1920929e-07f;
@@ -224,7 +226,7 @@ __device__ __forceinline__ void jacobi8(Mat& A, float (&w)[8], int& sweeps, bool
     ++done;
     own_sweeps += frozen ? 0 : 1;
     // LAPACK xGESVJ's quadratic-convergence test: the next sweep's rotations would be below the tolerance
-    const bool fin = frozen || 64.f * mxg2 * mxs2 < tol2;
+    const bool fin = frozen || conv * mxg2 * mxs2 < tol2;
     frozen = __shfl_sync(0xffffffffu, fin ? 1 : 0, src_lane) != 0;
     if (!__any_sync(0xffffffffu, !frozen)) break;
   }
@@ -361,7 +363,7 @@ __device__ __forceinline__ void inv_col_norms(const unsigned char* m, float (&in
 __global__ void __launch_bounds__(kWarps * 32, 1) k_canon8v2(long long L, const float2* __restrict__ ext,
                                                              float2* __restrict__ canon, float* __restrict__ lmbds,
                                                              float* __restrict__ colmax, float pinv_eps, int ncols, int nphases,
-                                                             const int* __restrict__ order, unsigned char* __restrict__ cost) {
+                                                             const int* __restrict__ order, unsigned char* __restrict__ cost, float conv) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int pair = lane >> 1;
@@ -464,7 +466,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_canon8v2(long long L, const 
       }
       const int before = n_sweeps;
       int own = 0;
-      jacobi8(A, w, n_sweeps, phase == 1, own);
+      jacobi8(A, w, n_sweeps, phase == 1, own, conv);
       if (phase == 0) {
         own_eig += own;
         it_eig = max(own, __shfl_xor_sync(0xffffffffu, own, 1));
@@ -671,8 +673,10 @@ int launch_fast_canon8v2(long long L, const void* ext, void* canon, void* lmbds,
   const long long groups = (L + kEdges - 1) / kEdges;
   long long grid = (groups + kWarps - 1) / kWarps;
   if (grid > sms) grid = sms;
+  // n^2 of LAPACK xGESVJ's estimate "next sweep's largest cosine ~ n max|cos| max|sin|" (experiments: BQA_B200_CANON_CONV)
+  static const float conv = [] { const char* e = getenv("BQA_B200_CANON_CONV"); return e ? (float)atof(e) : 64.f; }();
   k_canon8v2<<<(int)grid, kWarps * 32, kSmem, st>>>(L, (const float2*)ext, (float2*)canon, (float*)lmbds, (float*)colmax,
-                                                   (float)pinv_eps, ncols, 2, order, (unsigned char*)cost);
+                                                   (float)pinv_eps, ncols, 2, order, (unsigned char*)cost, conv);
   return after_launch("canonicalize(n=8, v2)");
 }
 

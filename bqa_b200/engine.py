@@ -179,9 +179,12 @@ class Engine:
         # collapses (backends.py:297-303), so the step is enqueued without waiting for the column maxima and they are
         # checked with the BP control block, in the step's only host read; a wrong guess redoes the update.
         self.speculate = os.environ.get("BQA_B200_SPECULATE", "1") != "0"
-        # edge order of the n = 8 canonicalizer kernel (bqa_b200_canonicalize_ordered): identity until costs exist
+        # edge order of the n = 8 canonicalizer kernel (bqa_b200_canonicalize_ordered).  OFF by default: measured on the
+        # 100k benchmark, regrouping the edges by last step's Jacobi sweep counts lowers the sweeps a warp runs only from
+        # 5.34 to 5.19 (every 8 steps) / 5.09 (every step): the slow matrices of one step are not the slow ones of the
+        # next, and the counting sort costs more than it saves (profiles/r2_canon_experiments.md)
         self._canon_order = self._canon_cost = None
-        self._canon_resort_every = int(os.environ.get("BQA_B200_CANON_RESORT", "8"))
+        self._canon_resort_every = int(os.environ.get("BQA_B200_CANON_RESORT", "0"))
         self._canon_age = 1                                   # the first regrouping needs one step of recorded costs
         if self.cuda and self._canon_resort_every > 0 and hasattr(self.lib, "canonicalize_ordered") and self.L > 0:
             self._canon_order = torch.arange(self.L, dtype=torch.int32, device=self.dev)

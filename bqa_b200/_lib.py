@@ -53,7 +53,7 @@ SIGNATURES = {
 EXPORTS = list(SIGNATURES) + ["bqa_b200_last_error", "bqa_b200_version", "bqa_b200_launch_count",
                               "bqa_b200_workspace_bytes", "bqa_b200_set_kernel_mode", "bqa_b200_canon_stats",
                               "bqa_b200_t_svd_scratch_bytes", "bqa_b200_canon_stats_detail",
-                              "bqa_b200_set_barrier_timeout"]
+                              "bqa_b200_set_barrier_timeout", "bqa_b200_set_bp_trace"]
 
 
 _CUDA_ONLY = ("bqa_b200_canonicalize_ordered", "bqa_b200_sort_edges_by_cost")
@@ -113,6 +113,10 @@ class Library:
         n = 8 canonicalizer (side-by-side measurements)."""
         if self._dll.bqa_b200_set_kernel_mode(int(mode)) != 0:
             raise RuntimeError(self._dll.bqa_b200_last_error().decode())
+
+    def set_bp_trace(self, device_ptr) -> None:
+        self._dll.bqa_b200_set_bp_trace.argtypes = [_vp]
+        self._dll.bqa_b200_set_bp_trace(device_ptr)
 
     def set_barrier_timeout(self, seconds: float) -> None:
         self._dll.bqa_b200_set_barrier_timeout.argtypes = [_d]

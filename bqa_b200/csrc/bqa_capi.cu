@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/bqa_b200.h"
 #include "bqa_core.cuh"
@@ -32,6 +33,14 @@ int after_launch(const char* what) {
   return 0;
 }
 
+// which n = 8 canonicalizer layout mode 0 uses: 2 (one lane per matrix, default: 0.83 ms for 150k edges) or 3 (two
+// lanes per matrix, 16 warps per SM: 1.03 ms -- its shuffles and selects cost more than the occupancy brings);
+// BQA_B200_CANON_V in the environment, for side-by-side measurements
+static int canon_variant() {
+  static const int v = [] { const char* e = getenv("BQA_B200_CANON_V"); return (e && atoi(e) == 3) ? 3 : 2; }();
+  return v;
+}
+
 static int check_shape(int prec, int degree, int D) {
   if (prec != BQA_C64 && prec != BQA_C128) return set_error("unknown precision code %d", prec);
   if (degree < 0 || degree > BQA_MAX_DEGREE) return set_error("degree %d outside [0, %d]", degree, BQA_MAX_DEGREE);
@@ -50,11 +59,17 @@ int bqa_b200_version(void) { return 1; }
 long long bqa_b200_launch_count(void) { return g_launches.load(); }
 /* profiling aid, see include/bqa_b200.h */
 int bqa_b200_canon_stats(unsigned long long* out3) {
-  if (g_kernel_mode.load() == 2) canon8_stats(out3); else canon8v2_stats(out3);
+  if (g_kernel_mode.load() == 2) canon8_stats(out3);
+  else if (canon_variant() == 2) canon8v2_stats(out3);
+  else { unsigned long long o[7]; canon8v3_stats(o); out3[0] = o[0]; out3[1] = o[1]; out3[2] = o[2]; }
   return 0;
 }
 int bqa_b200_canon_stats_detail(unsigned long long* out7) {
-  canon8v2_stats_detail(out7);
+  if (canon_variant() == 2) canon8v2_stats_detail(out7); else canon8v3_stats(out7);
+  return 0;
+}
+int bqa_b200_set_bp_trace(void* device_buffer) {
+  fast::set_bp_trace(device_buffer);
   return 0;
 }
 int bqa_b200_set_barrier_timeout(double seconds) {
@@ -211,8 +226,11 @@ int bqa_b200_canonicalize_ordered(int prec, int D, long long L, const void* ext,
   if (int rc = check_shape(prec, 0, D)) return rc;
   if (n_cols < 1 || n_cols > 2 * D) return set_error("n_cols %d outside [1, %d]", n_cols, 2 * D);
   cudaStream_t st = (cudaStream_t)stream;
-  if (g_kernel_mode.load() == 0 && prec == BQA_C64 && D == 4)
-    return launch_fast_canon8v2(L, ext, canon, lmbds, colmax, pinv_eps, n_cols, order, cost, st);
+  if (g_kernel_mode.load() == 0 && prec == BQA_C64 && D == 4) {
+    if (canon_variant() == 2 || order || cost)                 // the edge-order experiment lives in the v2 layout
+      return launch_fast_canon8v2(L, ext, canon, lmbds, colmax, pinv_eps, n_cols, order, cost, st);
+    return launch_fast_canon8v3(L, ext, canon, lmbds, colmax, pinv_eps, n_cols, st);
+  }
   if (g_kernel_mode.load() == 2 && prec == BQA_C64 && D == 4)
     return launch_fast_canon8(L, ext, canon, lmbds, colmax, pinv_eps, n_cols, st);
   if (prec == BQA_C64) return launch_canonicalize<float>(D, L, ext, canon, lmbds, colmax, pinv_eps, st);

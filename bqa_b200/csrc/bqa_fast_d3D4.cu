@@ -512,6 +512,7 @@ struct RunArgs {
   uint4* peer_xchg[BQA_MAX_PEERS]; // every rank's handshake lines [2][BQA_MAX_PEERS] (peer mapped): 64 bytes into its flag buffer
   unsigned seq_base;               // cross-GPU sequence numbers seq_base + 1, + 2, ... (one per sweep)
   long long timeout_cycles;        // a peer that stays silent this long aborts the run (status[3])
+  unsigned long long* trace;       // profiling aid (bqa_b200_set_bp_trace): 5 globaltimer stamps per sweep from CTA 0, or null
 };
 
 __device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
@@ -523,6 +524,11 @@ __device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 }
 __device__ __forceinline__ void st_volatile_v4(uint4* p, uint4 v) {
   asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -566,11 +572,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_bp_run_d3D4(const __grid_consta
   unsigned* counter = reinterpret_cast<unsigned*>(a.status + 2);
   unsigned generation = 0;
   int sweeps = r.max_iters, converged = 0;
+  const bool tracing = r.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
   for (int it = 0; it < r.max_iters; ++it) {
     const int cur = (r.parity + it) & 1;
+    if (tracing) r.trace[5 * it] = globaltimer_ns();
     // cap reached: the undamped sweep is kept (state.py:122-123)
     sweep<false, MULTI>(a, r.msgs[cur], r.msgs[cur ^ 1], it, it == r.max_iters - 1, PeersOfRun{r, cur ^ 1}, smem);
+    if (tracing) r.trace[5 * it + 1] = globaltimer_ns();
     if (!grid_barrier(counter, generation, a.status, r.timeout_cycles)) return;
+    if (tracing) { r.trace[5 * it + 2] = globaltimer_ns(); r.trace[5 * it + 3] = r.trace[5 * it + 4] = r.trace[5 * it + 2]; }
     float num = __ldcg(a.resid + 2 * it), den = __ldcg(a.resid + 2 * it + 1);     // local maxima (barrier above)
     if (MULTI && r.world > 1) {
       // Cross-GPU handshake of the sweep, one 16-byte line per peer (the layout of NCCL's low-latency protocol: two
@@ -591,6 +601,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_bp_run_d3D4(const __grid_consta
         if (blockIdx.x == 0) {
           __threadfence_system();
           st_volatile_v4(r.peer_xchg[q] + slot + r.rank, make_uint4(__float_as_uint(num), seq, __float_as_uint(den), seq));
+          if (r.trace && q == (r.rank == 0 ? 1 : 0)) r.trace[5 * it + 3] = globaltimer_ns();
         }
         const uint4* mine = r.peer_xchg[r.rank] + slot + q;
         uint4 line = ld_volatile_v4(mine);
@@ -604,6 +615,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_bp_run_d3D4(const __grid_consta
         atomicMax(&s_max[1], line.z);
       }
       __syncthreads();
+      if (tracing) r.trace[5 * it + 4] = globaltimer_ns();
       if (*((volatile int32_t*)a.status + 3) != 0) return;
       num = __uint_as_float(s_max[0]);
       den = __uint_as_float(s_max[1]);
@@ -617,6 +629,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_bp_run_d3D4(const __grid_consta
   if (blockIdx.x == 0 && threadIdx.x == 0) { a.status[1] = sweeps; a.status[0] = converged; }
 }
 
+static unsigned long long* g_bp_trace = nullptr;            // device buffer of 5 * max_iters stamps, or null
+void set_bp_trace(void* p) { g_bp_trace = (unsigned long long*)p; }
 static long long g_timeout_cycles = 20000000000LL;          // ~10 s at 2 GHz
 long long barrier_timeout_cycles() { return g_timeout_cycles; }
 void set_barrier_timeout_cycles(long long c) { g_timeout_cycles = c > 0 ? c : 20000000000LL; }
@@ -661,6 +675,7 @@ int launch_fast_bp_run_d3D4(long long B, const void* T, void* msgs0, void* msgs1
   }
   (void)peer_resid;
   r.timeout_cycles = barrier_timeout_cycles();
+  r.trace = g_bp_trace;
   const long long groups = (B + 3) / 4;
   long long grid = (groups + kWarps - 1) / kWarps;
   if (grid > sm_count()) grid = sm_count();

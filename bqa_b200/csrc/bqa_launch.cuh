@@ -90,6 +90,7 @@ int launch_sweep_sync(int prec, int rank, int world, void* const* peer_resid, in
 namespace fast {
 long long barrier_timeout_cycles();
 void set_barrier_timeout_cycles(long long cycles);
+void set_bp_trace(void* device_buffer);
 }
 
 // specialised canonicalizer kernel (bqa_fast_canon8.cu): D = 4 (n = 8), complex64
@@ -102,6 +103,10 @@ int launch_fast_canon8v2(long long L, const void* ext, void* canon, void* lmbds,
                          int ncols, const int32_t* order, void* cost, cudaStream_t st);
 int launch_sort_edges_by_cost(long long L, const void* cost, int32_t* order, cudaStream_t st);
 void canon8v2_stats(unsigned long long* out3);
+// third layout (bqa_fast_canon8v3.cu): two lanes per matrix, 16 warps per SM
+int launch_fast_canon8v3(long long L, const void* ext, void* canon, void* lmbds, void* colmax, double pinv_eps,
+                         int ncols, cudaStream_t st);
+void canon8v3_stats(unsigned long long* out7);
 void canon8v2_stats_detail(unsigned long long* out7);
 
 }  // namespace bqa

@@ -46,6 +46,10 @@ int bqa_b200_set_kernel_mode(int mode);
 /* how long an in-kernel grid barrier or cross-GPU handshake waits before it gives up, sets status[3] (sticky: the engine
  * raises at its next read of the control block) and lets the kernel end; default about 10 s */
 int bqa_b200_set_barrier_timeout(double seconds);
+/* profiling aid: with a device buffer of 5 * max_iters uint64, CTA 0 of bqa_b200_bp_run writes per sweep the
+ * %globaltimer (ns) at: sweep start | its last group done | grid barrier passed | handshake line sent | every peer's
+ * line received.  NULL switches it off (default). */
+int bqa_b200_set_bp_trace(void* device_buffer);
 
 /* profiling aid: out3[0] = warp-level Jacobi problems (4 matrices each) solved by the n = 8 canonicalizer kernel
  * since load, out3[1] = Jacobi sweeps summed over them, out3[2] = the part of out3[1] spent on the SVD of ker

@@ -75,7 +75,35 @@ def main():
                               "ker_share_of_sweeps": (s1[2] - s0[2]) / max(s1[1] - s0[1], 1)}
         if det:
             out["mode0"]["mean_sweeps_per_matrix"] = {"eigen": det[3] / max(det[5], 1), "svd": det[4] / max(det[6], 1)}
+    # one launch after an idle second vs back to back (boost clocks?), with nvidia-smi samples during a 2 s loop
+    import subprocess, time as _t
     lib.set_kernel_mode(0)
+    iso = []
+    for _ in range(4):
+        torch.cuda.synchronize(); _t.sleep(1.0)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); call(); b.record(); torch.cuda.synchronize()
+        iso.append(a.elapsed_time(b))
+    out["mode0_single_launch_after_idle_ms"] = iso
+    try:
+        smi = subprocess.Popen(["nvidia-smi", "--query-gpu=clocks.sm,power.draw,clocks_event_reasons.active", "--format=csv,noheader",
+                                "-lms", "100"], stdout=subprocess.PIPE, text=True)
+        t0 = _t.time()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        nloop = 0
+        while _t.time() - t0 < 2.0:
+            for _ in range(50):
+                call()
+            nloop += 50
+            torch.cuda.synchronize()
+        b.record(); torch.cuda.synchronize()
+        smi.terminate()
+        lines = smi.stdout.read().strip().splitlines()
+        out["mode0_sustained_ms"] = a.elapsed_time(b) / nloop
+        out["smi_during_loop"] = lines[2:: max(len(lines) // 6, 1)][:8]
+    except Exception as e:
+        out["smi_error"] = repr(e)
     out["lambda_max_abs_diff"] = float(np.abs(res[0][1] - res[2][1]).max())
     out["colmax"] = [res[0][2].tolist(), res[2][2].tolist()]
     import subprocess

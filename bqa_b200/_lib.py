@@ -53,7 +53,7 @@ SIGNATURES = {
 EXPORTS = list(SIGNATURES) + ["bqa_b200_last_error", "bqa_b200_version", "bqa_b200_launch_count",
                               "bqa_b200_workspace_bytes", "bqa_b200_set_kernel_mode", "bqa_b200_canon_stats",
                               "bqa_b200_t_svd_scratch_bytes", "bqa_b200_canon_stats_detail",
-                              "bqa_b200_set_barrier_timeout", "bqa_b200_set_bp_trace"]
+                              "bqa_b200_set_barrier_timeout", "bqa_b200_set_bp_trace", "bqa_b200_canon_span"]
 
 
 _CUDA_ONLY = ("bqa_b200_canonicalize_ordered", "bqa_b200_sort_edges_by_cost")
@@ -130,6 +130,11 @@ class Library:
 
     def svd_scratch_bytes(self, prec: int, n: int) -> int:
         return int(self._dll.bqa_b200_t_svd_scratch_bytes(prec, n))
+
+    def canon_span(self) -> tuple[int, int]:
+        out = (C.c_ulonglong * 2)()
+        self._dll.bqa_b200_canon_span(out)
+        return int(out[0]), int(out[1])
 
     def canon_stats_detail(self) -> list[int]:
         out = (C.c_ulonglong * 7)()

@@ -68,6 +68,10 @@ int bqa_b200_canon_stats_detail(unsigned long long* out7) {
   if (canon_variant() == 2) canon8v2_stats_detail(out7); else canon8v3_stats(out7);
   return 0;
 }
+int bqa_b200_canon_span(unsigned long long* out2) {
+  canon8v2_span(out2);
+  return 0;
+}
 int bqa_b200_set_bp_trace(void* device_buffer) {
   fast::set_bp_trace(device_buffer);
   return 0;

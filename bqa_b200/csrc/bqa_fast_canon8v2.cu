@@ -55,6 +55,7 @@ static_assert(kSmem <= 227 * 1024, "shared memory budget");
 // its slowest matrix has converged), [2] the part of [1] spent on the SVD of ker
 // [3] / [4]: sweeps summed over the single matrices until each one froze, eigen phase / SVD phase ([5] / [6]: matrices)
 __device__ unsigned long long g_stats[7];
+__device__ unsigned long long g_span[2] = {~0ull, 0ull};   // profiling aid: earliest start / latest end (%globaltimer, ns) of the last launches
 
 struct Mat {                               // column j, row pair k = (rows 2k, 2k + 1): X = real parts, Y = imaginary parts
   p2 X[8][4], Y[8][4];
@@ -365,6 +366,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_canon8v2(long long L, const 
                                                              float* __restrict__ colmax, float pinv_eps, int ncols, int nphases,
                                                              const int* __restrict__ order, unsigned char* __restrict__ cost, float conv) {
   extern __shared__ __align__(16) unsigned char smem[];
+  unsigned long long t_start;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int pair = lane >> 1;
   const bool leader = (lane & 1) == 0;
@@ -600,6 +603,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_canon8v2(long long L, const 
       atomicAdd(&g_stats[3], se); atomicAdd(&g_stats[4], sk); atomicAdd(&g_stats[5], ne); atomicAdd(&g_stats[6], nk);
     }
   }
+  if (threadIdx.x == 0) {
+    unsigned long long t_end;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+    atomicMin(&g_span[0], t_start);
+    atomicMax(&g_span[1], t_end);
+  }
   if (lane == 0) {
     atomicAdd(&g_stats[0], (unsigned long long)n_jac);
     atomicAdd(&g_stats[1], (unsigned long long)n_sweeps);
@@ -614,6 +623,12 @@ void canon8v2_stats(unsigned long long* out3) {
 }
 void canon8v2_stats_detail(unsigned long long* out7) {
   cudaMemcpyFromSymbol(out7, canon8v2::g_stats, sizeof(unsigned long long) * 7);
+}
+// (start, end) of the launches since the last call, then reset
+void canon8v2_span(unsigned long long* out2) {
+  cudaMemcpyFromSymbol(out2, canon8v2::g_span, sizeof(unsigned long long) * 2);
+  const unsigned long long init[2] = {~0ull, 0ull};
+  cudaMemcpyToSymbol(canon8v2::g_span, init, sizeof(init));
 }
 
 // ---- counting sort of the edges by cost, descending (one block; keys are bytes; warp-aggregated shared-memory atomics)

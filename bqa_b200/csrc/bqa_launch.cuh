@@ -108,5 +108,6 @@ int launch_fast_canon8v3(long long L, const void* ext, void* canon, void* lmbds,
                          int ncols, cudaStream_t st);
 void canon8v3_stats(unsigned long long* out7);
 void canon8v2_stats_detail(unsigned long long* out7);
+void canon8v2_span(unsigned long long* out2);
 
 }  // namespace bqa

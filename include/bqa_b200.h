@@ -59,6 +59,9 @@ int bqa_b200_canon_stats(unsigned long long* out3);
  * one had converged (eigen phase / SVD phase), out7[5] / out7[6] = matrices: what a warp loses by sweeping until its
  * slowest matrix is done */
 int bqa_b200_canon_stats_detail(unsigned long long* out7);
+/* profiling aid: out2 = (earliest CTA start, latest CTA end) in %globaltimer ns over the n = 8 launches since the last
+ * call (resets; synchronises the device) */
+int bqa_b200_canon_span(unsigned long long* out2);
 
 /* bytes of device scratch the node kernels need for a degree class (pass the max over classes) */
 size_t bqa_b200_workspace_bytes(int prec, int degree, int D, int D_new);

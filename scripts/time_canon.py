@@ -85,6 +85,12 @@ def main():
         a.record(); call(); b.record(); torch.cuda.synchronize()
         iso.append(a.elapsed_time(b))
     out["mode0_single_launch_after_idle_ms"] = iso
+    lib.canon_span()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); call(); b.record(); torch.cuda.synchronize()
+    t0, t1 = lib.canon_span()
+    out["mode0_one_launch"] = {"event_ms": a.elapsed_time(b), "first_cta_start_to_last_cta_end_ms": (t1 - t0) / 1e6}
     try:
         smi = subprocess.Popen(["nvidia-smi", "--query-gpu=clocks.sm,power.draw,clocks_event_reasons.active", "--format=csv,noheader",
                                 "-lms", "100"], stdout=subprocess.PIPE, text=True)

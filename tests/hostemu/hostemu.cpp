@@ -159,6 +159,7 @@ int bqa_b200_set_kernel_mode(int) { return 0; }
 int bqa_b200_canon_stats(unsigned long long* o) { o[0] = o[1] = o[2] = 0; return 0; }
 int bqa_b200_set_barrier_timeout(double) { return 0; }
 int bqa_b200_set_bp_trace(void*) { return 0; }
+int bqa_b200_canon_span(unsigned long long* o) { o[0] = o[1] = 0; return 0; }
 int bqa_b200_canon_stats_detail(unsigned long long* o) { for (int i = 0; i < 7; ++i) o[i] = 0; return 0; }
 int bqa_b200_gauge_msgs(int prec, int D_old, int D_new, long long L, const void* lmbds, void* msgs_out, void*) {
   DISPATCH(gauge_msgs<float>(D_old, D_new, L, lmbds, msgs_out), gauge_msgs<double>(D_old, D_new, L, lmbds, msgs_out));

@@ -20,7 +20,7 @@ SIGNATURES = {
     "bqa_b200_sweep_sync": [_i, _i, _i, _vp, _i, _vp, C.c_uint, _vp, _vp],
     "bqa_b200_gauge_msgs": [_i, _i, _i, _ll, _vp, _vp, _vp],
     "bqa_b200_bp_run": [_i, _i, _i, _ll, _vp, _vp, _vp, _i, _vp, _vp, _d, _d, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp,
-                        C.c_uint, _vp],
+                        C.c_uint, _vp, _vp, _ll, _vp],
     "bqa_b200_bp_sweep": [_i, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp, _d, _i, _d, _i, _vp, _vp, _vp, _sz, _vp],
     "bqa_b200_ext_msgs": [_i, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _d, _vp, _sz, _vp],
     "bqa_b200_canonicalize": [_i, _i, _ll, _vp, _vp, _vp, _vp, _d, _i, _vp],

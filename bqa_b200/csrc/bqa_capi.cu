@@ -150,7 +150,7 @@ int bqa_b200_bp_run(int prec, int degree, int D, long long B, const void* T, voi
                     const int32_t* in_pos, const int32_t* out_pos, double damping, double bp_eps, int max_iters,
                     void* resid, int32_t* status, const int32_t* remote_pos, void* const* peers0, void* const* peers1,
                     int rank, int world, void* const* peer_resid, void* const* peer_flags, unsigned seq_base,
-                    void* stream) {
+                    void* msgs2, void* const* peers2, long long boundary_nodes, void* stream) {
   if (int rc = check_shape(prec, degree, D)) return rc;
   if (max_iters < 1) return set_error("max_iters must be positive, got %d", max_iters);
   if (g_kernel_mode.load() == 1 || !fast_d3D4_available(prec, degree, D, B)) {
@@ -158,8 +158,8 @@ int bqa_b200_bp_run(int prec, int degree, int D, long long B, const void* T, voi
     return 2;                                              /* not an error: the caller enqueues bqa_b200_bp_sweep calls */
   }
   return launch_fast_bp_run_d3D4(B, T, msgs0, msgs1, parity, in_pos, out_pos, damping, bp_eps, max_iters, resid, status,
-                                 remote_pos, peers0, peers1, rank, world, peer_resid, peer_flags, seq_base,
-                                 (cudaStream_t)stream);
+                                 remote_pos, peers0, peers1, rank, world, peer_resid, peer_flags, seq_base, msgs2, peers2,
+                                 boundary_nodes, (cudaStream_t)stream);
 }
 
 int bqa_b200_ext_msgs_classes(int prec, int n_classes, const bqa_b200_class* cls, int D, const void* msgs_cur, void* ext,

@@ -143,17 +143,19 @@ struct PeersOfArgs {
 };
 template <bool EXT, bool MULTI, class Peers>
 __device__ __forceinline__ void sweep(const Args& a, const float2* msgs_cur, float2* msgs_out, int it, int write_undamped,
-                                      const Peers peers, unsigned char* smem) {
+                                      const Peers peers, unsigned char* smem, int g_lo = 0, int g_hi = 0x7fffffff) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int s = lane >> 3, t = lane & 7, p = t >> 2, la = t & 3;     // node slot, lane in node, physical, leg-0 index
   unsigned char* wbase = smem + wib * kWarpBytes;
   unsigned char* scratch = wbase + 2 * kStage;
   const int B = (int)a.B;
-  const int groups = (B + 3) >> 2, tail0 = B - 4;
+  // groups [g_lo, g_hi) of the class (default: all of them; the multi-GPU run sweeps the boundary groups first)
+  const int groups = min((B + 3) >> 2, g_hi), tail0 = B - 4;
   const int nwarps = (int)gridDim.x * kWarps;
   // warp-major numbering: the groups of the last, partial round land on one warp each of as many CTAs as possible
   // (a lone warp runs much faster than eight sharing the SM) instead of filling all warps of a few CTAs
   int g = wib * (int)gridDim.x + (int)blockIdx.x;
+  if (g < g_lo) g += (g_lo - g + nwarps - 1) / nwarps * nwarps;
   // boundary messages are also stored into the peers' halo slots.  Compile-time in the BP kernels; the extended-message
   // kernel has ONE instantiation that tests the pointer (two instantiations contracted its epilogue arithmetic into FMAs
   // differently, and single- and multi-GPU runs must stay bit-identical)
@@ -505,8 +507,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_msgs_d3D4(const __grid_constant
 // residual and stops or goes on.  No kernel launch and no host round trip per sweep.
 struct RunArgs {
   Args base;                       // msgs_cur / msgs_out / peers / it / write_undamped are filled per sweep
-  float2* msgs[2];                 // ping-pong message buffers; sweep `it` reads msgs[(parity + it) & 1]
-  unsigned char* peers[2][BQA_MAX_PEERS];
+  float2* msgs[3];                 // message buffers; sweep `it` reads msgs[(parity + it) % nbuf], writes the next one
+  unsigned char* peers[3][BQA_MAX_PEERS];
+  int nbuf;                        // 2 on one GPU; 3 across GPUs (the convergence test lags one sweep, see k_bp_run_d3D4)
+  int boundary_groups;             // the first groups of the class hold every node with a remote out-edge
   int parity, max_iters;
   int rank, world;                 // world == 1: single GPU
   uint4* peer_xchg[BQA_MAX_PEERS]; // every rank's handshake lines [2][BQA_MAX_PEERS] (peer mapped): 64 bytes into its flag buffer
@@ -573,58 +577,111 @@ __global__ void __launch_bounds__(kThreads, 1) k_bp_run_d3D4(const __grid_consta
   unsigned generation = 0;
   int sweeps = r.max_iters, converged = 0;
   const bool tracing = r.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
-  for (int it = 0; it < r.max_iters; ++it) {
-    const int cur = (r.parity + it) & 1;
-    if (tracing) r.trace[5 * it] = globaltimer_ns();
-    // cap reached: the undamped sweep is kept (state.py:122-123)
-    sweep<false, MULTI>(a, r.msgs[cur], r.msgs[cur ^ 1], it, it == r.max_iters - 1, PeersOfRun{r, cur ^ 1}, smem);
-    if (tracing) r.trace[5 * it + 1] = globaltimer_ns();
-    if (!grid_barrier(counter, generation, a.status, r.timeout_cycles)) return;
-    if (tracing) { r.trace[5 * it + 2] = globaltimer_ns(); r.trace[5 * it + 3] = r.trace[5 * it + 4] = r.trace[5 * it + 2]; }
-    float num = __ldcg(a.resid + 2 * it), den = __ldcg(a.resid + 2 * it + 1);     // local maxima (barrier above)
-    if (MULTI && r.world > 1) {
-      // Cross-GPU handshake of the sweep, one 16-byte line per peer (the layout of NCCL's low-latency protocol: two
-      // 8-byte words, each carrying data and the sequence number, because only 8-byte stores are atomic over NVLink):
-      //   {max |new - old|^2, seq, max |new + old|^2, seq}  ->  peer q's line [it & 1][rank]
-      // CTA 0 sends -- after one system-scope fence that orders every local CTA's halo stores (made visible to it by the
-      // grid barrier) before the line; EVERY CTA polls its own copy of the peers' lines in local memory and folds their
-      // maxima into the global residual (get_dist is a ratio of two GLOBAL maxima, backends.py:492-495).  No remote
-      // atomics, no second grid barrier, and nothing of a peer's control block is written, so a BP run needs no barrier
-      // in front of it.  (Two lines per peer: a rank can be at most one sweep ahead of the slowest reader.)
-      const unsigned seq = r.seq_base + it + 1;
-      __shared__ unsigned s_max[2];
-      if (threadIdx.x == 0) { s_max[0] = __float_as_uint(num); s_max[1] = __float_as_uint(den); }
+  if (!(MULTI && r.world > 1)) {
+    for (int it = 0; it < r.max_iters; ++it) {
+      const int cur = (r.parity + it) & 1;
+      if (tracing) r.trace[5 * it] = globaltimer_ns();
+      // cap reached: the undamped sweep is kept (state.py:122-123)
+      sweep<false, MULTI>(a, r.msgs[cur], r.msgs[cur ^ 1], it, it == r.max_iters - 1, PeersOfRun{r, cur ^ 1}, smem);
+      if (tracing) r.trace[5 * it + 1] = globaltimer_ns();
+      if (!grid_barrier(counter, generation, a.status, r.timeout_cycles)) return;
+      if (tracing) { r.trace[5 * it + 2] = globaltimer_ns(); r.trace[5 * it + 3] = r.trace[5 * it + 4] = r.trace[5 * it + 2]; }
+      const float num = __ldcg(a.resid + 2 * it), den = __ldcg(a.resid + 2 * it + 1);
+      if (sqrtf(num / den) < a.bp_eps) { sweeps = it + 1; converged = 1; break; }
+    }
+  } else {
+    // ---- across GPUs -------------------------------------------------------------------------------------------------
+    // A sweep needs the peers' halo messages of the previous sweep, and the convergence test needs the peers' residual
+    // maxima (get_dist is a ratio of two GLOBAL maxima, backends.py:492-495).  Both travel as 16-byte lines in the
+    // layout of NCCL's low-latency protocol (two 8-byte words, each carrying data and the sequence number: only 8-byte
+    // stores are atomic over NVLink), and both are taken off the critical path:
+    //   * the nodes with a remote out-edge come FIRST in the class.  The CTA that is the last to finish its boundary
+    //     groups fences (system scope: every CTA fenced its own halo stores before it arrived) and sends the DATA line
+    //     of the sweep; the interior groups and the grid barrier run while it is in flight;
+    //   * the RESID line {max |new - old|^2, seq, max |new + old|^2, seq} is sent after the grid barrier and read ONE
+    //     SWEEP LATER: sweep it + 1 starts without knowing whether sweep it converged.  The sweeps rotate through THREE
+    //     message buffers, so the input of the converging sweep -- what the reference keeps (state.py:118-120) -- is
+    //     still intact when the test arrives; the price is one discarded sweep per BP run.
+    // No remote atomics, no second grid barrier, nothing of a peer's control block is written.
+    unsigned* bcount = reinterpret_cast<unsigned*>(a.resid + 2 * r.max_iters);     // zeroed with the residuals
+    const int groups = (int)((a.B + 3) >> 2);
+    const int gb = min(r.boundary_groups, groups);
+    __shared__ unsigned s_max[2];
+    __shared__ int s_abort;
+    auto fold_resid = [&](int k) -> bool {                   // global residual of sweep k; true = converged
+      const unsigned seq = r.seq_base + k + 1;
+      if (threadIdx.x == 0) {
+        s_max[0] = __float_as_uint(__ldcg(a.resid + 2 * k));
+        s_max[1] = __float_as_uint(__ldcg(a.resid + 2 * k + 1));
+        s_abort = 0;
+      }
       __syncthreads();
       if (threadIdx.x < r.world && (int)threadIdx.x != r.rank) {
-        const int q = threadIdx.x;
-        const int slot = (it & 1) * BQA_MAX_PEERS;
-        if (blockIdx.x == 0) {
-          __threadfence_system();
-          st_volatile_v4(r.peer_xchg[q] + slot + r.rank, make_uint4(__float_as_uint(num), seq, __float_as_uint(den), seq));
-          if (r.trace && q == (r.rank == 0 ? 1 : 0)) r.trace[5 * it + 3] = globaltimer_ns();
-        }
-        const uint4* mine = r.peer_xchg[r.rank] + slot + q;
+        const uint4* mine = r.peer_xchg[r.rank] + (4 + (k & 3)) * BQA_MAX_PEERS + threadIdx.x;
         uint4 line = ld_volatile_v4(mine);
         const long long t0 = clock64();
         while (line.y != seq || line.w != seq) {
-          if (*((volatile int32_t*)a.status + 3) != 0 || clock64() - t0 > r.timeout_cycles) { a.status[3] = 1; break; }
+          if (*((volatile int32_t*)a.status + 3) != 0 || clock64() - t0 > r.timeout_cycles) { a.status[3] = 1; s_abort = 1; break; }
           line = ld_volatile_v4(mine);
         }
-        __threadfence_system();                             // the peer's halo stores are ordered before its line
         atomicMax(&s_max[0], line.x);                       // non-negative reals order like their bit patterns
         atomicMax(&s_max[1], line.z);
       }
       __syncthreads();
+      const float num = __uint_as_float(s_max[0]), den = __uint_as_float(s_max[1]);
+      if (blockIdx.x == 0 && threadIdx.x == 0) { a.resid[2 * k] = num; a.resid[2 * k + 1] = den; }   // the host reads the GLOBAL one
+      return sqrtf(num / den) < a.bp_eps;
+    };
+    for (int it = 0; it < r.max_iters; ++it) {
+      const int cur = (r.parity + it) % r.nbuf, nxt = (cur + 1) % r.nbuf;
+      const unsigned seq = r.seq_base + it + 1;
+      const int undamped = it == r.max_iters - 1;
+      if (tracing) r.trace[5 * it] = globaltimer_ns();
+      // 1. boundary groups; the last CTA to finish them sends the DATA lines
+      sweep<false, MULTI>(a, r.msgs[cur], r.msgs[nxt], it, undamped, PeersOfRun{r, nxt}, smem, 0, gb);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence_system();                             // this CTA's halo stores, system-wide, before its arrival
+        const unsigned arrived = atomicAdd(bcount, 1u);
+        if (arrived == (unsigned)(it + 1) * gridDim.x - 1u) {
+          __threadfence_system();
+          for (int q = 0; q < r.world; ++q)
+            if (q != r.rank) st_volatile_v4(r.peer_xchg[q] + (it & 3) * BQA_MAX_PEERS + r.rank, make_uint4(seq, seq, seq, seq));
+        }
+      }
+      if (tracing) r.trace[5 * it + 1] = globaltimer_ns();
+      // 2. interior groups, grid barrier (local messages and local residual of the sweep complete)
+      sweep<false, MULTI>(a, r.msgs[cur], r.msgs[nxt], it, undamped, PeersOfRun{r, nxt}, smem, gb, groups);
+      if (!grid_barrier(counter, generation, a.status, r.timeout_cycles)) return;
+      if (tracing) r.trace[5 * it + 2] = globaltimer_ns();
+      // 3. RESID line of this sweep (read by the peers one sweep later)
+      if (blockIdx.x == 0 && threadIdx.x < r.world && (int)threadIdx.x != r.rank) {
+        const unsigned num = __float_as_uint(__ldcg(a.resid + 2 * it)), den = __float_as_uint(__ldcg(a.resid + 2 * it + 1));
+        st_volatile_v4(r.peer_xchg[threadIdx.x] + (4 + (it & 3)) * BQA_MAX_PEERS + r.rank, make_uint4(num, seq, den, seq));
+      }
+      if (tracing) r.trace[5 * it + 3] = globaltimer_ns();
+      // 4. the peers' halo messages of this sweep must have landed before the next sweep reads them
+      if (threadIdx.x < r.world && (int)threadIdx.x != r.rank) {
+        const uint4* mine = r.peer_xchg[r.rank] + (it & 3) * BQA_MAX_PEERS + threadIdx.x;
+        uint4 line = ld_volatile_v4(mine);
+        const long long t0 = clock64();
+        while (line.x != seq || line.w != seq) {
+          if (*((volatile int32_t*)a.status + 3) != 0 || clock64() - t0 > r.timeout_cycles) { a.status[3] = 1; break; }
+          line = ld_volatile_v4(mine);
+        }
+        __threadfence_system();                             // the peer's halo stores are ordered before its line
+      }
+      __syncthreads();
       if (tracing) r.trace[5 * it + 4] = globaltimer_ns();
       if (*((volatile int32_t*)a.status + 3) != 0) return;
-      num = __uint_as_float(s_max[0]);
-      den = __uint_as_float(s_max[1]);
-      if (blockIdx.x == 0 && threadIdx.x == 0) {            // the host reads the GLOBAL residual of the last sweep
-        a.resid[2 * it] = num;
-        a.resid[2 * it + 1] = den;
-      }
+      // 5. convergence test of the PREVIOUS sweep
+      if (it >= 1 && fold_resid(it - 1)) { sweeps = it; converged = 1; break; }
+      if (*((volatile int32_t*)a.status + 3) != 0) return;
     }
-    if (sqrtf(num / den) < a.bp_eps) { sweeps = it + 1; converged = 1; break; }
+    if (!converged) {                                        // the last sweep's own test (cap reached or not)
+      if (fold_resid(r.max_iters - 1)) { sweeps = r.max_iters; converged = 1; }
+      if (*((volatile int32_t*)a.status + 3) != 0) return;
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) { a.status[1] = sweeps; a.status[0] = converged; }
 }
@@ -648,7 +705,7 @@ int launch_fast_bp_run_d3D4(long long B, const void* T, void* msgs0, void* msgs1
                             const int32_t* out_pos, double damping, double bp_eps, int max_iters, void* resid,
                             int32_t* status, const int32_t* remote_pos, void* const* peers0, void* const* peers1, int rank,
                             int world, void* const* peer_resid, void* const* peer_flags, unsigned seq_base,
-                            cudaStream_t st) {
+                            void* msgs2, void* const* peers2, long long boundary_nodes, cudaStream_t st) {
   using namespace fast;
   if (B == 0) return 0;
   if (world < 1 || world > BQA_MAX_PEERS) return set_error("bp_run: world %d outside [1, %d]", world, BQA_MAX_PEERS);
@@ -666,11 +723,16 @@ int launch_fast_bp_run_d3D4(long long B, const void* T, void* msgs0, void* msgs1
   a.B = B; a.T = (const float2*)T; a.in_pos = in_pos; a.out_pos = out_pos;
   a.damping = (float)damping; a.bp_eps = (float)bp_eps; a.resid = (float*)resid; a.status = status;
   a.remote_pos = (world > 1 && peers0 && peers1) ? remote_pos : nullptr;
-  r.msgs[0] = (float2*)msgs0; r.msgs[1] = (float2*)msgs1;
-  r.parity = parity & 1; r.max_iters = max_iters; r.rank = rank; r.world = world; r.seq_base = seq_base;
+  r.msgs[0] = (float2*)msgs0; r.msgs[1] = (float2*)msgs1; r.msgs[2] = (float2*)msgs2;
+  r.nbuf = world > 1 ? 3 : 2;
+  if (world > 1 && (!msgs2 || !peers2)) return set_error("bp_run: the multi-GPU run needs a third message buffer");
+  if (boundary_nodes < 0 || boundary_nodes > B) return set_error("bp_run: %lld boundary nodes of %lld", boundary_nodes, B);
+  r.boundary_groups = (int)((boundary_nodes + 3) / 4);
+  r.parity = world > 1 ? ((parity % 3) + 3) % 3 : (parity & 1); r.max_iters = max_iters; r.rank = rank; r.world = world; r.seq_base = seq_base;
   for (int q = 0; q < BQA_MAX_PEERS; ++q) {
     r.peers[0][q] = (a.remote_pos && peers0) ? (unsigned char*)peers0[q] : nullptr;
     r.peers[1][q] = (a.remote_pos && peers1) ? (unsigned char*)peers1[q] : nullptr;
+    r.peers[2][q] = (a.remote_pos && peers2) ? (unsigned char*)peers2[q] : nullptr;
     r.peer_xchg[q] = (world > 1 && q < world) ? (uint4*)((unsigned char*)peer_flags[q] + 64) : nullptr;
   }
   (void)peer_resid;

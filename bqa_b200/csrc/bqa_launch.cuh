@@ -69,7 +69,7 @@ int launch_fast_bp_run_d3D4(long long B, const void* T, void* msgs0, void* msgs1
                             const int32_t* out_pos, double damping, double bp_eps, int max_iters, void* resid,
                             int32_t* status, const int32_t* remote_pos, void* const* peers0, void* const* peers1, int rank,
                             int world, void* const* peer_resid, void* const* peer_flags, unsigned seq_base,
-                            cudaStream_t st);
+                            void* msgs2, void* const* peers2, long long boundary_nodes, cudaStream_t st);
 // symmetric-gauge messages of every slot, msgs[p] = diag(lambda[p mod L][:Dn]) / trace      (state.py:56-57)
 template <typename R>
 int launch_gauge_msgs(int D_old, int Dn, long long L, const void* lmbds, void* msgs_out, cudaStream_t st);

@@ -154,7 +154,10 @@ class Engine:
                 T=[torch.zeros(elems, dtype=self.cdtype, device=self.dev) for _ in range(2)],
                 node_ids_host=ids))
         Dm = self.Dmax
-        self._msgs = [self._alloc_shared(self.E2 * Dm * Dm, self.cdtype, f"msgs{i}") for i in range(2)]
+        # message buffers the BP sweeps rotate through: 2 (read one, write the other); 3 in the partitioned engine's
+        # peer-memory mode, where the convergence test lags one sweep (bqa_b200_bp_run)
+        self._nbuf = self._n_msg_buffers()
+        self._msgs = [self._alloc_shared(self.E2 * Dm * Dm, self.cdtype, f"msgs{i}") for i in range(self._nbuf)]
         self._msgs_cur = 0
         self._ext = None         # allocated on first simple update (size depends on the largest D reached)
         self._canon = None
@@ -163,7 +166,7 @@ class Engine:
         # control block, read back with ONE copy per chunk of sweeps (one per step in the steady state):
         # [resid (max_iters, 2) reals | status int32 x4 | column maxima of the lambdas (2 Dmax reals)]
         rsize = 4 if self.precision == "single" else 8
-        rbytes = ((max(self.max_iters, 1) * 2 * rsize) + 15) // 16 * 16
+        rbytes = (((max(self.max_iters, 1) + 2) * 2 * rsize) + 15) // 16 * 16      # + 2 rows: counters of bqa_b200_bp_run
         cbytes = (2 * Dm * rsize + 15) // 16 * 16
         self._ctrl = self._alloc_shared(rbytes + 16 + cbytes, torch.uint8, "ctrl")
         self._ctrl_rbytes = rbytes
@@ -201,6 +204,9 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     # plumbing
     # ------------------------------------------------------------------------------------------
+    def _n_msg_buffers(self) -> int:
+        return 2
+
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.dev).cuda_stream if self.cuda else 0
 
@@ -374,10 +380,11 @@ class Engine:
 
     def _enqueue_sweep(self, it: int, write_undamped: bool) -> None:
         D = self.D
-        cur = self._msgs[(self._msgs_cur + it) % 2]
-        nxt = self._msgs[(self._msgs_cur + it + 1) % 2]
+        nb = self._nbuf
+        cur = self._msgs[(self._msgs_cur + it) % nb]
+        nxt = self._msgs[(self._msgs_cur + it + 1) % nb]
         st = self._stream()
-        peers = self._peer_targets("msgs", (self._msgs_cur + it + 1) % 2)
+        peers = self._peer_targets("msgs", (self._msgs_cur + it + 1) % nb)
         for c in self.classes:
             if c.degree == 0:
                 continue
@@ -403,8 +410,9 @@ class Engine:
         """Hook for the partitioned engine (orders the control-block reset against the peers' residual pushes)."""
 
     def _bp_run_peers(self):
-        """(rank, world, peers0, peers1, peer_resid, peer_flags, seq_base) of the single-launch BP run; one GPU here."""
-        return 0, 1, None, None, None, None, 0
+        """(rank, world, peers0, peers1, peer_resid, peer_flags, seq_base, peers2, boundary nodes) of the single-launch BP
+        run; one GPU here."""
+        return 0, 1, None, None, None, None, 0, None, 0
 
     def _bp_run_done(self, sweeps: int) -> None:
         """Hook for the partitioned engine (advances the cross-GPU barrier sequence)."""
@@ -433,11 +441,13 @@ class Engine:
         peers = self._bp_run_peers()
         if peers is None:
             return None
-        rank, world, p0, p1, presid, pflags, seq = peers
+        rank, world, p0, p1, presid, pflags, seq, p2, n_boundary = peers
+        m2 = self._msgs[2].data_ptr() if self._nbuf > 2 else None
         ok = self.lib.bp_run(self.prec, c.degree, self.D, c.B, c.T[c.cur].data_ptr(), self._msgs[0].data_ptr(),
                              self._msgs[1].data_ptr(), self._msgs_cur, c.in_pos.data_ptr(), c.out_pos.data_ptr(),
                              self.damping, self.bp_eps, self.max_iters, self._resid.data_ptr(), self._status.data_ptr(),
-                             c.remote_pos.data_ptr(), p0, p1, rank, world, presid, pflags, seq, self._stream())
+                             c.remote_pos.data_ptr(), p0, p1, rank, world, presid, pflags, seq, m2, p2, n_boundary,
+                             self._stream())
         if not ok:
             self._no_bp_run[self.D] = True
             return None
@@ -497,11 +507,11 @@ class Engine:
             raise FloatingPointError(f"BP residual is not finite ({dist}) after {sweeps} sweeps: the state holds NaN/Inf")
         if done:
             # converged: keep the *input* of the converging sweep (state.py:118-120)
-            self._msgs_cur = (self._msgs_cur + sweeps - 1) % 2
+            self._msgs_cur = (self._msgs_cur + sweeps - 1) % self._nbuf
             log.debug(f"BP algorithm completed after {sweeps - 1} iterations")
         else:
             # cap reached: the last, undamped sweep output becomes the state (state.py:122-124)
-            self._msgs_cur = (self._msgs_cur + max_it) % 2
+            self._msgs_cur = (self._msgs_cur + max_it) % self._nbuf
             log.warning(f"BP algorithm exceeds iterations limit set to {max_it}, obtained bp_eps {dist}")
         self.stats["bp_sweeps"].append(sweeps)
         self.stats["bp_dist"].append(dist)

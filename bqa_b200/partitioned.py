@@ -205,6 +205,7 @@ class ExchangePlan:
     n_local_edges: int
     n_cut_edges: int
     max_local_edges: int = 0          # over all ranks (symmetric buffers are sized for it)
+    n_boundary_nodes: dict = None     # degree -> owned nodes with a remote out-edge (they come first in the class)
 
 
 def build_local_context(ctx: Context, part: np.ndarray, rank: int, world: int):
@@ -248,19 +249,27 @@ def build_local_context(ctx: Context, part: np.ndarray, rank: int, world: int):
     gid2lid = np.full(part.shape[0], -1, np.int64)
     gid2lid[owned] = np.arange(owned.size)
     layouts = {}
+    n_boundary = {}
     for d, lay in ctx.degree_to_layout.items():
         ids = _np(lay.node_ids).astype(np.int64)
         m = part[ids] == rank
         if not m.any():
             continue
         d = int(d)
-        sel = lambda a: _np(a).reshape(d, -1)[:, m]
+        # owned nodes of the class, those with a remote out-edge FIRST (stable): the single-launch BP run sweeps them
+        # first and sends its "halo ready" line while the interior nodes are still being swept
+        rem = remote(_np(lay.output_msgs_position).reshape(d, -1)[:, m]) if d > 0 else np.zeros((0, int(m.sum())), np.int64)
+        is_b = (rem >= 0).any(axis=0) if d > 0 else np.zeros(int(m.sum()), bool)
+        order = np.argsort(~is_b, kind="stable")
+        n_boundary[d] = int(is_b.sum())
+        sel = lambda a, order=order, m=m, d=d: _np(a).reshape(d, -1)[:, m][:, order]
+        sel1 = lambda a, order=order, m=m: np.asarray(a)[m][order]
         layouts[d] = Layout(
-            node_ids=gid2lid[ids[m]],
+            node_ids=gid2lid[sel1(ids)],
             input_msgs_position=slot(sel(lay.input_msgs_position)),
             output_msgs_position=slot(sel(lay.output_msgs_position)),
             lmbds_position=g2l[np.asarray(sel(lay.lmbds_position), np.int64)],
-            node_ampls=np.real(_np(lay.node_ampls))[m], edge_ampls=np.real(sel(lay.edge_ampls)),
+            node_ampls=sel1(np.real(_np(lay.node_ampls))), edge_ampls=np.real(sel(lay.edge_ampls)),
             remote_msgs_position=remote(sel(lay.output_msgs_position)))
     # boundary messages: forward position e is lhs -> rhs, backward position e + L is rhs -> lhs
     cut = np.flatnonzero(local_edge & (pl != pr))
@@ -276,7 +285,7 @@ def build_local_context(ctx: Context, part: np.ndarray, rank: int, world: int):
     plan = ExchangePlan(rank=rank, world=world, owned=owned, max_local_edges=max(L_all),
                         send_slots={q: slot(np.sort(np.array(v))) for q, v in send.items()},
                         recv_slots={q: slot(np.sort(np.array(v))) for q, v in recv.items()},
-                        n_local_edges=Lr, n_cut_edges=int(cut.size))
+                        n_local_edges=Lr, n_cut_edges=int(cut.size), n_boundary_nodes=n_boundary)
     local = replace(ctx, nodes_number=int(owned.size), edges_number=2 * Lr, degree_to_layout=layouts,
                     edges=E[le], couplings=np.asarray(ctx.couplings)[le], fields=np.asarray(ctx.fields)[owned],
                     node_degree=None, node_slot=None)
@@ -346,13 +355,17 @@ class PartitionedEngine(Engine):
         if self.p2p:
             self._ensure_edge_buffers(self.Dmax)              # symmetric allocations are collective: do them all now
             # 64 bytes of per-peer barrier flags (bqa_b200_sweep_sync) + the handshake lines of the single-launch BP run
-            self._flags = self._alloc_shared(64 + 2 * 16 * 8, torch.uint8, "flags")
+            self._flags = self._alloc_shared(64 + 8 * 16 * 8, torch.uint8, "flags")
             ptrs = lambda tag: (C.c_void_p * 8)(*([int(x) for x in self._symm[tag][1].buffer_ptrs] + [0] * (8 - self.world)))
-            self._peer_ptrs = {("msgs", 0): ptrs("msgs0"), ("msgs", 1): ptrs("msgs1"), ("ext", 0): ptrs("ext"),
+            self._peer_ptrs = {("msgs", 0): ptrs("msgs0"), ("msgs", 1): ptrs("msgs1"), ("msgs", 2): ptrs("msgs2"),
+                               ("ext", 0): ptrs("ext"),
                                "ctrl": ptrs("ctrl"), "flags": ptrs("flags")}
             dist.barrier(group=self.group)
         log.info(f"rank {self.rank}/{self.world}: {plan.owned.size} nodes, {plan.n_local_edges} local edges, "
                  f"{plan.n_cut_edges} cut, transport {'peer memory' if self.p2p else 'torch.distributed'}")
+
+    def _n_msg_buffers(self) -> int:
+        return 3 if self.p2p else 2
 
     # -- symmetric memory ------------------------------------------------------------------------------
     def _alloc_shared(self, numel: int, dtype, tag: str) -> torch.Tensor:
@@ -385,10 +398,13 @@ class PartitionedEngine(Engine):
         if not self.p2p:
             return None                # the torch.distributed transport exchanges between sweeps: no single launch
         pp = self._peer_ptrs
-        return self.rank, self.world, pp[("msgs", 0)], pp[("msgs", 1)], pp["ctrl"], pp["flags"], self._seq
+        active = [c for c in self.classes if c.degree > 0 and c.B > 0]
+        n_boundary = int((self.plan.n_boundary_nodes or {}).get(active[0].degree, active[0].B)) if active else 0
+        return (self.rank, self.world, pp[("msgs", 0)], pp[("msgs", 1)], pp["ctrl"], pp["flags"], self._seq,
+                pp[("msgs", 2)], n_boundary)
 
     def _bp_run_done(self, sweeps: int) -> None:
-        self._seq += sweeps            # one cross-GPU barrier per executed sweep, same count on every rank
+        self._seq += self.max_iters + 1    # sequence numbers a run may have used (one per executed sweep, <= max + 1)
 
     def _before_bp(self) -> None:
         # per-sweep launches: nobody pushes residuals of the new run before everybody has reset its control block.

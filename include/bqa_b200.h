@@ -112,22 +112,26 @@ int bqa_b200_ext_msgs_p2p(int prec, int degree, int D, long long B, const void* 
 int bqa_b200_sweep_sync(int prec, int rank, int world, void* const* peer_resid, int it, void* const* peer_flags,
                         unsigned seq, int32_t* status, void* stream);
 /* The whole BP run of a degree class in ONE cooperative launch (reference _run_bp, state.py:97-124): persistent CTAs
- * iterate sweep -> grid barrier -> (world > 1: cross-GPU handshake, below) -> global residual test.
- * Sweep `it` reads msgs{(parity + it) & 1} and writes the other buffer; on return status[0] = converged (0 / 1),
- * status[1] = number of sweeps executed; status[2] (grid-barrier counter) and resid must be zero before the call.
- * Only for graphs whose nodes all sit in ONE degree class that has a specialised kernel; returns 2 (and changes
- * nothing) when there is none -- the caller then enqueues bqa_b200_bp_sweep[_p2p] calls.  peers0/peers1 = peer bases
- * of the two message buffers.  Cross-GPU handshake of a sweep: CTA 0 stores ONE 16-byte line {max |new - old|^2, seq,
- * max |new + old|^2, seq} into every peer (after a system-scope fence behind the grid barrier: the halo stores come
- * first), every CTA polls the peers' lines in local memory and folds their maxima into the global residual.  The
- * lines live 64 bytes into each rank's flag buffer: peer_flags[q] must point to at least 64 + 2 * 16 *
- * BQA_B200_MAX_PEERS zero-initialised bytes; sequence numbers used: seq_base + 1 ... seq_base + status[1].  Nothing of a
- * peer's control block is written (peer_resid is unused), so no barrier is needed in front of a run. */
+ * iterate sweep -> grid barrier -> residual test on the device.  On return status[0] = converged (0 / 1), status[1] =
+ * the reference's sweep count; status[2] (grid-barrier counter) and resid -- (max_iters + 2) x 2 reals, the tail is used
+ * as a counter -- must be zero before the call.  Only for graphs whose nodes all sit in ONE degree class that has a
+ * specialised kernel; returns 2 (and changes nothing) when there is none -- the caller then enqueues
+ * bqa_b200_bp_sweep[_p2p] calls.
+ *   world == 1: sweep `it` reads msgs{(parity + it) & 1} and writes the other buffer (msgs2 / peers* unused).
+ *   world > 1: THREE message buffers, sweep `it` reads msgs{(parity + it) % 3} and writes the next one; peers0/1/2 =
+ *   peer bases of the three buffers; the first `boundary_nodes` nodes of the class are those with a remote out-edge.
+ *   Per sweep: boundary groups first; the last CTA to finish them fences and sends a 16-byte DATA line to every peer;
+ *   interior groups and the grid barrier run while it is in flight; the RESID line {max |new - old|^2, seq,
+ *   max |new + old|^2, seq} follows the barrier and is read by the peers ONE SWEEP LATER (the convergence test lags one
+ *   sweep: the third buffer keeps the input of the converging sweep intact, one sweep per run is discarded).  The lines
+ *   live 64 bytes into each rank's flag buffer: peer_flags[q] must point to at least 64 + 8 * 16 * BQA_B200_MAX_PEERS
+ *   zero-initialised bytes; sequence numbers seq_base + 1 ... seq_base + max_iters + 1 are used.  Nothing of a peer's
+ *   control block is written (peer_resid is unused), so no barrier is needed in front of a run. */
 int bqa_b200_bp_run(int prec, int degree, int D, long long B, const void* T, void* msgs0, void* msgs1, int parity,
                     const int32_t* in_pos, const int32_t* out_pos, double damping, double bp_eps, int max_iters,
                     void* resid, int32_t* status, const int32_t* remote_pos, void* const* peers0, void* const* peers1,
                     int rank, int world, void* const* peer_resid, void* const* peer_flags, unsigned seq_base,
-                    void* stream);
+                    void* msgs2, void* const* peers2, long long boundary_nodes, void* stream);
 /* msgs_out[p] = diag(lmbds[p mod L][:D_new]) / trace for every slot p < 2L (state.py:56-57); lmbds: real (L, 2 D_old) */
 int bqa_b200_gauge_msgs(int prec, int D_old, int D_new, long long L, const void* lmbds, void* msgs_out, void* stream);
 

@@ -172,7 +172,7 @@ int bqa_b200_ext_msgs_p2p(int, int, int, long long, const void*, const void*, vo
 int bqa_b200_sweep_sync(int, int, int, void* const*, int, void* const*, unsigned, int32_t*, void*) { return no_p2p(); }
 int bqa_b200_bp_run(int, int, int, long long, const void*, void*, void*, int, const int32_t*, const int32_t*, double, double,
                     int, void*, int32_t*, const int32_t*, void* const*, void* const*, int, int, void* const*, void* const*,
-                    unsigned, void*) { return 2; }        // "no single-launch kernel": the engine enqueues sweeps
+                    unsigned, void*, void* const*, long long, void*) { return 2; }   // "no single-launch kernel": the engine enqueues sweeps
 size_t bqa_b200_workspace_bytes(int, int, int, int) { return 16; }
 
 int bqa_b200_bp_sweep(int prec, int degree, int D, long long B, const void* T, const void* msgs_cur, void* msgs_nxt,

@@ -26,6 +26,7 @@ SIGNATURES = {
     "bqa_b200_canonicalize": [_i, _i, _ll, _vp, _vp, _vp, _vp, _d, _i, _vp],
     "bqa_b200_canonicalize_ordered": [_i, _i, _ll, _vp, _vp, _vp, _vp, _d, _i, _vp, _vp, _vp],
     "bqa_b200_sort_edges_by_cost": [_ll, _vp, _vp, _vp],
+    "bqa_b200_canonicalize_p2p": [_i, _i, _ll, _vp, _vp, _vp, _vp, _d, _i, _ll, _vp, _vp, _vp, _vp, _vp, _vp],
     "bqa_b200_apply_update": [_i, _i, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _vp, _sz, _vp],
     "bqa_b200_density": [_i, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp],
     "bqa_b200_argmax_unmeasured": [_i, _ll, _vp, _vp, _vp, _vp, _vp],
@@ -56,7 +57,7 @@ EXPORTS = list(SIGNATURES) + ["bqa_b200_last_error", "bqa_b200_version", "bqa_b2
                               "bqa_b200_set_barrier_timeout", "bqa_b200_set_bp_trace", "bqa_b200_canon_span"]
 
 
-_CUDA_ONLY = ("bqa_b200_canonicalize_ordered", "bqa_b200_sort_edges_by_cost")
+_CUDA_ONLY = ("bqa_b200_canonicalize_ordered", "bqa_b200_sort_edges_by_cost", "bqa_b200_canonicalize_p2p")
 
 
 class ClassDesc(C.Structure):

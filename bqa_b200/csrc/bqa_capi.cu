@@ -221,6 +221,18 @@ int bqa_b200_canonicalize(int prec, int D, long long L, const void* ext, void* c
   return bqa_b200_canonicalize_ordered(prec, D, L, ext, canon, lmbds, colmax, pinv_eps, n_cols, nullptr, nullptr, stream);
 }
 
+int bqa_b200_canonicalize_p2p(int prec, int D, long long L, const void* ext, void* canon, void* lmbds, void* colmax,
+                              double pinv_eps, int n_cols, long long n_owned, const int32_t* owned, const int32_t* remote,
+                              void* const* peer_canon, void* const* peer_lmbds, const long long* peer_L, void* stream) {
+  if (int rc = check_shape(prec, 0, D)) return rc;
+  if (n_cols < 1 || n_cols > 2 * D) return set_error("n_cols %d outside [1, %d]", n_cols, 2 * D);
+  if (g_kernel_mode.load() == 0 && prec == BQA_C64 && D == 4 && owned && remote)
+    return launch_fast_canon8v2(L, ext, canon, lmbds, colmax, pinv_eps, n_cols, owned, nullptr, (cudaStream_t)stream, n_owned,
+                                remote, peer_canon, peer_lmbds, peer_L);
+  // no single-owner path for this shape: every rank decomposes all of its local edges (identical results)
+  return bqa_b200_canonicalize(prec, D, L, ext, canon, lmbds, colmax, pinv_eps, n_cols, stream);
+}
+
 int bqa_b200_sort_edges_by_cost(long long L, const void* cost, int32_t* order, void* stream) {
   return launch_sort_edges_by_cost(L, cost, order, (cudaStream_t)stream);
 }

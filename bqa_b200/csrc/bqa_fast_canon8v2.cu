@@ -57,6 +57,15 @@ static_assert(kSmem <= 227 * 1024, "shared memory budget");
 __device__ unsigned long long g_stats[7];
 __device__ unsigned long long g_span[2] = {~0ull, 0ull};   // profiling aid: earliest start / latest end (%globaltimer, ns) of the last launches
 
+// Multi-GPU, one owner per cut edge (bqa_b200_canonicalize_p2p): the owner stores the edge's canonicalizers and lambdas
+// into the other endpoint's rank as well.  remote[e] = -1 or (peer << 27 | that rank's index of the edge).
+struct Remote {
+  const int* code;                          // per local edge, or null
+  float2* canon[BQA_MAX_PEERS];             // peer-mapped bases of the ranks' canonicalizer arrays
+  float* lmbds[BQA_MAX_PEERS];
+  long long L[BQA_MAX_PEERS];               // local edge counts of the ranks (slot of C_f = index + L)
+};
+
 struct Mat {                               // column j, row pair k = (rows 2k, 2k + 1): X = real parts, Y = imaginary parts
   p2 X[8][4], Y[8][4];
 };
@@ -361,10 +370,12 @@ __device__ __forceinline__ void inv_col_norms(const unsigned char* m, float (&in
   for (int j = 0; j < 8; ++j) inv[j] = w[j] > 0.f ? 1.f / w[j] : 0.f;
 }
 
-__global__ void __launch_bounds__(kWarps * 32, 1) k_canon8v2(long long L, const float2* __restrict__ ext,
+// n edges are processed: order[0 .. n) (or 0 .. n - 1 without `order`); L = local edge count (slot of m_b / C_f = e + L)
+__global__ void __launch_bounds__(kWarps * 32, 1) k_canon8v2(long long n, long long L, const float2* __restrict__ ext,
                                                              float2* __restrict__ canon, float* __restrict__ lmbds,
                                                              float* __restrict__ colmax, float pinv_eps, int ncols, int nphases,
-                                                             const int* __restrict__ order, unsigned char* __restrict__ cost, float conv) {
+                                                             const int* __restrict__ order, unsigned char* __restrict__ cost, float conv,
+                                                             const __grid_constant__ Remote rem) {
   extern __shared__ __align__(16) unsigned char smem[];
   unsigned long long t_start;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
@@ -375,7 +386,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_canon8v2(long long L, const 
   unsigned char* F = wbase + pair * kPair;                  // A_f (published), needed until the epilogue
   unsigned char* Bm = F + kMat;                             // input m_f, then A_b (published)
   unsigned char* Qm = Bm + kMat;                            // input m_b
-  const long long groups = (L + kEdges - 1) / kEdges;
+  const long long groups = (n + kEdges - 1) / kEdges;
   const long long nwarps = (long long)gridDim.x * kWarps;
   const unsigned char* gext = reinterpret_cast<const unsigned char*>(ext);
   float cm[8];
@@ -393,7 +404,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_canon8v2(long long L, const 
   unsigned bar_parity = 0;
   auto prefetch = [&](long long g) {
     long long e = g * kEdges + (lane & 15);
-    e = e < L ? e : L - 1;
+    e = e < n ? e : n - 1;
     if (order) e = __ldg(order + e);
     const unsigned dst = smem_u32(wbase) + (lane & 15) * kPair + (lane < 16 ? kMat : 2 * kMat);
     fence_proxy_async();                                    // this lane's earlier loads / stores of the slots come first
@@ -407,9 +418,21 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_canon8v2(long long L, const 
 #pragma unroll 1
   for (; g < groups; g += nwarps) {
     long long e = g * kEdges + pair;
-    const bool live = e < L;
-    e = live ? e : L - 1;
-    if (order) e = __ldg(order + e);                        // edges grouped by the sweeps they needed last time (see `cost`)
+    const bool live = e < n;
+    e = live ? e : n - 1;
+    if (order) e = __ldg(order + e);                        // the edges this rank owns / edges grouped by cost
+    // a cut edge this rank owns: the other endpoint's rank gets the same results
+    const int rcode = (rem.code && live) ? __ldg(rem.code + e) : -1;
+    float2* far_canon = nullptr;
+    float* far_lmbds = nullptr;
+    long long far_e = 0, far_L = 0;
+    if (rcode >= 0) {
+      const int q = rcode >> 27;
+      far_e = rcode & ((1 << 27) - 1);
+      far_L = rem.L[q];
+      far_canon = rem.canon[q];
+      far_lmbds = rem.lmbds[q];
+    }
     int it_eig = 0, it_ker = 0;
     mbar_wait(bar, bar_parity);
     bar_parity ^= 1;
@@ -519,6 +542,11 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_canon8v2(long long L, const 
         float4* lo = reinterpret_cast<float4*>(lmbds + (size_t)e * 8);
         lo[0] = make_float4(sorted[0], sorted[1], sorted[2], sorted[3]);
         lo[1] = make_float4(sorted[4], sorted[5], sorted[6], sorted[7]);
+        if (far_lmbds) {
+          float4* fo = reinterpret_cast<float4*>(far_lmbds + (size_t)far_e * 8);
+          fo[0] = lo[0];
+          fo[1] = lo[1];
+        }
 #pragma unroll
         for (int c = 0; c < 8; ++c) cm[c] = fmaxf(cm[c], sorted[c]);
       }
@@ -536,6 +564,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_canon8v2(long long L, const 
         }
       }
       float2* cf = canon + (size_t)(e + L) * 64;
+      float2* far_cf = far_canon ? far_canon + (size_t)(far_e + far_L) * 64 : nullptr;
 #pragma unroll 2
       for (int r = 0; r < 8; ++r) {
         float2 f[8];
@@ -556,12 +585,17 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_canon8v2(long long L, const 
             re = x2::fnma2(FY[k], A.Y[j][k], re);
             im = x2::fma2(FY[k], A.X[j][k], im);
           }
-          if (live && rk[j] < ncols) cf[r * 8 + rk[j]] = make_float2(x2::hsum(re), x2::hsum(im));
+          if (live && rk[j] < ncols) {
+            const float2 v = make_float2(x2::hsum(re), x2::hsum(im));
+            cf[r * 8 + rk[j]] = v;
+            if (far_cf) far_cf[r * 8 + rk[j]] = v;
+          }
         }
       }
     } else {
       // follower: column j holds conj(C_b)[:, j]; slot e, column position = the leader's rank of j
       float2* cb = canon + (size_t)e * 64;
+      float2* far_cb = far_canon ? far_canon + (size_t)far_e * 64 : nullptr;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int c = (int)((packed >> (3 * j)) & 7u);
@@ -570,8 +604,11 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_canon8v2(long long L, const 
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const float2 xr = x2::unpk(A.X[j][k]), yi = x2::unpk(A.Y[j][k]);
-            cb[(2 * k) * 8 + c] = keep ? make_float2(xr.x, -yi.x) : make_float2(0.f, 0.f);
-            cb[(2 * k + 1) * 8 + c] = keep ? make_float2(xr.y, -yi.y) : make_float2(0.f, 0.f);
+            const float2 v0 = keep ? make_float2(xr.x, -yi.x) : make_float2(0.f, 0.f);
+            const float2 v1 = keep ? make_float2(xr.y, -yi.y) : make_float2(0.f, 0.f);
+            cb[(2 * k) * 8 + c] = v0;
+            cb[(2 * k + 1) * 8 + c] = v1;
+            if (far_cb) { far_cb[(2 * k) * 8 + c] = v0; far_cb[(2 * k + 1) * 8 + c] = v1; }
           }
         }
       }
@@ -670,9 +707,19 @@ int launch_sort_edges_by_cost(long long L, const void* cost, int32_t* order, cud
 }
 
 int launch_fast_canon8v2(long long L, const void* ext, void* canon, void* lmbds, void* colmax, double pinv_eps,
-                         int ncols, const int32_t* order, void* cost, cudaStream_t st) {
+                         int ncols, const int32_t* order, void* cost, cudaStream_t st, long long n_edges,
+                         const int32_t* remote, void* const* peer_canon, void* const* peer_lmbds, const long long* peer_L) {
   using namespace canon8v2;
-  if (L == 0) return 0;
+  const long long n = n_edges >= 0 ? n_edges : L;
+  if (n == 0) return 0;
+  if (n > L || (n < L && !order)) return set_error("canonicalize: %lld of %lld edges without an edge list", n, L);
+  Remote rem{};
+  rem.code = (remote && peer_canon && peer_lmbds && peer_L) ? remote : nullptr;
+  for (int q = 0; q < BQA_MAX_PEERS; ++q) {
+    rem.canon[q] = rem.code ? (float2*)peer_canon[q] : nullptr;
+    rem.lmbds[q] = rem.code ? (float*)peer_lmbds[q] : nullptr;
+    rem.L[q] = rem.code ? peer_L[q] : 0;
+  }
   if (ncols < 1 || ncols > 8) return set_error("canonicalize: %d canonicalizer columns requested for n = 8", ncols);
   static bool configured[64] = {};
   int dev = 0;
@@ -685,13 +732,13 @@ int launch_fast_canon8v2(long long L, const void* ext, void* canon, void* lmbds,
   int sms = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (sms <= 0) sms = 148;
-  const long long groups = (L + kEdges - 1) / kEdges;
+  const long long groups = (n + kEdges - 1) / kEdges;
   long long grid = (groups + kWarps - 1) / kWarps;
   if (grid > sms) grid = sms;
   // n^2 of LAPACK xGESVJ's estimate "next sweep's largest cosine ~ n max|cos| max|sin|" (experiments: BQA_B200_CANON_CONV)
   static const float conv = [] { const char* e = getenv("BQA_B200_CANON_CONV"); return e ? (float)atof(e) : 64.f; }();
-  k_canon8v2<<<(int)grid, kWarps * 32, kSmem, st>>>(L, (const float2*)ext, (float2*)canon, (float*)lmbds, (float*)colmax,
-                                                   (float)pinv_eps, ncols, 2, order, (unsigned char*)cost, conv);
+  k_canon8v2<<<(int)grid, kWarps * 32, kSmem, st>>>(n, L, (const float2*)ext, (float2*)canon, (float*)lmbds, (float*)colmax,
+                                                   (float)pinv_eps, ncols, 2, order, (unsigned char*)cost, conv, rem);
   return after_launch("canonicalize(n=8, v2)");
 }
 

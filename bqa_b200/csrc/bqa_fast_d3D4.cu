@@ -26,6 +26,8 @@
 // of the message each lane stores; the traces are all-reduced early from the partial diagonals.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "bqa_core.cuh"
 #include "bqa_fast_common.cuh"
 #include "bqa_launch.cuh"
@@ -516,6 +518,12 @@ struct RunArgs {
   uint4* peer_xchg[BQA_MAX_PEERS]; // every rank's handshake lines [2][BQA_MAX_PEERS] (peer mapped): 64 bytes into its flag buffer
   unsigned seq_base;               // cross-GPU sequence numbers seq_base + 1, + 2, ... (one per sweep)
   long long timeout_cycles;        // a peer that stays silent this long aborts the run (status[3])
+  // Fences of the handshake (BQA_B200_FENCE): the sender orders its halo stores before the line with a system-scope
+  // fence in every mode.  Receiver, after it has seen the line: 0 = fence.sc.sys, 1 = fence.acq_rel.sys (3.5 us each on
+  // B200 with peer mappings: measured, profiles/r2_multigpu.md), 2 (default) = fence.acq_rel.gpu, 0.8 us -- the halo slots
+  // and the line are in THIS GPU's memory, read through its L2 (cp.async.cg, ld.volatile), which is where the peer's
+  // stores land in the order its fence gave them.
+  int fence_mode;
   unsigned long long* trace;       // profiling aid (bqa_b200_set_bp_trace): 5 globaltimer stamps per sweep from CTA 0, or null
 };
 
@@ -533,6 +541,14 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
+}
+__device__ __forceinline__ void fence_release_sys(int mode) {
+  if (mode == 0) __threadfence_system(); else asm volatile("fence.acq_rel.sys;" ::: "memory");
+}
+__device__ __forceinline__ void fence_acquire_sys(int mode) {
+  if (mode == 0) __threadfence_system();
+  else if (mode == 1) asm volatile("fence.acq_rel.sys;" ::: "memory");
+  else asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 __device__ __forceinline__ void st_volatile_v4(uint4* p, uint4 v) {
   asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -607,7 +623,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_bp_run_d3D4(const __grid_consta
     const int groups = (int)((a.B + 3) >> 2);
     const int gb = min(r.boundary_groups, groups);
     __shared__ unsigned s_max[2];
+    __shared__ unsigned s_bdone;                             // warps of this CTA that finished their boundary groups (all sweeps)
     __shared__ int s_abort;
+    if (threadIdx.x == 0) s_bdone = 0;
+    __syncthreads();
     auto fold_resid = [&](int k) -> bool {                   // global residual of sweep k; true = converged
       const unsigned seq = r.seq_base + k + 1;
       if (threadIdx.x == 0) {
@@ -637,16 +656,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_bp_run_d3D4(const __grid_consta
       const unsigned seq = r.seq_base + it + 1;
       const int undamped = it == r.max_iters - 1;
       if (tracing) r.trace[5 * it] = globaltimer_ns();
-      // 1. boundary groups; the last CTA to finish them sends the DATA lines
+      // 1. boundary groups; the last warp of the last CTA to finish them sends the DATA lines.  No CTA-wide barrier and
+      // one system-scope fence per rank and sweep: every warp releases its halo stores at gpu scope (fence + counter),
+      // the warp that completes the count fences at system scope -- cumulativity carries the other warps' stores -- and
+      // stores the lines; everybody else is already sweeping interior groups.
       sweep<false, MULTI>(a, r.msgs[cur], r.msgs[nxt], it, undamped, PeersOfRun{r, nxt}, smem, 0, gb);
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        __threadfence_system();                             // this CTA's halo stores, system-wide, before its arrival
-        const unsigned arrived = atomicAdd(bcount, 1u);
-        if (arrived == (unsigned)(it + 1) * gridDim.x - 1u) {
-          __threadfence_system();
-          for (int q = 0; q < r.world; ++q)
-            if (q != r.rank) st_volatile_v4(r.peer_xchg[q] + (it & 3) * BQA_MAX_PEERS + r.rank, make_uint4(seq, seq, seq, seq));
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) {
+        __threadfence();
+        if (atomicAdd(&s_bdone, 1u) == (unsigned)(it + 1) * kWarps - 1u) {
+          __threadfence();
+          if (atomicAdd(bcount, 1u) == (unsigned)(it + 1) * gridDim.x - 1u) {
+            fence_release_sys(r.fence_mode);
+            for (int q = 0; q < r.world; ++q)
+              if (q != r.rank) st_volatile_v4(r.peer_xchg[q] + (it & 3) * BQA_MAX_PEERS + r.rank, make_uint4(seq, seq, seq, seq));
+          }
         }
       }
       if (tracing) r.trace[5 * it + 1] = globaltimer_ns();
@@ -669,7 +693,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_bp_run_d3D4(const __grid_consta
           if (*((volatile int32_t*)a.status + 3) != 0 || clock64() - t0 > r.timeout_cycles) { a.status[3] = 1; break; }
           line = ld_volatile_v4(mine);
         }
-        __threadfence_system();                             // the peer's halo stores are ordered before its line
+        fence_acquire_sys(r.fence_mode);                    // the peer's halo stores are ordered before its line
       }
       __syncthreads();
       if (tracing) r.trace[5 * it + 4] = globaltimer_ns();
@@ -738,6 +762,8 @@ int launch_fast_bp_run_d3D4(long long B, const void* T, void* msgs0, void* msgs1
   (void)peer_resid;
   r.timeout_cycles = barrier_timeout_cycles();
   r.trace = g_bp_trace;
+  static const int fence_mode = [] { const char* e = getenv("BQA_B200_FENCE"); return e ? atoi(e) : 2; }();
+  r.fence_mode = fence_mode;
   const long long groups = (B + 3) / 4;
   long long grid = (groups + kWarps - 1) / kWarps;
   if (grid > sm_count()) grid = sm_count();

@@ -100,7 +100,9 @@ int launch_fast_canon8(long long L, const void* ext, void* canon, void* lmbds, v
 void canon8_stats(unsigned long long* out3);
 // second design (bqa_fast_canon8v2.cu): Cholesky factor + column Jacobi for the eigenproblems, stacked SVD of ker
 int launch_fast_canon8v2(long long L, const void* ext, void* canon, void* lmbds, void* colmax, double pinv_eps,
-                         int ncols, const int32_t* order, void* cost, cudaStream_t st);
+                         int ncols, const int32_t* order, void* cost, cudaStream_t st, long long n_edges = -1,
+                         const int32_t* remote = nullptr, void* const* peer_canon = nullptr,
+                         void* const* peer_lmbds = nullptr, const long long* peer_L = nullptr);
 int launch_sort_edges_by_cost(long long L, const void* cost, int32_t* order, cudaStream_t st);
 void canon8v2_stats(unsigned long long* out3);
 // third layout (bqa_fast_canon8v3.cu): two lanes per matrix, 16 warps per SM

@@ -161,7 +161,8 @@ class Engine:
         self._msgs_cur = 0
         self._ext = None         # allocated on first simple update (size depends on the largest D reached)
         self._canon = None
-        self._lmbds = torch.ones(self.L * 2 * Dm, dtype=self.rdtype, device=self.dev)
+        self._lmbds = self._alloc_shared(self.L * 2 * Dm, self.rdtype, "lmbds")
+        self._lmbds.fill_(1.0)
         self._lmbd_stride = 2      # row stride of the lambda array = 2 * D of the update that produced it
         # control block, read back with ONE copy per chunk of sweeps (one per step in the steady state):
         # [resid (max_iters, 2) reals | status int32 x4 | column maxima of the lambdas (2 Dmax reals)]
@@ -241,7 +242,7 @@ class Engine:
         if self._ext is None or self._ext.numel() < need:
             self._ext = self._alloc_shared(need, self.cdtype, "ext")
         if self._canon is None or self._canon.numel() < need:
-            self._canon = torch.zeros(need, dtype=self.cdtype, device=self.dev)
+            self._canon = self._alloc_shared(need, self.cdtype, "canon")
 
     @property
     def ctrl_bytes_per_bp_read(self) -> int:
@@ -550,21 +551,7 @@ class Engine:
                 self.lib.ext_msgs_p2p(*args, c.remote_pos.data_ptr(), peers, st)
         self._exchange_ext()
         self._colmax.zero_()
-        if self._canon_order is not None and self.precision == "single" and D == 4:
-            # n = 8 kernel: edges grouped by the Jacobi sweeps they needed (regrouped every few steps from the costs the
-            # kernel records; a warp sweeps until its slowest matrix is done, results do not depend on the grouping)
-            if self._canon_age >= self._canon_resort_every:
-                self.lib.sort_edges_by_cost(self.L, self._canon_cost.data_ptr(), self._canon_order.data_ptr(), st)
-                self._canon_age = 0
-            self._canon_age += 1
-            self.lib.canonicalize_ordered(self.prec, D, self.L, self._ext.data_ptr(), self._canon.data_ptr(),
-                                          self._lmbds.data_ptr(), self._colmax.data_ptr(), self.pinv_eps,
-                                          min(2 * D, self.Dmax), self._canon_order.data_ptr(),
-                                          self._canon_cost.data_ptr(), st)
-        else:
-            self.lib.canonicalize(self.prec, D, self.L, self._ext.data_ptr(), self._canon.data_ptr(),
-                                  self._lmbds.data_ptr(), self._colmax.data_ptr(), self.pinv_eps,
-                                  min(2 * D, self.Dmax), st)
+        self._canonicalize(D, st)
         self._lmbd_stride = 2 * D
         self._reduce_colmax(self._colmax)
         speculative = self.speculate and self.cuda and D == self.Dmax
@@ -589,6 +576,24 @@ class Engine:
         self.stats["trunc_err"].append(err)
         log.info(f"Truncation performed, per edge error upper bound: {err}")
         log.info(f"Layer with ztime {ztime} and xtime {xtime} has been applied")
+
+    def _canonicalize(self, D: int, st: int) -> None:
+        """Canonicalizers and lambdas of every edge from the extended messages (state.py:171-200)."""
+        if self._canon_order is not None and self.precision == "single" and D == 4:
+            # n = 8 kernel: edges grouped by the Jacobi sweeps they needed (regrouped every few steps from the costs the
+            # kernel records; a warp sweeps until its slowest matrix is done, results do not depend on the grouping)
+            if self._canon_age >= self._canon_resort_every:
+                self.lib.sort_edges_by_cost(self.L, self._canon_cost.data_ptr(), self._canon_order.data_ptr(), st)
+                self._canon_age = 0
+            self._canon_age += 1
+            self.lib.canonicalize_ordered(self.prec, D, self.L, self._ext.data_ptr(), self._canon.data_ptr(),
+                                          self._lmbds.data_ptr(), self._colmax.data_ptr(), self.pinv_eps,
+                                          min(2 * D, self.Dmax), self._canon_order.data_ptr(),
+                                          self._canon_cost.data_ptr(), st)
+        else:
+            self.lib.canonicalize(self.prec, D, self.L, self._ext.data_ptr(), self._canon.data_ptr(),
+                                  self._lmbds.data_ptr(), self._colmax.data_ptr(), self.pinv_eps,
+                                  min(2 * D, self.Dmax), st)
 
     def _truncation(self, colmax: np.ndarray, D: int):
         """(new bond dimension, per-edge error bound) from the column maxima of the lambdas (backends.py:297-303)."""

@@ -206,6 +206,9 @@ class ExchangePlan:
     n_cut_edges: int
     max_local_edges: int = 0          # over all ranks (symmetric buffers are sized for it)
     n_boundary_nodes: dict = None     # degree -> owned nodes with a remote out-edge (they come first in the class)
+    canon_owned: np.ndarray = None    # local edge indices this rank canonicalizes (inner edges + its share of the cut edges)
+    canon_remote: np.ndarray = None   # per local edge: -1 or (peer << 27 | the peer's index of the edge), for owned cut edges
+    local_edges_all: list = None      # local edge count of every rank
 
 
 def build_local_context(ctx: Context, part: np.ndarray, rank: int, world: int):
@@ -282,10 +285,25 @@ def build_local_context(ctx: Context, part: np.ndarray, rank: int, world: int):
         send.setdefault(peer, []).append(s_pos)
         recv.setdefault(peer, []).append(r_pos)
     assert max(L_all) < (1 << 26), "too many local edges for the 27-bit remote slot code"
+    # one owner per cut edge (alternating by edge parity between the two endpoint ranks): it canonicalizes the edge and
+    # stores the result into the other rank as well (bqa_b200_canonicalize_p2p)
+    el = E[le]
+    ple, pre = part[el[:, 0]], part[el[:, 1]]
+    is_cut = ple != pre
+    owner = np.where(le % 2 == 0, ple, pre)
+    mine = ~is_cut | (owner == rank)
+    other = np.where(ple == rank, pre, ple)
+    canon_remote = np.full(Lr, -1, np.int64)
+    sel_c = is_cut & (owner == rank)
+    for q in range(world):
+        mq = sel_c & (other == q)
+        canon_remote[mq] = (q << 27) | g2l_all[q][le[mq]]
     plan = ExchangePlan(rank=rank, world=world, owned=owned, max_local_edges=max(L_all),
                         send_slots={q: slot(np.sort(np.array(v))) for q, v in send.items()},
                         recv_slots={q: slot(np.sort(np.array(v))) for q, v in recv.items()},
-                        n_local_edges=Lr, n_cut_edges=int(cut.size), n_boundary_nodes=n_boundary)
+                        n_local_edges=Lr, n_cut_edges=int(cut.size), n_boundary_nodes=n_boundary,
+                        canon_owned=np.flatnonzero(mine).astype(np.int32), canon_remote=canon_remote.astype(np.int32),
+                        local_edges_all=L_all)
     local = replace(ctx, nodes_number=int(owned.size), edges_number=2 * Lr, degree_to_layout=layouts,
                     edges=E[le], couplings=np.asarray(ctx.couplings)[le], fields=np.asarray(ctx.fields)[owned],
                     node_degree=None, node_slot=None)
@@ -358,8 +376,11 @@ class PartitionedEngine(Engine):
             self._flags = self._alloc_shared(64 + 8 * 16 * 8, torch.uint8, "flags")
             ptrs = lambda tag: (C.c_void_p * 8)(*([int(x) for x in self._symm[tag][1].buffer_ptrs] + [0] * (8 - self.world)))
             self._peer_ptrs = {("msgs", 0): ptrs("msgs0"), ("msgs", 1): ptrs("msgs1"), ("msgs", 2): ptrs("msgs2"),
-                               ("ext", 0): ptrs("ext"),
+                               ("ext", 0): ptrs("ext"), "canon": ptrs("canon"), "lmbds": ptrs("lmbds"),
                                "ctrl": ptrs("ctrl"), "flags": ptrs("flags")}
+            self._canon_owned = torch.from_numpy(plan.canon_owned).to(dev)
+            self._canon_remote = torch.from_numpy(plan.canon_remote).to(dev)
+            self._canon_peer_L = (C.c_longlong * 8)(*([int(x) for x in plan.local_edges_all] + [0] * (8 - self.world)))
             dist.barrier(group=self.group)
         log.info(f"rank {self.rank}/{self.world}: {plan.owned.size} nodes, {plan.n_local_edges} local edges, "
                  f"{plan.n_cut_edges} cut, transport {'peer memory' if self.p2p else 'torch.distributed'}")
@@ -375,8 +396,10 @@ class PartitionedEngine(Engine):
         esize = torch.empty(0, dtype=dtype).element_size()
         if tag.startswith("msgs"):                            # same size on every rank: the largest local slot count
             numel = 2 * self.plan.max_local_edges * self.Dmax * self.Dmax
-        elif tag == "ext":
+        elif tag in ("ext", "canon"):
             numel = 2 * self.plan.max_local_edges * 4 * self.Dmax * self.Dmax
+        elif tag == "lmbds":
+            numel = self.plan.max_local_edges * 2 * self.Dmax
         nbytes = (numel * esize + 511) // 512 * 512
         raw = symm_mem.empty(nbytes, dtype=torch.uint8, device=self.dev)
         raw.zero_()
@@ -447,6 +470,17 @@ class PartitionedEngine(Engine):
             self._sync(-1)
             return
         self._exchange(self._ext, 4 * self.D * self.D)
+
+    def _canonicalize(self, D: int, st: int) -> None:
+        """One owner per cut edge on the peer-memory path (the owner stores the result into the other rank too); the max
+        all-reduce of the column maxima that follows on every rank's stream orders those stores before the apply kernels."""
+        if not self.p2p or os.environ.get("BQA_B200_CANON_SINGLE_OWNER", "1") == "0":
+            return super()._canonicalize(D, st)
+        pp = self._peer_ptrs
+        self.lib.canonicalize_p2p(self.prec, D, self.L, self._ext.data_ptr(), self._canon.data_ptr(), self._lmbds.data_ptr(),
+                                  self._colmax.data_ptr(), self.pinv_eps, min(2 * D, self.Dmax), self._canon_owned.numel(),
+                                  self._canon_owned.data_ptr(), self._canon_remote.data_ptr(), pp["canon"], pp["lmbds"],
+                                  self._canon_peer_L, st)
 
     def _reduce_colmax(self, colmax: torch.Tensor) -> None:
         dist.all_reduce(colmax, op=dist.ReduceOp.MAX, group=self.group)

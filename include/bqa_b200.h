@@ -161,6 +161,16 @@ int bqa_b200_canonicalize(int prec, int D, long long L, const void* ext, void* c
 int bqa_b200_canonicalize_ordered(int prec, int D, long long L, const void* ext, void* canon, void* lmbds, void* colmax,
                                   double pinv_eps, int n_cols, const int32_t* order, void* cost, void* stream);
 int bqa_b200_sort_edges_by_cost(long long L, const void* cost, int32_t* order, void* stream);
+/* Multi-GPU (no reference counterpart): ONE owner per cut edge instead of both endpoint ranks decomposing it.  This rank
+ * decomposes the n_owned edges listed in `owned` (indices into its local edge numbering) and, for those with
+ * remote[e] = (peer << 27 | the peer's index of the edge) >= 0, stores C_f, C_b and the lambdas into the peer's arrays as
+ * well (peer_canon / peer_lmbds: HOST arrays of peer-mapped bases, peer_L: the ranks' local edge counts), so that every
+ * rank ends up with exactly the arrays the duplicate computation gives.  The caller orders the peers' stores before its
+ * next kernel (the engine: the max all-reduce of the column maxima that follows on every rank's stream).  Shapes without
+ * the specialised n = 8 kernel decompose all L local edges as bqa_b200_canonicalize does. */
+int bqa_b200_canonicalize_p2p(int prec, int D, long long L, const void* ext, void* canon, void* lmbds, void* colmax,
+                              double pinv_eps, int n_cols, long long n_owned, const int32_t* owned, const int32_t* remote,
+                              void* const* peer_canon, void* const* peer_lmbds, const long long* peer_L, void* stream);
 
 /* ---- K3c + K4: apply the simple update to a degree class ---------------------------------------
  * replaces batch_truncate_all_but + apply_canonicalizers_with_extensions (state.py:235-246,

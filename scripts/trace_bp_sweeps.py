@@ -1,5 +1,6 @@
 """Where a BP sweep's time goes inside the single-launch run, per rank (launch under torchrun for N > 1):
-sweep compute | grid barrier | fence + handshake line sent | peers' lines received.  Uses bqa_b200_set_bp_trace
+one GPU: sweep | grid barrier | residual test; N GPUs: boundary groups | interior groups + grid barrier | residual line
+sent | wait for the peers' halo-ready lines | lagged residual test.  Uses bqa_b200_set_bp_trace
 (%globaltimer stamps of CTA 0).  Prints one JSON line per rank."""
 import json
 import os
@@ -53,9 +54,12 @@ def main():
     r = np.concatenate(rows)
     us = np.nanmean(r, 0) / 1e3
     print(json.dumps({"rank": rank, "world": world, "qubits": n, "owned_nodes": int(eng.N), "sweeps": int(r.shape[0]),
-                      "us_per_sweep": {"compute_cta0": us[0], "grid_barrier": us[1], "fence_and_send": us[2],
-                                       "wait_for_peers": us[3], "residual_test_to_next_sweep": us[4],
-                                       "total": float(np.nansum(us))}}), flush=True)
+                      "us_per_sweep": ({"sweep_cta0": us[0], "grid_barrier": us[1], "residual_test_to_next_sweep": us[4]}
+                                       if world == 1 else
+                                       {"boundary_groups_cta0": us[0], "interior_groups_and_grid_barrier": us[1],
+                                        "resid_line_sent": us[2], "wait_for_peers_halo_lines": us[3],
+                                        "lagged_residual_test_to_next_sweep": us[4]}) | {"total": float(np.nansum(us))}}),
+          flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

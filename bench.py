@@ -546,6 +546,7 @@ def measure_roofline(eng, lib, layers, torch, dev) -> dict:
     # entry point -> bucket (the partitioned engine calls the *_p2p variants)
     buckets = {"bp_sweep": "bp_sweep", "bp_sweep_p2p": "bp_sweep", "ext_msgs": "ext_msgs", "ext_msgs_p2p": "ext_msgs",
                "canonicalize": "canonicalize", "canonicalize_ordered": "canonicalize", "sort_edges_by_cost": "canonicalize",
+               "canonicalize_p2p": "canonicalize",
                "apply_update": "apply_update", "sweep_sync": "sweep_sync",
                "gauge_msgs": "gauge_msgs", "bp_run": "bp_run"}
     names = sorted(set(buckets.values()))

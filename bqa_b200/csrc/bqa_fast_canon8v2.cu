@@ -370,15 +370,24 @@ __device__ __forceinline__ void inv_col_norms(const unsigned char* m, float (&in
   for (int j = 0; j < 8; ++j) inv[j] = w[j] > 0.f ? 1.f / w[j] : 0.f;
 }
 
-// n edges are processed: order[0 .. n) (or 0 .. n - 1 without `order`); L = local edge count (slot of m_b / C_f = e + L)
+// n edges are processed: order[0 .. n) (or 0 .. n - 1 without `order`); L = local edge count (slot of m_b / C_f = e + L).
+// REMOTE: the multi-GPU instantiation that also stores into the peers (compiled separately: with the peer stores in the
+// one kernel the single-GPU launch measured 0.94 ms instead of 0.85 ms)
+template <bool REMOTE>
 __global__ void __launch_bounds__(kWarps * 32, 1) k_canon8v2(long long n, long long L, const float2* __restrict__ ext,
                                                              float2* __restrict__ canon, float* __restrict__ lmbds,
                                                              float* __restrict__ colmax, float pinv_eps, int ncols, int nphases,
                                                              const int* __restrict__ order, unsigned char* __restrict__ cost, float conv,
                                                              const __grid_constant__ Remote rem) {
   extern __shared__ __align__(16) unsigned char smem[];
-  unsigned long long t_start;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+  // Bookkeeping that lives across the Jacobi loops sits in shared memory, not in registers (the kernel runs at the 255
+  // register limit: every long-lived scalar became a spill inside the sweep loop): per warp 8 column maxima + 6 counters
+  __shared__ unsigned s_cm[kWarps][8];
+  __shared__ int s_cnt[kWarps][8];          // sweeps, ker sweeps, Jacobi runs, own eig sweeps, own ker sweeps, live edges
+  __shared__ unsigned long long s_t0;
+  if (threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(s_t0));
+  if ((threadIdx.x & 31) < 8) { s_cm[threadIdx.x >> 5][threadIdx.x & 31] = 0u; s_cnt[threadIdx.x >> 5][threadIdx.x & 31] = 0; }
+  __syncthreads();
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int pair = lane >> 1;
   const bool leader = (lane & 1) == 0;
@@ -386,13 +395,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_canon8v2(long long n, long l
   unsigned char* F = wbase + pair * kPair;                  // A_f (published), needed until the epilogue
   unsigned char* Bm = F + kMat;                             // input m_f, then A_b (published)
   unsigned char* Qm = Bm + kMat;                            // input m_b
-  const long long groups = (n + kEdges - 1) / kEdges;
-  const long long nwarps = (long long)gridDim.x * kWarps;
+  const int groups = (int)((n + kEdges - 1) / kEdges);
+  const int nwarps = (int)gridDim.x * kWarps;
   const unsigned char* gext = reinterpret_cast<const unsigned char*>(ext);
-  float cm[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) cm[j] = 0.f;
-  int n_sweeps = 0, n_ker = 0, n_jac = 0, own_eig = 0, own_ker = 0, n_iter = 0;
 
   // The 32 input matrices of a group (m_f of its 16 edges, then m_b) arrive by TMA: every lane issues ONE 512-byte bulk
   // copy (lane t < 16: m_f of edge t -> slot B of pair t; lane t >= 16: m_b of edge t - 16 -> slot Q) and the warp's
@@ -402,8 +407,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_canon8v2(long long n, long l
   fence_proxy_async();
   __syncwarp();
   unsigned bar_parity = 0;
-  auto prefetch = [&](long long g) {
-    long long e = g * kEdges + (lane & 15);
+  auto prefetch = [&](int g) {
+    long long e = (long long)g * kEdges + (lane & 15);
     e = e < n ? e : n - 1;
     if (order) e = __ldg(order + e);
     const unsigned dst = smem_u32(wbase) + (lane & 15) * kPair + (lane < 16 ? kMat : 2 * kMat);
@@ -413,26 +418,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_canon8v2(long long n, long l
     __syncwarp();
     bulk_g2s(dst, gext + (size_t)(lane < 16 ? e : e + L) * 512, 512, bar);
   };
-  long long g = (long long)blockIdx.x * kWarps + wib;
+  int g = (int)blockIdx.x * kWarps + wib;
   if (g < groups) prefetch(g);
 #pragma unroll 1
   for (; g < groups; g += nwarps) {
-    long long e = g * kEdges + pair;
-    const bool live = e < n;
-    e = live ? e : n - 1;
-    if (order) e = __ldg(order + e);                        // the edges this rank owns / edges grouped by cost
-    // a cut edge this rank owns: the other endpoint's rank gets the same results
-    const int rcode = (rem.code && live) ? __ldg(rem.code + e) : -1;
-    float2* far_canon = nullptr;
-    float* far_lmbds = nullptr;
-    long long far_e = 0, far_L = 0;
-    if (rcode >= 0) {
-      const int q = rcode >> 27;
-      far_e = rcode & ((1 << 27) - 1);
-      far_L = rem.L[q];
-      far_canon = rem.canon[q];
-      far_lmbds = rem.lmbds[q];
-    }
     int it_eig = 0, it_ker = 0;
     mbar_wait(bar, bar_parity);
     bar_parity ^= 1;
@@ -490,23 +479,32 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_canon8v2(long long n, long l
         // slots B and Q are free: the next group's inputs stream in behind the SVD phase
         if (g + nwarps < groups) prefetch(g + nwarps);
       }
-      const int before = n_sweeps;
-      int own = 0;
-      jacobi8(A, w, n_sweeps, phase == 1, own, conv);
-      if (phase == 0) {
-        own_eig += own;
-        it_eig = max(own, __shfl_xor_sync(0xffffffffu, own, 1));
-      } else {
-        own_ker += own;
-        it_ker = own;
-      }
-      n_jac += 1;
+      int own = 0, ran = 0;
+      jacobi8(A, w, ran, phase == 1, own, conv);
+      if (phase == 0) it_eig = max(own, __shfl_xor_sync(0xffffffffu, own, 1)); else it_ker = own;
+      if (lane == 0) { s_cnt[wib][0] += ran; s_cnt[wib][1] += phase == 1 ? ran : 0; s_cnt[wib][2] += 1; }
+      atomicAdd(&s_cnt[wib][phase == 0 ? 3 : 4], (phase == 0 || leader) ? own : 0);
       if (phase == 0) {
         eig_publish(A, w, (leader ? Bm : Qm) + kPad, leader ? F : Bm, pinv_eps);
         __syncwarp();
-      } else {
-        n_ker += n_sweeps - before;
       }
+    }
+    // the edge of this lane pair (re-derived here: nothing but the matrix lives across the sweeps)
+    long long e = (long long)g * kEdges + pair;
+    const bool live = e < n;
+    e = live ? e : n - 1;
+    if (order) e = __ldg(order + e);                        // the edges this rank owns / edges grouped by cost
+    // a cut edge this rank owns: the other endpoint's rank gets the same results
+    const int rcode = (REMOTE && rem.code && live) ? __ldg(rem.code + e) : -1;
+    float2* far_canon = nullptr;
+    float* far_lmbds = nullptr;
+    long long far_e = 0, far_L = 0;
+    if (rcode >= 0) {
+      const int q = rcode >> 27;
+      far_e = rcode & ((1 << 27) - 1);
+      far_L = rem.L[q];
+      far_canon = rem.canon[q];
+      far_lmbds = rem.lmbds[q];
     }
     // ---- epilogue.  Leader: w = S^2 per column
     int rk[8];
@@ -548,7 +546,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_canon8v2(long long n, long l
           fo[1] = lo[1];
         }
 #pragma unroll
-        for (int c = 0; c < 8; ++c) cm[c] = fmaxf(cm[c], sorted[c]);
+        for (int c = 0; c < 8; ++c) atomicMax(&s_cm[wib][c], __float_as_uint(sorted[c]));
       }
       // G[i][j] = (ker W)[i][j] / (S_j |A_f col i|^2) for the kept columns;  C_f[r][j] = sum_i A_f[r][i] G[i][j]
       float invf[8];
@@ -613,43 +611,26 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_canon8v2(long long n, long l
         }
       }
     }
-    n_iter += live ? 1 : 0;
+    if (leader && live) atomicAdd(&s_cnt[wib][5], 1);
     __syncwarp();                                           // F is rewritten by the next iteration's phase 1
   }
-  // column-wise max of lambda over all edges (truncate_lmbds, backends.py:297-299); only leaders hold values
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) cm[c] = fmaxf(cm[c], __shfl_xor_sync(0xffffffffu, cm[c], o));
-  }
-  if (lane < 8) {
-    float v = cm[0];
-#pragma unroll
-    for (int c = 1; c < 8; ++c) v = lane == c ? cm[c] : v;
-    atomicMax(reinterpret_cast<unsigned int*>(colmax + lane), __float_as_uint(v));
-  }
-  {
-    unsigned long long se = (unsigned long long)own_eig * (n_iter ? 1 : 0), sk = leader ? (unsigned long long)own_ker : 0ull;
-    unsigned long long ne = (unsigned long long)n_iter, nk = leader ? (unsigned long long)n_iter : 0ull;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      se += __shfl_xor_sync(0xffffffffu, se, o); sk += __shfl_xor_sync(0xffffffffu, sk, o);
-      ne += __shfl_xor_sync(0xffffffffu, ne, o); nk += __shfl_xor_sync(0xffffffffu, nk, o);
-    }
-    if (lane == 0) {
-      atomicAdd(&g_stats[3], se); atomicAdd(&g_stats[4], sk); atomicAdd(&g_stats[5], ne); atomicAdd(&g_stats[6], nk);
-    }
+  // column-wise max of lambda over all edges (truncate_lmbds, backends.py:297-299)
+  __syncwarp();
+  if (lane < 8) atomicMax(reinterpret_cast<unsigned int*>(colmax + lane), s_cm[wib][lane]);
+  if (lane == 0) {
+    atomicAdd(&g_stats[0], (unsigned long long)s_cnt[wib][2]);
+    atomicAdd(&g_stats[1], (unsigned long long)s_cnt[wib][0]);
+    atomicAdd(&g_stats[2], (unsigned long long)s_cnt[wib][1]);
+    atomicAdd(&g_stats[3], (unsigned long long)s_cnt[wib][3]);
+    atomicAdd(&g_stats[4], (unsigned long long)s_cnt[wib][4]);
+    atomicAdd(&g_stats[5], 2ull * (unsigned long long)s_cnt[wib][5]);
+    atomicAdd(&g_stats[6], (unsigned long long)s_cnt[wib][5]);
   }
   if (threadIdx.x == 0) {
     unsigned long long t_end;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
-    atomicMin(&g_span[0], t_start);
+    atomicMin(&g_span[0], s_t0);
     atomicMax(&g_span[1], t_end);
-  }
-  if (lane == 0) {
-    atomicAdd(&g_stats[0], (unsigned long long)n_jac);
-    atomicAdd(&g_stats[1], (unsigned long long)n_sweeps);
-    atomicAdd(&g_stats[2], (unsigned long long)n_ker);
   }
 }
 
@@ -725,7 +706,8 @@ int launch_fast_canon8v2(long long L, const void* ext, void* canon, void* lmbds,
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(k_canon8v2, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaError_t e = cudaFuncSetAttribute(k_canon8v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_canon8v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(k_canon8v2): %s", cudaGetErrorString(e));
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
@@ -737,8 +719,14 @@ int launch_fast_canon8v2(long long L, const void* ext, void* canon, void* lmbds,
   if (grid > sms) grid = sms;
   // n^2 of LAPACK xGESVJ's estimate "next sweep's largest cosine ~ n max|cos| max|sin|" (experiments: BQA_B200_CANON_CONV)
   static const float conv = [] { const char* e = getenv("BQA_B200_CANON_CONV"); return e ? (float)atof(e) : 64.f; }();
-  k_canon8v2<<<(int)grid, kWarps * 32, kSmem, st>>>(n, L, (const float2*)ext, (float2*)canon, (float*)lmbds, (float*)colmax,
-                                                   (float)pinv_eps, ncols, 2, order, (unsigned char*)cost, conv, rem);
+  if (rem.code)
+    k_canon8v2<true><<<(int)grid, kWarps * 32, kSmem, st>>>(n, L, (const float2*)ext, (float2*)canon, (float*)lmbds,
+                                                           (float*)colmax, (float)pinv_eps, ncols, 2, order,
+                                                           (unsigned char*)cost, conv, rem);
+  else
+    k_canon8v2<false><<<(int)grid, kWarps * 32, kSmem, st>>>(n, L, (const float2*)ext, (float2*)canon, (float*)lmbds,
+                                                            (float*)colmax, (float)pinv_eps, ncols, 2, order,
+                                                            (unsigned char*)cost, conv, rem);
   return after_launch("canonicalize(n=8, v2)");
 }
 

@@ -26,6 +26,8 @@ def main():
     from bqa_b200 import _lib
     from bqa_b200.config import config_to_context
     from bqa_b200.engine import Engine
+    if os.environ.get("BQA_B200_LIB_EXPERIMENT"):            # side-by-side builds of the library (scratch/, not the product)
+        _lib._cached = _lib.bind(os.environ["BQA_B200_LIB_EXPERIMENT"])
     lib = _lib.load_library()
     ctx = config_to_context(instances.bench_config(args.qubits))
     eng = Engine(ctx, precision="single")

@@ -581,3 +581,43 @@ def test_multiclass_launches_equal_per_class_launches(lib, name, precision):
     assert np.array_equal(out[True][0], out[False][0])
     assert out[True][1:5] == out[False][1:5]
     assert out[True][5] <= 4.0 + 1e-9 and out[False][5] > out[True][5]
+
+
+def test_engine_on_a_device_that_is_not_current(lib):
+    """Engine(device="cuda:1") while cuda:0 is the current device: the raw launches behind the C ABI (cooperative launch,
+    function attributes, SM count) act on cudaGetDevice(), so the engine makes its device current around every call
+    (skipped on a 1-GPU box)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from bqa_b200.config import config_to_context
+    from bqa_b200.engine import Engine
+    torch.cuda.set_device(0)
+    cfg = _rr_config(3000, 12, 2.4, [])
+    ctx = config_to_context(cfg)
+    out = []
+    for dev in ("cuda:0", "cuda:1"):
+        eng = Engine(ctx, precision="single", device=dev)
+        for ins in [i for i in ctx.instructions if isinstance(i, dict)]:
+            eng.run_layer(ins["xtime"], ins["ztime"])
+        assert torch.cuda.current_device() == 0
+        out.append(eng.bloch_vectors())
+    assert np.array_equal(out[0], out[1])
+
+
+def test_nan_state_fails_loudly(lib):
+    """A non-finite node tensor must not let BP "converge" on the finite entries: the residual becomes non-finite and the
+    engine raises (the reference fails its `assert best_msgs is not None`, state.py:113-123)."""
+    import torch
+    from bqa_b200.config import config_to_context
+    from bqa_b200.engine import Engine
+    for precision, cfg in (("single", _rr_config(400, 12, 2.4, [])), ("double", instances.cfg_grid4())):
+        ctx = config_to_context(cfg)
+        eng = Engine(ctx, precision=precision)
+        layers = [i for i in ctx.instructions if isinstance(i, dict)]
+        for ins in layers[:10]:
+            eng.run_layer(ins["xtime"], ins["ztime"])
+        c = eng.classes[-1]
+        c.T[c.cur][3] = float("nan")
+        with pytest.raises(FloatingPointError):
+            eng.run_bp()

@@ -41,8 +41,17 @@ struct MultiArgs {
   int32_t* status;
   cx<R>* ws;
   size_t ws_per_warp;
+  int ws_in_smem;                  // the per-warp scratch fits into shared memory (small D): no global-memory round trips
   long long timeout_cycles;
 };
+
+// scratch of this warp: a slab of the CTA's dynamic shared memory when it fits (ws_in_smem), else of the global workspace
+template <typename R>
+__device__ __forceinline__ cx<R>* warp_scratch(const MultiArgs<R>& a, long long warp) {
+  extern __shared__ __align__(16) unsigned char mc_smem[];
+  return a.ws_in_smem ? reinterpret_cast<cx<R>*>(mc_smem) + (size_t)(threadIdx.x >> 5) * a.ws_per_warp
+                      : a.ws + (size_t)warp * a.ws_per_warp;
+}
 
 template <typename R>
 __device__ __forceinline__ int find_class(const MultiArgs<R>& a, long long item) {
@@ -64,7 +73,7 @@ __device__ __forceinline__ void mc_sweep(const MultiArgs<R>& a, const cx<R>* cur
     const ClassRow<R>& c = a.c[find_class(a, item)];
     const long long node = item - c.first;
     const int d = c.d, W = 2 * ipow(D, d);
-    cx<R>* P = a.ws + (size_t)warp * a.ws_per_warp;
+    cx<R>* P = warp_scratch<R>(a, warp);
     cx<R>* E = P + W;
     cx<R>* gram = E + W;
     const cx<R>* mp[BQA_MAX_DEGREE];
@@ -137,7 +146,7 @@ __global__ void __launch_bounds__(128) k_mc_ext(const __grid_constant__ MultiArg
     const ClassRow<R>& c = a.c[find_class(a, item)];
     const long long node = item - c.first;
     const int d = c.d, W = 2 * ipow(D, d);
-    cx<R>* P = a.ws + (size_t)warp * a.ws_per_warp;
+    cx<R>* P = warp_scratch<R>(a, warp);
     cx<R>* E = P + W;
     cx<R>* gram = E + W;
     const cx<R>* mp[BQA_MAX_DEGREE];
@@ -165,7 +174,7 @@ __global__ void __launch_bounds__(128) k_mc_apply(const __grid_constant__ MultiA
     const long long node = item - c.first;
     const int d = c.d;
     const int Win = 2 * ipow(D, d), Wout = 2 * ipow(Dn, d), Wmax = 2 * ipow(D > Dn ? D : Dn, d);
-    cx<R>* bufA = a.ws + (size_t)warp * a.ws_per_warp;
+    cx<R>* bufA = warp_scratch<R>(a, warp);
     cx<R>* bufB = bufA + Wmax;
     cx<R>* wbuf = bufB + Wmax;
     const cx<R>* cp[BQA_MAX_DEGREE];
@@ -218,26 +227,36 @@ int launch_multiclass(int kind, int n_classes, const bqa_b200_class* cls, int D,
   long long blocks = (total + 3) / 4;
   const long long cap = (long long)BQA_GENERIC_MAX_WARPS / 4;
   if (blocks > cap) blocks = cap;
+  // scratch in shared memory when 4 warps' worth fits beside a second CTA (D <= 8 at degree 3 in complex64, ...): the
+  // generic per-node code then never leaves the SM (in the global workspace every intermediate is written through to L2)
+  size_t smem = per_warp * sizeof(cx<R>) * 4;
+  a.ws_in_smem = smem <= 100 * 1024 ? 1 : 0;
+  if (!a.ws_in_smem) smem = 0;
+  const void* fn = kind == 0 ? (const void*)k_mc_ext<R> : (kind == 1 ? (const void*)k_mc_apply<R> : (const void*)k_mc_bp_run<R>);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(multiclass): %s", cudaGetErrorString(e));
+  }
   if (kind == 2) {                                                    // every CTA must be resident: cooperative launch
     int dev = 0, sms = 0, occ = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mc_bp_run<R>, 128, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mc_bp_run<R>, 128, smem);
     if (occ < 1 || sms < 1) return set_error("bp_run_classes: the kernel cannot be made resident");
     if (blocks > (long long)occ * sms) blocks = (long long)occ * sms;
   }
-  if (ws_bytes < per_warp * sizeof(cx<R>) * (size_t)blocks * 4)
+  if (!a.ws_in_smem && ws_bytes < per_warp * sizeof(cx<R>) * (size_t)blocks * 4)
     return set_error("workspace too small: need %zu bytes, got %zu", per_warp * sizeof(cx<R>) * (size_t)blocks * 4, ws_bytes);
   if (kind == 0) {
-    k_mc_ext<R><<<(int)blocks, 128, 0, st>>>(a);
+    k_mc_ext<R><<<(int)blocks, 128, smem, st>>>(a);
     return after_launch("ext_msgs_classes");
   }
   if (kind == 1) {
-    k_mc_apply<R><<<(int)blocks, 128, 0, st>>>(a);
+    k_mc_apply<R><<<(int)blocks, 128, smem, st>>>(a);
     return after_launch("apply_update_classes");
   }
   void* params[] = {&a};
-  cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_mc_bp_run<R>, dim3((unsigned)blocks), dim3(128), params, 0, st);
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_mc_bp_run<R>, dim3((unsigned)blocks), dim3(128), params, smem, st);
   if (e != cudaSuccess) return set_error("cudaLaunchCooperativeKernel(k_mc_bp_run): %s", cudaGetErrorString(e));
   return after_launch("bp_run_classes");
 }

@@ -376,8 +376,7 @@ def run_ours(args) -> None:
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tw0 = time.perf_counter()
     ev0.record()
-    for ins in layers[k:k + steps]:
-        eng.run_layer(ins["xtime"], ins["ztime"])
+    eng.run_layers(layers[k:k + steps])      # = run_layer per step, each announcing the next step's ztime
     ev1.record()
     barrier()
     tw1 = time.perf_counter()
@@ -498,8 +497,7 @@ def config5_block(steps: int, warmup: int, torch, dist, dev, rank: int, world: i
     n0 = len(eng.stats["bp_sweeps"])
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for ins in layers[k:k + steps]:
-        eng.run_layer(ins["xtime"], ins["ztime"])
+    eng.run_layers(layers[k:k + steps])
     e1.record()
     dist.barrier()
     torch.cuda.synchronize(dev)
@@ -545,6 +543,7 @@ def measure_roofline(eng, lib, layers, torch, dev) -> dict:
         else (6650.0, "fallback (B200_PROFILING.md)")
     # entry point -> bucket (the partitioned engine calls the *_p2p variants)
     buckets = {"bp_sweep": "bp_sweep", "bp_sweep_p2p": "bp_sweep", "ext_msgs": "ext_msgs", "ext_msgs_p2p": "ext_msgs",
+               "ext_msgs_after_run": "ext_msgs",
                "canonicalize": "canonicalize", "canonicalize_ordered": "canonicalize", "sort_edges_by_cost": "canonicalize",
                "canonicalize_p2p": "canonicalize",
                "apply_update": "apply_update", "sweep_sync": "sweep_sync",
@@ -568,8 +567,7 @@ def measure_roofline(eng, lib, layers, torch, dev) -> dict:
         setattr(lib, n, wrap(n))
     n_runs0 = len(eng.stats["bp_sweeps"])
     try:
-        for ins in layers:
-            eng.run_layer(ins["xtime"], ins["ztime"])
+        eng.run_layers(layers)
         torch.cuda.synchronize(dev)
     finally:
         for n in buckets:
@@ -631,8 +629,7 @@ def measure_e2e(eng, snapshot, layers, torch, dev, bloch_resident, world, dist) 
     n0 = len(eng.stats["bp_sweeps"])
     t0 = time.perf_counter()
     eng.load_state(snapshot)
-    for ins in layers:
-        eng.run_layer(ins["xtime"], ins["ztime"])
+    eng.run_layers(layers)
     b = eng.bloch_vectors()
     torch.cuda.synchronize(dev)
     dt = time.perf_counter() - t0

@@ -22,6 +22,8 @@ SIGNATURES = {
     "bqa_b200_bp_run": [_i, _i, _i, _ll, _vp, _vp, _vp, _i, _vp, _vp, _d, _d, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp,
                         C.c_uint, _vp, _vp, _ll, _vp],
     "bqa_b200_bp_sweep": [_i, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp, _d, _i, _d, _i, _vp, _vp, _vp, _sz, _vp],
+    "bqa_b200_ext_msgs_after_run": [_i, _i, _i, _ll, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _d, _vp, _vp,
+                                    _vp],
     "bqa_b200_ext_msgs": [_i, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _d, _vp, _sz, _vp],
     "bqa_b200_canonicalize": [_i, _i, _ll, _vp, _vp, _vp, _vp, _d, _i, _vp],
     "bqa_b200_canonicalize_ordered": [_i, _i, _ll, _vp, _vp, _vp, _vp, _d, _i, _vp, _vp, _vp],
@@ -57,7 +59,8 @@ EXPORTS = list(SIGNATURES) + ["bqa_b200_last_error", "bqa_b200_version", "bqa_b2
                               "bqa_b200_set_barrier_timeout", "bqa_b200_set_bp_trace", "bqa_b200_canon_span"]
 
 
-_CUDA_ONLY = ("bqa_b200_canonicalize_ordered", "bqa_b200_sort_edges_by_cost", "bqa_b200_canonicalize_p2p")
+_CUDA_ONLY = ("bqa_b200_canonicalize_ordered", "bqa_b200_sort_edges_by_cost", "bqa_b200_canonicalize_p2p",
+              "bqa_b200_ext_msgs_after_run")
 
 
 class ClassDesc(C.Structure):
@@ -95,7 +98,7 @@ class Library:
     def _checked(self, name, fn):
         def call(*args):
             rc = fn(*args)
-            if rc == 2 and name == "bqa_b200_bp_run":
+            if rc == 2 and name in ("bqa_b200_bp_run", "bqa_b200_ext_msgs_after_run"):
                 return False                  # no single-launch kernel for this shape: not an error
             if rc != 0:
                 raise RuntimeError(f"{name}: {self._dll.bqa_b200_last_error().decode()}")

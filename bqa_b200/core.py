@@ -91,7 +91,8 @@ def run_context(context, precision=None, device=None, engine_cls=Engine, checkpo
         ins = instructions[i]
         log.info(f"Instruction number {i} / {n} started")
         if isinstance(ins, dict):
-            engine.run_layer(ins["xtime"], ins["ztime"])        # "type" is ignored like in the reference (core.py:23)
+            nxt = instructions[i + 1] if i + 1 < n else None    # "type" is ignored like in the reference (core.py:23)
+            engine.run_layer(ins["xtime"], ins["ztime"], next_ztime=nxt["ztime"] if isinstance(nxt, dict) else None)
         elif ins == "measure":
             results.append(["measurement_outcomes", engine.measure()])
         elif ins == "get_bloch_vectors":

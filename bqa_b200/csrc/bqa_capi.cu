@@ -146,6 +146,21 @@ int bqa_b200_ext_msgs(int prec, int degree, int D, long long B, const void* T, c
                                workspace_bytes, nullptr, nullptr, stream);
 }
 
+int bqa_b200_ext_msgs_after_run(int prec, int degree, int D, long long B, const void* T, const void* msgs0,
+                                const void* msgs1, const void* msgs2, int nbuf, int parity, int max_iters,
+                                const int32_t* status, void* ext, const int32_t* in_pos, const int32_t* out_pos,
+                                const void* edge_ampls, double ztime, const int32_t* remote_pos, void* const* peers,
+                                void* stream) {
+  if (int rc = check_shape(prec, degree, D)) return rc;
+  if (g_kernel_mode.load() == 1 || !fast_d3D4_available(prec, degree, D, B)) {
+    set_error("ext_msgs_after_run: no kernel for precision %d, degree %d, D = %d", prec, degree, D);
+    return 2;                                              /* not an error: the caller waits for the run and uses ext_msgs */
+  }
+  AfterRun after{{msgs0, msgs1, msgs2}, nbuf, parity, max_iters, status};
+  return launch_fast_msgs_d3D4(true, B, T, nullptr, ext, in_pos, out_pos, edge_ampls, ztime, 0.0, 0, 0.0, 0, nullptr,
+                               nullptr, remote_pos, peers, (cudaStream_t)stream, &after);
+}
+
 int bqa_b200_bp_run(int prec, int degree, int D, long long B, const void* T, void* msgs0, void* msgs1, int parity,
                     const int32_t* in_pos, const int32_t* out_pos, double damping, double bp_eps, int max_iters,
                     void* resid, int32_t* status, const int32_t* remote_pos, void* const* peers0, void* const* peers1,

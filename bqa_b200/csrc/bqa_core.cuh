@@ -257,13 +257,16 @@ BQA_HDN void node_project(G g, cx<R>* t, int half, int bit) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// one-sided (Hestenes) Jacobi SVD of a complex n x n matrix held row-major in `A`:
-// on exit  A = U diag(sigma) (columns),  V = right singular vectors,  A_in = U diag(sigma) V^H.
-// `order` receives the column permutation that sorts sigma descending.  Lane r owns row r.
+// one-sided (Hestenes) Jacobi SVD of a complex n x n matrix held row-major in `A` with row stride `ld`:
+// on exit  A = U diag(sigma) (columns),  V = right singular vectors (same stride),  A_in = U diag(sigma) V^H.
+// `order` receives the column permutation that sorts sigma descending.  Lane r owns row r, so a column access
+// touches one element per row: in shared memory ld = n + 1 keeps those accesses off a common bank (with ld = n = 16
+// complex64 every lane of a column access hit the same two banks: 12.7 conflicts per shared-memory instruction in
+// the r2 capture of the n = 16 kernel).
 // ------------------------------------------------------------------------------------------------
 template <typename R, typename G>
-BQA_HDN void jacobi_svd(G g, int n, cx<R>* A, cx<R>* V, R* sigma, int* order) {
-  for (int i = g.rank(); i < n * n; i += g.size()) V[i] = mk<R>((i / n == i % n) ? R(1) : R(0), R(0));
+BQA_HDN void jacobi_svd(G g, int n, int ld, cx<R>* A, cx<R>* V, R* sigma, int* order) {
+  for (int i = g.rank(); i < n * n; i += g.size()) V[(i / n) * ld + i % n] = mk<R>((i / n == i % n) ? R(1) : R(0), R(0));
   g.sync();
   const R tol = num_traits<R>::eps() * R(2) * msqrt((R)n);
   // columns whose norm has fallen below eps * |A|_F are numerically zero (the absolute accuracy LAPACK's
@@ -272,7 +275,7 @@ BQA_HDN void jacobi_svd(G g, int n, cx<R>* A, cx<R>* V, R* sigma, int* order) {
   // would rescale the healthy column of the pair.
   R fro2 = 0;
   for (int r = g.rank(); r < n; r += g.size())
-    for (int j = 0; j < n; ++j) fro2 += norm2(A[r * n + j]);
+    for (int j = 0; j < n; ++j) fro2 += norm2(A[r * ld + j]);
   fro2 = g.sum(fro2);
   const R nul = num_traits<R>::eps() * num_traits<R>::eps() * fro2;
   for (int sweep = 0; sweep < 40; ++sweep) {
@@ -281,7 +284,7 @@ BQA_HDN void jacobi_svd(G g, int n, cx<R>* A, cx<R>* V, R* sigma, int* order) {
       for (int q = p + 1; q < n; ++q) {
         R al = 0, be = 0, gr = 0, gi = 0;
         for (int r = g.rank(); r < n; r += g.size()) {
-          const cx<R> ap = A[r * n + p], aq = A[r * n + q];
+          const cx<R> ap = A[r * ld + p], aq = A[r * ld + q];
           al += norm2(ap);
           be += norm2(aq);
           gr += ap.re * aq.re + ap.im * aq.im;          // conj(ap) * aq
@@ -297,12 +300,12 @@ BQA_HDN void jacobi_svd(G g, int n, cx<R>* A, cx<R>* V, R* sigma, int* order) {
         const R c = R(1) / msqrt(R(1) + t * t), s = c * t;
         const cx<R> ph = mk<R>(gr / ag, -gi / ag);      // e^{-i arg(gamma)}
         for (int r = g.rank(); r < n; r += g.size()) {
-          cx<R> ap = A[r * n + p], aq = ph * A[r * n + q];
-          A[r * n + p] = c * ap - s * aq;
-          A[r * n + q] = s * ap + c * aq;
-          ap = V[r * n + p]; aq = ph * V[r * n + q];
-          V[r * n + p] = c * ap - s * aq;
-          V[r * n + q] = s * ap + c * aq;
+          cx<R> ap = A[r * ld + p], aq = ph * A[r * ld + q];
+          A[r * ld + p] = c * ap - s * aq;
+          A[r * ld + q] = s * ap + c * aq;
+          ap = V[r * ld + p]; aq = ph * V[r * ld + q];
+          V[r * ld + p] = c * ap - s * aq;
+          V[r * ld + q] = s * ap + c * aq;
         }
         g.sync();
       }
@@ -312,7 +315,7 @@ BQA_HDN void jacobi_svd(G g, int n, cx<R>* A, cx<R>* V, R* sigma, int* order) {
   // singular values = column norms
   for (int j = 0; j < n; ++j) {
     R a = 0;
-    for (int r = g.rank(); r < n; r += g.size()) a += norm2(A[r * n + j]);
+    for (int r = g.rank(); r < n; r += g.size()) a += norm2(A[r * ld + j]);
     a = g.sum(a);
     if (g.rank() == 0) sigma[j] = msqrt(a);
   }
@@ -331,54 +334,58 @@ BQA_HDN void jacobi_svd(G g, int n, cx<R>* A, cx<R>* V, R* sigma, int* order) {
 
 // ------------------------------------------------------------------------------------------------
 // canonicalizers of one undirected edge (forward message slot e, backward slot e + L)
-//   scratch: 6 n^2 complex + 3 n reals + 3 n ints  (see edge_scratch_bytes)
+//   scratch: 6 matrices of n rows with stride n + 1 (complex) + 3 n reals + 3 n ints  (see edge_scratch_elems)
 // ------------------------------------------------------------------------------------------------
 template <typename R>
-BQA_HD size_t edge_scratch_elems(int n) { return (size_t)6 * n * n; }
+BQA_HD size_t edge_scratch_elems(int n) { return (size_t)6 * n * (n + 1); }
 
 template <typename R, typename G>
 BQA_HDN void edge_canonicalize(G g, int n, const cx<R>* ext_f, const cx<R>* ext_b, R pinv_eps,
                                cx<R>* scratch, R* rscratch, int* iscratch,
                                cx<R>* canon_at_e /* backward */, cx<R>* canon_at_eL /* forward */,
                                R* lmbd_out /* n */) {
-  const int nn = n * n;
-  cx<R>* Af = scratch;           cx<R>* Vf = scratch + nn;
-  cx<R>* Ab = scratch + 2 * nn;  cx<R>* Vb = scratch + 3 * nn;
-  cx<R>* K = scratch + 4 * nn;   cx<R>* Vk = scratch + 5 * nn;
+  const int nn = n * n, ld = n + 1, sz = n * ld;              // scratch matrices: row stride ld (see jacobi_svd)
+  cx<R>* Af = scratch;           cx<R>* Vf = scratch + sz;
+  cx<R>* Ab = scratch + 2 * sz;  cx<R>* Vb = scratch + 3 * sz;
+  cx<R>* K = scratch + 4 * sz;   cx<R>* Vk = scratch + 5 * sz;
   R* sf = rscratch;  R* sb = rscratch + n;  R* sk = rscratch + 2 * n;
   int* of = iscratch;  int* ob = iscratch + n;  int* ok = iscratch + 2 * n;
-  for (int i = g.rank(); i < nn; i += g.size()) { Af[i] = ext_f[i]; Ab[i] = ext_b[i]; }
+  for (int i = g.rank(); i < nn; i += g.size()) {
+    const int at = (i / n) * ld + i % n;
+    Af[at] = ext_f[i];
+    Ab[at] = ext_b[i];
+  }
   g.sync();
-  jacobi_svd<R>(g, n, Af, Vf, sf, of);
-  jacobi_svd<R>(g, n, Ab, Vb, sb, ob);
+  jacobi_svd<R>(g, n, ld, Af, Vf, sf, of);
+  jacobi_svd<R>(g, n, ld, Ab, Vb, sb, ob);
   // ker[i][j] = sum_k lu_f[i][k] lu_b[j][k],  lu[i][k] = sqrt(s_i) conj(V[k][col_i])  (masked s_i > pinv_eps)
   for (int o = g.rank(); o < nn; o += g.size()) {
     const int i = o / n, j = o - i * n;
     const int ci = of[i], cj = ob[j];
     cx<R> acc = mk<R>(0, 0);
     if (sf[ci] > pinv_eps && sb[cj] > pinv_eps) {
-      for (int k = 0; k < n; ++k) cmac(acc, conj(Vf[k * n + ci]), conj(Vb[k * n + cj]));
+      for (int k = 0; k < n; ++k) cmac(acc, conj(Vf[k * ld + ci]), conj(Vb[k * ld + cj]));
       acc = msqrt(sf[ci] * sb[cj]) * acc;
     }
-    K[o] = acc;
+    K[i * ld + j] = acc;
   }
   g.sync();
   // ul = u * pinv(sqrt s): column c of A (= u_c s_c) scaled by s_c^{-3/2}; stored back into A columns
   for (int o = g.rank(); o < nn; o += g.size()) {
-    const int c = o % n;
+    const int c = o % n, at = (o / n) * ld + c;
     {
       const R s = sf[c];
       const R w = (s > pinv_eps && msqrt(s) > num_traits<R>::eps()) ? R(1) / (s * msqrt(s)) : R(0);
-      Af[o] = w * Af[o];
+      Af[at] = w * Af[at];
     }
     {
       const R s = sb[c];
       const R w = (s > pinv_eps && msqrt(s) > num_traits<R>::eps()) ? R(1) / (s * msqrt(s)) : R(0);
-      Ab[o] = w * Ab[o];
+      Ab[at] = w * Ab[at];
     }
   }
   g.sync();
-  jacobi_svd<R>(g, n, K, Vk, sk, ok);
+  jacobi_svd<R>(g, n, ld, K, Vk, sk, ok);
   // lambda = masked singular values, L2 normalised (reference state.py:200)
   R nrm2 = 0;
   for (int j = 0; j < n; ++j) { const R s = sk[ok[j]]; if (s > pinv_eps) nrm2 += s * s; }
@@ -397,8 +404,8 @@ BQA_HDN void edge_canonicalize(G g, int n, const cx<R>* ext_f, const cx<R>* ext_
       const R is = R(1) / s;
       for (int k = 0; k < n; ++k) {
         // U2[k'][cj] = K[k'][cj] / s with k' indexing the *sorted* columns of the forward decomposition
-        cmac(cf, Af[r * n + of[k]], K[k * n + cj]);
-        cmac(cb, Ab[r * n + ob[k]], conj(Vk[k * n + cj]));
+        cmac(cf, Af[r * ld + of[k]], K[k * ld + cj]);
+        cmac(cb, Ab[r * ld + ob[k]], conj(Vk[k * ld + cj]));
       }
       cf = is * cf;
     }

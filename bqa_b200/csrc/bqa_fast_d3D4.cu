@@ -75,6 +75,11 @@ struct Args {
   // multi-GPU over peer memory (see NodeArgs in bqa_generic.cuh)
   const int32_t* remote_pos;
   unsigned char* peers[BQA_MAX_PEERS];
+  // extended messages launched BEHIND a single-launch BP run whose outcome the host has not read yet: the kernel picks
+  // the buffer the run left the messages in from the run's status words (the host's rule, engine._finish_bp)
+  const int32_t* sel_status;       // null: msgs_cur is used
+  const float2* sel_msgs[3];
+  int sel_parity, sel_nbuf, sel_max_iters;
 };
 
 __device__ __forceinline__ float rcp_approx(float v) {
@@ -143,9 +148,15 @@ struct PeersOfArgs {
   const Args& a;
   __device__ __forceinline__ unsigned char* operator()(int q) const { return a.peers[q]; }
 };
-template <bool EXT, bool MULTI, class Peers>
+struct NoMid {
+  __device__ __forceinline__ void operator()() const {}
+};
+// mid() runs once per warp, after the warp's last group below g_mid (the multi-GPU run: "my boundary groups are stored")
+// while the copies of its next group are already in flight
+template <bool EXT, bool MULTI, class Peers, class Mid = NoMid>
 __device__ __forceinline__ void sweep(const Args& a, const float2* msgs_cur, float2* msgs_out, int it, int write_undamped,
-                                      const Peers peers, unsigned char* smem, int g_lo = 0, int g_hi = 0x7fffffff) {
+                                      const Peers peers, unsigned char* smem, int g_lo = 0, int g_hi = 0x7fffffff,
+                                      bool rev = false, int g_mid = 0, const Mid mid = Mid{}) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int s = lane >> 3, t = lane & 7, p = t >> 2, la = t & 3;     // node slot, lane in node, physical, leg-0 index
   unsigned char* wbase = smem + wib * kWarpBytes;
@@ -158,6 +169,12 @@ __device__ __forceinline__ void sweep(const Args& a, const float2* msgs_cur, flo
   // (a lone warp runs much faster than eight sharing the SM) instead of filling all warps of a few CTAs
   int g = wib * (int)gridDim.x + (int)blockIdx.x;
   if (g < g_lo) g += (g_lo - g + nwarps - 1) / nwarps * nwarps;
+  // rev: the groups are visited from the last to the first.  The single-GPU run alternates the direction from sweep to
+  // sweep, so a sweep starts on the part of T and of the messages that the previous one left in L2 (the working set of
+  // the 100k instance, 180 MB, cycles through the 126 MB L2 otherwise); every sweep reads one buffer and writes the
+  // other, so the order does not enter the results
+  const int gflip = rev ? groups - 1 : 0, gdir = rev ? -4 : 4;
+  auto first_node = [&](int gg) { return min(gflip * 4 + gdir * gg, tail0); };
   // boundary messages are also stored into the peers' halo slots.  Compile-time in the BP kernels; the extended-message
   // kernel has ONE instantiation that tests the pointer (two instantiations contracted its epilogue arithmetic into FMAs
   // differently, and single- and multi-GPU runs must stay bit-identical)
@@ -198,27 +215,28 @@ __device__ __forceinline__ void sweep(const Args& a, const float2* msgs_cur, flo
   const p2 rot = x2::pk(-1.f, 1.f);                                   // (y, x) * rot = (-y, x) = i (x + i y)
   int idx_cur = 0, idx_nxt = 0, rp_cur = -1, rp_nxt = -1;
   if (g < groups) {
-    const int n0 = min(g * 4, tail0);
+    const int n0 = first_node(g);
     idx_cur = load_idx(q, n0);
     rp_cur = load_rpos(q, n0);
     issue_group<EXT>(q, 0u, n0, idx_cur);
     cp_async_commit();
     if (g + nwarps < groups) {
-      const int n1 = min((g + nwarps) * 4, tail0);
+      const int n1 = first_node(g + nwarps);
       idx_nxt = load_idx(q, n1);
       rp_nxt = load_rpos(q, n1);
     }
   }
   int cur = 0;
+  if (g >= g_mid) mid();
 #pragma unroll 1
   for (; g < groups; g += nwarps, cur ^= 1) {
     unsigned char* st = wbase + cur * kStage;
-    const int n0 = min(g * 4, tail0);
+    const int n0 = first_node(g);
     int idx_nn = 0, rp_nn = -1;
     if (g + nwarps < groups) {
-      issue_group<EXT>(q, cur ? 0u : (unsigned)kStage, min((g + nwarps) * 4, tail0), idx_nxt);
+      issue_group<EXT>(q, cur ? 0u : (unsigned)kStage, first_node(g + nwarps), idx_nxt);
       if (g + 2 * nwarps < groups) {
-        const int n2 = min((g + 2 * nwarps) * 4, tail0);
+        const int n2 = first_node(g + 2 * nwarps);
         idx_nn = load_idx(q, n2);
         rp_nn = load_rpos(q, n2);
       }
@@ -475,6 +493,7 @@ __device__ __forceinline__ void sweep(const Args& a, const float2* msgs_cur, flo
     rp_cur = rp_nxt;
     rp_nxt = rp_nn;
     __syncwarp();                                           // stage `cur` may be overwritten by the next issue
+    if (g < g_mid && g + nwarps >= g_mid) mid();
   }
   if (!EXT) {
 #pragma unroll
@@ -500,7 +519,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_msgs_d3D4(const __grid_constant
       return;
     }
   }
-  sweep<EXT, MULTI>(a, a.msgs_cur, a.msgs_out, a.it, a.write_undamped, PeersOfArgs{a}, smem);
+  const float2* cur = a.msgs_cur;
+  if (EXT && a.sel_status != nullptr) {
+    // converged: the input of the converging sweep; cap reached: the output of the last sweep (state.py:118-124)
+    const int conv = a.sel_status[0], sw = a.sel_status[1];
+    const int idx = (a.sel_parity + (conv ? sw - 1 : a.sel_max_iters)) % a.sel_nbuf;
+    cur = idx == 0 ? a.sel_msgs[0] : (idx == 1 ? a.sel_msgs[1] : a.sel_msgs[2]);
+  }
+  sweep<EXT, MULTI>(a, cur, a.msgs_out, a.it, a.write_undamped, PeersOfArgs{a}, smem);
 }
 
 // ---- whole BP run in ONE cooperative launch (reference _run_bp, state.py:97-124) ----------------------------------
@@ -524,6 +550,7 @@ struct RunArgs {
   // and the line are in THIS GPU's memory, read through its L2 (cp.async.cg, ld.volatile), which is where the peer's
   // stores land in the order its fence gave them.
   int fence_mode;
+  int zigzag;                        // 1: odd sweeps of the single-GPU run visit the groups in reverse (L2 reuse)
   unsigned long long* trace;       // profiling aid (bqa_b200_set_bp_trace): 5 globaltimer stamps per sweep from CTA 0, or null
 };
 
@@ -598,7 +625,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_bp_run_d3D4(const __grid_consta
       const int cur = (r.parity + it) & 1;
       if (tracing) r.trace[5 * it] = globaltimer_ns();
       // cap reached: the undamped sweep is kept (state.py:122-123)
-      sweep<false, MULTI>(a, r.msgs[cur], r.msgs[cur ^ 1], it, it == r.max_iters - 1, PeersOfRun{r, cur ^ 1}, smem);
+      sweep<false, MULTI>(a, r.msgs[cur], r.msgs[cur ^ 1], it, it == r.max_iters - 1, PeersOfRun{r, cur ^ 1}, smem, 0,
+                          0x7fffffff, (it & r.zigzag) != 0);
       if (tracing) r.trace[5 * it + 1] = globaltimer_ns();
       if (!grid_barrier(counter, generation, a.status, r.timeout_cycles)) return;
       if (tracing) { r.trace[5 * it + 2] = globaltimer_ns(); r.trace[5 * it + 3] = r.trace[5 * it + 4] = r.trace[5 * it + 2]; }
@@ -660,22 +688,25 @@ __global__ void __launch_bounds__(kThreads, 1) k_bp_run_d3D4(const __grid_consta
       // one system-scope fence per rank and sweep: every warp releases its halo stores at gpu scope (fence + counter),
       // the warp that completes the count fences at system scope -- cumulativity carries the other warps' stores -- and
       // stores the lines; everybody else is already sweeping interior groups.
-      sweep<false, MULTI>(a, r.msgs[cur], r.msgs[nxt], it, undamped, PeersOfRun{r, nxt}, smem, 0, gb);
-      __syncwarp();
-      if ((threadIdx.x & 31) == 0) {
-        __threadfence();
-        if (atomicAdd(&s_bdone, 1u) == (unsigned)(it + 1) * kWarps - 1u) {
+      // ONE pass over all groups (boundary groups come first in the node order): the copies of a warp's first interior
+      // group are in flight while it finishes its last boundary group and signals
+      auto boundary_done = [&]() {
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) {
           __threadfence();
-          if (atomicAdd(bcount, 1u) == (unsigned)(it + 1) * gridDim.x - 1u) {
-            fence_release_sys(r.fence_mode);
-            for (int q = 0; q < r.world; ++q)
-              if (q != r.rank) st_volatile_v4(r.peer_xchg[q] + (it & 3) * BQA_MAX_PEERS + r.rank, make_uint4(seq, seq, seq, seq));
+          if (atomicAdd(&s_bdone, 1u) == (unsigned)(it + 1) * kWarps - 1u) {
+            __threadfence();
+            if (atomicAdd(bcount, 1u) == (unsigned)(it + 1) * gridDim.x - 1u) {
+              fence_release_sys(r.fence_mode);
+              for (int q = 0; q < r.world; ++q)
+                if (q != r.rank) st_volatile_v4(r.peer_xchg[q] + (it & 3) * BQA_MAX_PEERS + r.rank, make_uint4(seq, seq, seq, seq));
+            }
           }
+          if (tracing) r.trace[5 * it + 1] = globaltimer_ns();
         }
-      }
-      if (tracing) r.trace[5 * it + 1] = globaltimer_ns();
+      };
       // 2. interior groups, grid barrier (local messages and local residual of the sweep complete)
-      sweep<false, MULTI>(a, r.msgs[cur], r.msgs[nxt], it, undamped, PeersOfRun{r, nxt}, smem, gb, groups);
+      sweep<false, MULTI>(a, r.msgs[cur], r.msgs[nxt], it, undamped, PeersOfRun{r, nxt}, smem, 0, groups, false, gb, boundary_done);
       if (!grid_barrier(counter, generation, a.status, r.timeout_cycles)) return;
       if (tracing) r.trace[5 * it + 2] = globaltimer_ns();
       // 3. RESID line of this sweep (read by the peers one sweep later)
@@ -764,14 +795,39 @@ int launch_fast_bp_run_d3D4(long long B, const void* T, void* msgs0, void* msgs1
   r.trace = g_bp_trace;
   static const int fence_mode = [] { const char* e = getenv("BQA_B200_FENCE"); return e ? atoi(e) : 2; }();
   r.fence_mode = fence_mode;
+  static const int zigzag = [] { const char* e = getenv("BQA_B200_BP_ZIGZAG"); return e ? atoi(e) & 1 : 1; }();
+  r.zigzag = zigzag;
   const long long groups = (B + 3) / 4;
   long long grid = (groups + kWarps - 1) / kWarps;
   if (grid > sm_count()) grid = sm_count();
   void* params[] = {&r};
   const bool multi = world > 1 || a.remote_pos != nullptr;
   const void* fn = multi ? (const void*)k_bp_run_d3D4<true> : (const void*)k_bp_run_d3D4<false>;
-  cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(kThreads), params, (size_t)kSmem, st);
-  if (e != cudaSuccess) return set_error("cudaLaunchCooperativeKernel(k_bp_run_d3D4): %s", cudaGetErrorString(e));
+  // experiment switch: BQA_B200_BP_L2_PERSIST_MB > 0 pins that many MB of T in L2 for the run (access policy window)
+  static const long long persist_mb = [] { const char* e = getenv("BQA_B200_BP_L2_PERSIST_MB"); return e ? atoll(e) : 0LL; }();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = (size_t)kSmem; cfg.stream = st;
+  cudaLaunchAttribute attrs[2];
+  attrs[0].id = cudaLaunchAttributeCooperative; attrs[0].val.cooperative = 1;
+  cfg.attrs = attrs; cfg.numAttrs = 1;
+  if (persist_mb > 0 && !multi) {
+    static bool limit_set[64] = {};
+    if (dev >= 0 && dev < 64 && !limit_set[dev]) {
+      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)persist_mb << 20);
+      limit_set[dev] = true;
+    }
+    const size_t t_bytes = (size_t)B * 1024, want = (size_t)persist_mb << 20;
+    cudaAccessPolicyWindow w{};
+    w.base_ptr = const_cast<void*>(T);
+    w.num_bytes = t_bytes;
+    w.hitRatio = t_bytes <= want ? 1.f : (float)((double)want / (double)t_bytes);
+    w.hitProp = cudaAccessPropertyPersisting;
+    w.missProp = cudaAccessPropertyStreaming;
+    attrs[1].id = cudaLaunchAttributeAccessPolicyWindow; attrs[1].val.accessPolicyWindow = w;
+    cfg.numAttrs = 2;
+  }
+  cudaError_t e = cudaLaunchKernelExC(&cfg, fn, params);
+  if (e != cudaSuccess) return set_error("cudaLaunchKernelExC(k_bp_run_d3D4, cooperative): %s", cudaGetErrorString(e));
   return after_launch("bp_run(d3D4)");
 }
 
@@ -783,7 +839,7 @@ bool fast_d3D4_available(int prec, int degree, int D, long long B) {
 int launch_fast_msgs_d3D4(bool ext, long long B, const void* T, const void* msgs_cur, void* msgs_out,
                           const int32_t* in_pos, const int32_t* out_pos, const void* edge_ampls, double ztime,
                           double damping, int write_undamped, double bp_eps, int it, void* resid, int32_t* status,
-                          const int32_t* remote_pos, void* const* peers, cudaStream_t st) {
+                          const int32_t* remote_pos, void* const* peers, cudaStream_t st, const AfterRun* after) {
   using namespace fast;
   if (B == 0) return 0;
   static bool configured[64] = {};           // the attribute is per device
@@ -804,6 +860,15 @@ int launch_fast_msgs_d3D4(bool ext, long long B, const void* T, const void* msgs
   a.write_undamped = write_undamped; a.it = it; a.resid = (float*)resid; a.status = status;
   a.remote_pos = peers ? remote_pos : nullptr;
   for (int q = 0; q < BQA_MAX_PEERS; ++q) a.peers[q] = peers ? (unsigned char*)peers[q] : nullptr;
+  if (after) {
+    if (!ext || !after->status || after->nbuf < 2 || after->nbuf > 3 || !after->msgs[0] || !after->msgs[1] ||
+        (after->nbuf == 3 && !after->msgs[2]))
+      return set_error("ext_msgs_after_run: needs the run's status words and its %d message buffers", after->nbuf);
+    a.sel_status = after->status;
+    for (int k = 0; k < 3; ++k) a.sel_msgs[k] = (const float2*)after->msgs[k];
+    a.sel_nbuf = after->nbuf; a.sel_max_iters = after->max_iters;
+    a.sel_parity = ((after->parity % after->nbuf) + after->nbuf) % after->nbuf;
+  }
   const long long groups = (B + 3) / 4;
   long long grid = (groups + kWarps - 1) / kWarps;
   if (grid > sm_count()) grid = sm_count();

@@ -60,10 +60,17 @@ int launch_multiclass(int kind, int n_classes, const bqa_b200_class* cls, int D,
 
 // specialised kernels (bqa_fast_d3D4.cu): degree 3, D = 4, complex64
 bool fast_d3D4_available(int prec, int degree, int D, long long B);
+// extended messages enqueued behind a single-launch BP run: the buffers and status words the kernel selects from
+struct AfterRun {
+  const void* msgs[3];
+  int nbuf, parity, max_iters;
+  const int32_t* status;
+};
 int launch_fast_msgs_d3D4(bool ext, long long B, const void* T, const void* msgs_cur, void* msgs_out,
                           const int32_t* in_pos, const int32_t* out_pos, const void* edge_ampls, double ztime,
                           double damping, int write_undamped, double bp_eps, int it, void* resid, int32_t* status,
-                          const int32_t* remote_pos, void* const* peers, cudaStream_t st);
+                          const int32_t* remote_pos, void* const* peers, cudaStream_t st,
+                          const AfterRun* after = nullptr);
 // the whole BP run of the degree class in one cooperative launch (bqa_fast_d3D4.cu)
 int launch_fast_bp_run_d3D4(long long B, const void* T, void* msgs0, void* msgs1, int parity, const int32_t* in_pos,
                             const int32_t* out_pos, double damping, double bp_eps, int max_iters, void* resid,

@@ -227,10 +227,21 @@ int launch_multiclass(int kind, int n_classes, const bqa_b200_class* cls, int D,
   long long blocks = (total + 3) / 4;
   const long long cap = (long long)BQA_GENERIC_MAX_WARPS / 4;
   if (blocks > cap) blocks = cap;
-  // scratch in shared memory when 4 warps' worth fits beside a second CTA (D <= 8 at degree 3 in complex64, ...): the
-  // generic per-node code then never leaves the SM (in the global workspace every intermediate is written through to L2)
+  // per-warp scratch in shared memory only where it measured faster (r2, profiles/r2_small_configs.jsonl): a footprint the
+  // L1 does not hold (>= 18 KB per warp: D = 8 in complex64) on a graph small enough that the CTAs it needs are resident
+  // anyway -- heavy-hex 127 at D <= 8: 436 -> 459 steps/s.  Elsewhere the global workspace wins: smaller footprints stay
+  // in L1 (grid 20x20, D <= 4: 1258 vs 1216 steps/s), and on a large graph the per-node code is latency bound and the
+  // warps lost to the shared-memory footprint cost more than the L2 round trips (20k nodes at D = 8: BP run 29.5 ms
+  // against 37.4 ms with 78 KB per CTA).  BQA_B200_MC_SMEM=0/1 forces the choice.
   size_t smem = per_warp * sizeof(cx<R>) * 4;
-  a.ws_in_smem = smem <= 100 * 1024 ? 1 : 0;
+  static const int smem_mode = [] { const char* e = getenv("BQA_B200_MC_SMEM"); return e ? atoi(e) : -1; }();
+  {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long fit = smem ? (long long)((200 * 1024) / smem) * sms : 0;     // CTAs resident with this footprint
+    a.ws_in_smem = smem_mode >= 0 ? (smem_mode != 0 && smem <= 100 * 1024) : (smem >= 72 * 1024 && smem <= 100 * 1024 && blocks <= fit);
+  }
   if (!a.ws_in_smem) smem = 0;
   const void* fn = kind == 0 ? (const void*)k_mc_ext<R> : (kind == 1 ? (const void*)k_mc_apply<R> : (const void*)k_mc_bp_run<R>);
   if (smem > 48 * 1024) {

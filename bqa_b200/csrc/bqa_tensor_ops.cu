@@ -258,7 +258,7 @@ __global__ void k_svd(long long batch, int n, const cx<R>* __restrict__ a, cx<R>
   for (long long b = warp; b < batch; b += nwarps) {
     for (int i = lane; i < nn; i += 32) A[i] = a[b * nn + i];
     g.sync();
-    jacobi_svd<R>(g, n, A, V, sigma, order);
+    jacobi_svd<R>(g, n, n, A, V, sigma, order);
     for (int i = lane; i < nn; i += 32) {
       const int r = i / n, c = i - r * n;
       const int col = order[c];

@@ -183,6 +183,14 @@ class Engine:
         # collapses (backends.py:297-303), so the step is enqueued without waiting for the column maxima and they are
         # checked with the BP control block, in the step's only host read; a wrong guess redoes the update.
         self.speculate = os.environ.get("BQA_B200_SPECULATE", "1") != "0"
+        # extended messages of the next step enqueued behind the BP run, before the host reads the run's outcome
+        # (run_layer(next_ztime=...) / run_layers): the GPU never waits for the host between two steps
+        self.ext_ahead = os.environ.get("BQA_B200_EXT_AHEAD", "1") != "0"
+        self._next_ztime = None                 # lookahead of the run_layer call in progress
+        self._ext_done_for = None               # (ztime, D) of extended messages already sitting in self._ext
+        self._side_stream = torch.cuda.Stream(self.dev) if self.cuda else None
+        self._bp_done_event = torch.cuda.Event() if self.cuda else None
+        self._read_after_event = False
         # edge order of the n = 8 canonicalizer kernel (bqa_b200_canonicalize_ordered).  OFF by default: measured on the
         # 100k benchmark, regrouping the edges by last step's Jacobi sweep counts lowers the sweeps a warp runs only from
         # 5.34 to 5.19 (every 8 steps) / 5.09 (every step): the slow matrices of one step are not the slow ones of the
@@ -218,7 +226,17 @@ class Engine:
     def _read_ctrl(self) -> np.ndarray:
         """Host copy of the whole control block (page-locked staging buffer: one asynchronous copy + stream sync)."""
         if self._ctrl_host is None:
+            self._read_after_event = False
             ctrl = self._to_host(self._ctrl)
+        elif self._read_after_event:
+            # work of the next step is already queued behind the BP run: copy on a side stream that waits for the run only
+            self._read_after_event = False
+            self.host_reads += 1
+            self._side_stream.wait_event(self._bp_done_event)
+            with torch.cuda.stream(self._side_stream):
+                self._ctrl_host.copy_(self._ctrl, non_blocking=True)
+            self._side_stream.synchronize()
+            ctrl = self._ctrl_host.numpy().copy()
         else:
             self.host_reads += 1
             self._ctrl_host.copy_(self._ctrl, non_blocking=True)
@@ -325,6 +343,7 @@ class Engine:
         D = int(snap["D"])
         if not 1 <= D <= self.Dmax:
             raise ValueError(f"bond dimension {D} outside [1, {self.Dmax}]")
+        self._ext_done_for = None
         np_c = np.complex64 if self.precision == "single" else np.complex128
         pinned = snap.get("_pinned", {})
 
@@ -452,7 +471,25 @@ class Engine:
         if not ok:
             self._no_bp_run[self.D] = True
             return None
+        if self._next_ztime is not None:
+            self._enqueue_ext_ahead(c, self._next_ztime)
         return self._read_bp_run()
+
+    def _enqueue_ext_ahead(self, c, ztime: float) -> None:
+        """Extended messages of the next step behind the BP run just launched (bqa_b200_ext_msgs_after_run: the kernel
+        picks the message buffer from the run's status words); the control-block read then waits for the run only."""
+        st = torch.cuda.current_stream(self.dev)
+        self._bp_done_event.record(st)
+        m2 = self._msgs[2].data_ptr() if self._nbuf > 2 else None
+        ok = self.lib.ext_msgs_after_run(self.prec, c.degree, self.D, c.B, c.T[c.cur].data_ptr(), self._msgs[0].data_ptr(),
+                                         self._msgs[1].data_ptr(), m2, self._nbuf, self._msgs_cur, self.max_iters,
+                                         self._status.data_ptr(), self._ext.data_ptr(), c.in_pos.data_ptr(),
+                                         c.out_pos.data_ptr(), c.edge_ampls.data_ptr(), float(ztime),
+                                         c.remote_pos.data_ptr() if self._peer_targets("ext") is not None else None,
+                                         self._peer_targets("ext"), st.cuda_stream)
+        if ok:
+            self._ext_done_for = (float(ztime), self.D)
+            self._read_after_event = True
 
     def _read_bp_run(self):
         """(converged, sweeps, residuals) of a single-launch BP run: the step's one read of the control block"""
@@ -468,6 +505,7 @@ class Engine:
     def run_bp(self) -> int:
         max_it = self.max_iters
         assert max_it > 0, "max_bp_iter_number must be positive"      # reference: assert best_msgs is not None
+        self._ext_done_for = None                                     # the messages change
         self._ensure_ws(self.D, self.D)
         self._ctrl_bp.zero_()
         self._before_bp()
@@ -526,12 +564,26 @@ class Engine:
     def _reduce_colmax(self, colmax: torch.Tensor) -> None:
         """Hook for the partitioned engine (all-reduce max); no-op on one GPU."""
 
+    def run_layers(self, layers) -> None:
+        """A sequence of annealing steps ({"xtime": .., "ztime": ..} dicts, the reference's instruction format): every
+        step but the last one announces the next step's ztime to run_layer."""
+        layers = list(layers)
+        for k, ins in enumerate(layers):
+            nxt = layers[k + 1]["ztime"] if k + 1 < len(layers) else None
+            self.run_layer(ins["xtime"], ins["ztime"], next_ztime=nxt)
+
     @_on_device
-    def run_layer(self, xtime: float, ztime: float) -> None:
+    def run_layer(self, xtime: float, ztime: float, next_ztime: float | None = None) -> None:
+        """One annealing step.  ``next_ztime``: ztime of the step that follows, when the caller knows it -- its extended
+        messages are then enqueued behind this step's BP run before the host reads the run's outcome (same kernels,
+        same inputs, same results; the step after that finds them ready)."""
         D = self.D
         st = self._stream()
         self._ensure_ws(D, min(2 * D, self.Dmax))
         self._ensure_edge_buffers(D)
+        ahead, self._ext_done_for = self._ext_done_for, None
+        if ahead == (float(ztime), D):
+            return self._rest_of_layer(D, st, xtime, ztime, next_ztime)
         cur = self.msgs_buffer
         peers = self._peer_targets("ext")
         multi = self._use_multiclass()
@@ -549,6 +601,9 @@ class Engine:
                 self.lib.ext_msgs(*args, st)
             else:
                 self.lib.ext_msgs_p2p(*args, c.remote_pos.data_ptr(), peers, st)
+        self._rest_of_layer(D, st, xtime, ztime, next_ztime)
+
+    def _rest_of_layer(self, D: int, st: int, xtime: float, ztime: float, next_ztime) -> None:
         self._exchange_ext()
         self._colmax.zero_()
         self._canonicalize(D, st)
@@ -561,7 +616,12 @@ class Engine:
             colmax = self._to_host(self._colmax)[: 2 * D].astype(np.float64)      # host sync: the bond dimension changes
             Dn, err = self._truncation(colmax, D)
         n_bp = len(self.stats["bp_sweeps"])
-        self._apply_and_bp(D, Dn, xtime, ztime)
+        # lookahead only where a mis-speculated bond dimension cannot occur after the fact: the check below redoes the step
+        self._next_ztime = next_ztime if (speculative and self.ext_ahead and next_ztime is not None) else None
+        try:
+            self._apply_and_bp(D, Dn, xtime, ztime)
+        finally:
+            self._next_ztime = None
         if speculative:
             rb = self._ctrl_rbytes + 16
             colmax = self._ctrl_last[rb: rb + 2 * D * self._colmax.element_size()].view(self.np_rdtype).astype(np.float64)
@@ -571,6 +631,7 @@ class Engine:
                     c.cur = 1 - c.cur
                 del self.stats["bp_sweeps"][n_bp:], self.stats["bp_dist"][n_bp:]
                 self.D, Dn = D, Dn_true
+                self._ext_done_for = None                                         # computed from the discarded state
                 self._apply_and_bp(D, Dn, xtime, ztime)
         self.stats["bond_dims"].append(Dn)
         self.stats["trunc_err"].append(err)

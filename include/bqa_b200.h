@@ -111,6 +111,20 @@ int bqa_b200_ext_msgs_p2p(int prec, int degree, int D, long long B, const void* 
  * zero-initialised; seq: 1, 2, 3, ... per call.  A peer that never arrives sets status[3] after ~10 s. */
 int bqa_b200_sweep_sync(int prec, int rank, int world, void* const* peer_resid, int it, void* const* peer_flags,
                         unsigned seq, int32_t* status, void* stream);
+/* Extended messages of the NEXT annealing step, enqueued directly behind bqa_b200_bp_run on the same stream -- before
+ * the host has read the run's outcome.  The kernel selects the buffer the run left the messages in from the run's
+ * status words (converged: the input of the converging sweep, msgs[(parity + sweeps - 1) % nbuf]; cap reached: the
+ * output of the last sweep, msgs[(parity + max_iters) % nbuf]; state.py:118-124), so the GPU works on step k + 1 while
+ * the host reads step k's control block.  nbuf = 2 (one GPU, msgs2 = NULL) or 3 (bqa_b200_bp_run across GPUs);
+ * parity / max_iters / status: the values given to that bp_run call.  Returns 2 when the shape has no such kernel
+ * (the caller then reads the outcome first and calls bqa_b200_ext_msgs).  Replaces: State._get_extended_msgs on
+ * the messages _run_bp returned, src/bqa/state.py:127-139 after :97-124. */
+int bqa_b200_ext_msgs_after_run(int prec, int degree, int D, long long B, const void* T, const void* msgs0,
+                                const void* msgs1, const void* msgs2, int nbuf, int parity, int max_iters,
+                                const int32_t* status, void* ext, const int32_t* in_pos, const int32_t* out_pos,
+                                const void* edge_ampls, double ztime, const int32_t* remote_pos, void* const* peers,
+                                void* stream);
+
 /* The whole BP run of a degree class in ONE cooperative launch (reference _run_bp, state.py:97-124): persistent CTAs
  * iterate sweep -> grid barrier -> residual test on the device.  On return status[0] = converged (0 / 1), status[1] =
  * the reference's sweep count; status[2] (grid-barrier counter) and resid -- (max_iters + 2) x 2 reals, the tail is used

@@ -60,9 +60,12 @@ def main():
     for n in names:
         setattr(lib, n, wrap(n))
     n0 = len(eng.stats["bp_sweeps"])
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStart()       # ncu --profile-from-start off: only the steps at the final D are captured
     for ins in layers[k:k + args.steps]:
         eng.run_layer(ins["xtime"], ins["ztime"])
     torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStop()
     for n in names:
         setattr(lib, n, orig[n])
     out = {"qubits": args.qubits, "D": eng.D, "precision": args.precision, "steps_to_reach_D": k, "timed_steps": args.steps,

@@ -229,10 +229,10 @@ def test_checkpoint_resume_continues_bit_for_bit(tmp_path, emu):
         pass
 
     class Flaky(Engine):
-        def run_layer(self, xtime, ztime):
+        def run_layer(self, xtime, ztime, next_ztime=None):
             if len(self.stats["bond_dims"]) == 11:
                 raise Crash("power cut")
-            return super().run_layer(xtime, ztime)
+            return super().run_layer(xtime, ztime, next_ztime=next_ztime)
 
     with pytest.raises(Crash):
         run_context(ctx, precision="double", engine_cls=Flaky, checkpoint=path, checkpoint_every=4, _testing_lib=emu)

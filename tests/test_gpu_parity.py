@@ -518,6 +518,39 @@ def test_isolated_qubit_gpu(lib, precision, tol):
     assert len(res["measurement_outcomes"]) == 4
 
 
+def test_ext_msgs_enqueued_behind_the_bp_run(lib):
+    """run_layers / run_layer(next_ztime=...): the next step's extended messages are enqueued behind the BP run and pick
+    the message buffer on the device (bqa_b200_ext_msgs_after_run).  Same kernels on the same inputs: results identical
+    to the step-by-step path, also when runs hit the iteration cap (the other buffer rule) and after a state upload."""
+    from bqa_b200.config import config_to_context
+    from bqa_b200.engine import Engine
+    for cfg in (_rr_config(3000, 24, 4.8, []), _rr_config(1000, 24, 4.8, [], max_bp_iter_number=3, damping=0.2),
+                _rr_config(1000, 24, 4.8, [], max_bp_iter_number=4)):
+        ctx = config_to_context(cfg)
+        layers = [i for i in ctx.instructions if isinstance(i, dict)]
+        out, used = {}, 0
+        for ahead in (False, True):
+            eng = Engine(ctx, precision="single")
+            eng.ext_ahead = ahead
+            orig = eng.lib.ext_msgs_after_run
+            calls = []
+            eng.lib.ext_msgs_after_run = lambda *a: (calls.append(1), orig(*a))[1]
+            try:
+                eng.run_layers(layers[:-4])
+                snap = eng.state_to_host()
+                eng.run_layer(layers[-4]["xtime"], layers[-4]["ztime"], next_ztime=layers[-3]["ztime"])
+                eng.load_state(snap)                      # drops the extended messages computed ahead
+                eng.run_layers(layers[-4:])
+            finally:
+                eng.lib.ext_msgs_after_run = orig
+            used += len(calls) if ahead else 0
+            assert ahead or not calls
+            out[ahead] = (eng.bloch_vectors(), eng.stats["bp_sweeps"], eng.stats["bond_dims"])
+        assert used > 0 and out[True][2][-1] == 4
+        assert out[True][1] == out[False][1] and out[True][2] == out[False][2]
+        assert np.array_equal(out[True][0], out[False][0])
+
+
 def test_single_launch_bp_run_equals_per_sweep_launches(lib):
     """bqa_b200_bp_run (the whole BP loop in one cooperative launch with in-kernel grid barriers) against the
     per-sweep launches of bqa_b200_bp_sweep: same arithmetic, so identical sweep counts, residuals and marginals."""

@@ -151,10 +151,10 @@ def _worker_ckpt(rank, world, port, cfg, emu_path, path, crash_after, out):
         from bqa_b200.core import run_context
 
         class Flaky(PartitionedEngine):
-            def run_layer(self, xtime, ztime):
+            def run_layer(self, xtime, ztime, next_ztime=None):
                 if crash_after is not None and len(self.stats["bond_dims"]) == crash_after:
                     raise KeyboardInterrupt("power cut")
-                return super().run_layer(xtime, ztime)
+                return super().run_layer(xtime, ztime, next_ztime=next_ztime)
         try:
             res = run_context(config_to_context(cfg), precision="double", engine_cls=Flaky, checkpoint=path,
                               checkpoint_every=4, resume=True, _testing_lib=_lib.bind(emu_path))

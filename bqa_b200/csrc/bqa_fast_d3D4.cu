@@ -803,31 +803,9 @@ int launch_fast_bp_run_d3D4(long long B, const void* T, void* msgs0, void* msgs1
   void* params[] = {&r};
   const bool multi = world > 1 || a.remote_pos != nullptr;
   const void* fn = multi ? (const void*)k_bp_run_d3D4<true> : (const void*)k_bp_run_d3D4<false>;
-  // experiment switch: BQA_B200_BP_L2_PERSIST_MB > 0 pins that many MB of T in L2 for the run (access policy window)
-  static const long long persist_mb = [] { const char* e = getenv("BQA_B200_BP_L2_PERSIST_MB"); return e ? atoll(e) : 0LL; }();
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = (size_t)kSmem; cfg.stream = st;
-  cudaLaunchAttribute attrs[2];
-  attrs[0].id = cudaLaunchAttributeCooperative; attrs[0].val.cooperative = 1;
-  cfg.attrs = attrs; cfg.numAttrs = 1;
-  if (persist_mb > 0 && !multi) {
-    static bool limit_set[64] = {};
-    if (dev >= 0 && dev < 64 && !limit_set[dev]) {
-      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)persist_mb << 20);
-      limit_set[dev] = true;
-    }
-    const size_t t_bytes = (size_t)B * 1024, want = (size_t)persist_mb << 20;
-    cudaAccessPolicyWindow w{};
-    w.base_ptr = const_cast<void*>(T);
-    w.num_bytes = t_bytes;
-    w.hitRatio = t_bytes <= want ? 1.f : (float)((double)want / (double)t_bytes);
-    w.hitProp = cudaAccessPropertyPersisting;
-    w.missProp = cudaAccessPropertyStreaming;
-    attrs[1].id = cudaLaunchAttributeAccessPolicyWindow; attrs[1].val.accessPolicyWindow = w;
-    cfg.numAttrs = 2;
-  }
-  cudaError_t e = cudaLaunchKernelExC(&cfg, fn, params);
-  if (e != cudaSuccess) return set_error("cudaLaunchKernelExC(k_bp_run_d3D4, cooperative): %s", cudaGetErrorString(e));
+  // (pinning T in L2 with an access-policy window was tried in r2: no change at 48 MB, see profiles/r2_bp_l2_experiments.md)
+  cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(kThreads), params, (size_t)kSmem, st);
+  if (e != cudaSuccess) return set_error("cudaLaunchCooperativeKernel(k_bp_run_d3D4): %s", cudaGetErrorString(e));
   return after_launch("bp_run(d3D4)");
 }
 

@@ -112,17 +112,23 @@ BQA_HD int ipow(int b, int e) {
 // ------------------------------------------------------------------------------------------------
 // buf viewed as [outer][D][inner]; every fibre v (fixed outer, inner) becomes m . v with m[a][b] row-major.
 // One fibre per lane => safe in place.
-template <typename R, typename G>
-BQA_HDN void mode_product_inplace(G g, cx<R>* buf, int outer, int D, int inner, const cx<R>* m) {
+// DT > 0: the bond dimension as a compile-time constant (same operations in the same order, loops unrolled, the fibre
+// in registers instead of a dynamically indexed local array); DT = 0: any D <= BQA_MAX_D.
+template <typename R, typename G, int DT = 0>
+BQA_HDN void mode_product_inplace(G g, cx<R>* buf, int outer, int D_, int inner, const cx<R>* m) {
+  const int D = DT ? DT : D_;
   const int nf = outer * inner;
   for (int f = g.rank(); f < nf; f += g.size()) {
     const int o = f / inner, i = f - o * inner;
     cx<R>* p = buf + (size_t)o * D * inner + i;
-    cx<R> v[BQA_MAX_D];
-    for (int b = 0; b < D; ++b) v[b] = p[(size_t)b * inner];
-    for (int a = 0; a < D; ++a) {
+    cx<R> v[DT ? DT : BQA_MAX_D];
+#pragma unroll
+    for (int b = 0; b < (DT ? DT : D); ++b) v[b] = p[(size_t)b * inner];
+#pragma unroll
+    for (int a = 0; a < (DT ? DT : D); ++a) {
       cx<R> acc = mk<R>(0, 0);
-      for (int b = 0; b < D; ++b) cmac(acc, m[a * D + b], v[b]);
+#pragma unroll
+      for (int b = 0; b < (DT ? DT : D); ++b) cmac(acc, m[a * D + b], v[b]);
       p[(size_t)a * inner] = acc;
     }
   }
@@ -136,9 +142,10 @@ BQA_HDN void mode_product_inplace(G g, cx<R>* buf, int outer, int D, int inner, 
 // P and E are scratch buffers of 2 * D^d elements.  Leg contractions are shared through the prefix P
 // (legs < k already contracted): (d-1) + d(d-1)/2 mode products instead of the reference's d(d-1).
 // ------------------------------------------------------------------------------------------------
-template <typename R, typename G>
-BQA_HDN void node_gram(G g, int d, int D, const cx<R>* T, const cx<R>* const* msgs, cx<R>* P, cx<R>* E,
-                       cx<R>* gram) {
+template <typename R, typename G, int DT = 0>
+BQA_HDN void node_gram_impl(G g, int d, int D_, const cx<R>* T, const cx<R>* const* msgs, cx<R>* P, cx<R>* E,
+                            cx<R>* gram) {
+  const int D = DT ? DT : D_;
   const int W = 2 * ipow(D, d);
   for (int i = g.rank(); i < W; i += g.size()) P[i] = T[i];
   g.sync();
@@ -146,23 +153,36 @@ BQA_HDN void node_gram(G g, int d, int D, const cx<R>* T, const cx<R>* const* ms
     for (int i = g.rank(); i < W; i += g.size()) E[i] = P[i];
     g.sync();
     for (int j = k + 1; j < d; ++j)
-      mode_product_inplace<R>(g, E, 2 * ipow(D, j), D, ipow(D, d - 1 - j), msgs[j]);
+      mode_product_inplace<R, G, DT>(g, E, 2 * ipow(D, j), D, ipow(D, d - 1 - j), msgs[j]);
     // closing contraction over everything but leg k
     const int pre = ipow(D, k), post = ipow(D, d - 1 - k);
     const int half = W / 2;
     for (int o = g.rank(); o < 2 * D * D; o += g.size()) {
       const int p = o / (D * D), x = (o / D) % D, y = o % D;
       cx<R> acc = mk<R>(0, 0);
-      const cx<R>* tb = T + (size_t)p * half;
-      const cx<R>* eb = E + (size_t)p * half;
-      for (int a = 0; a < pre; ++a)
-        for (int i = 0; i < post; ++i)
-          cmacc(acc, tb[((size_t)a * D + x) * post + i], eb[((size_t)a * D + y) * post + i]);
+      const cx<R>* tb = T + (size_t)p * half + (size_t)x * post;
+      const cx<R>* eb = E + (size_t)p * half + (size_t)y * post;
+      const int step = D * post;
+      for (int a = 0; a < pre; ++a, tb += step, eb += step) {
+#pragma unroll 4
+        for (int i = 0; i < post; ++i) cmacc(acc, tb[i], eb[i]);
+      }
       gram[(size_t)k * 2 * D * D + o] = acc;
     }
     g.sync();
-    if (k + 1 < d) mode_product_inplace<R>(g, P, 2 * pre, D, post, msgs[k]);
+    if (k + 1 < d) mode_product_inplace<R, G, DT>(g, P, 2 * pre, D, post, msgs[k]);
   }
+}
+
+// bond dimensions 2, 4, 8 get the compile-time variant (D = 8 in the r2 capture: index arithmetic, loop control and the
+// dynamically indexed fibre made up most of the 7.5 G warp instructions of a 20k-node BP run)
+template <typename R, typename G>
+BQA_HDN void node_gram(G g, int d, int D, const cx<R>* T, const cx<R>* const* msgs, cx<R>* P, cx<R>* E,
+                       cx<R>* gram) {
+  if (D == 8) node_gram_impl<R, G, 8>(g, d, D, T, msgs, P, E, gram);
+  else if (D == 4) node_gram_impl<R, G, 4>(g, d, D, T, msgs, P, E, gram);
+  else if (D == 2) node_gram_impl<R, G, 2>(g, d, D, T, msgs, P, E, gram);
+  else node_gram_impl<R, G, 0>(g, d, D, T, msgs, P, E, gram);
 }
 
 // complex principal square roots of cos(theta), sin(theta) and the ZZ half-gate factors

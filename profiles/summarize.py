@@ -67,7 +67,7 @@ def kernel(src, dst, pattern=""):
                     out.write(f"| {h.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', '')} | {r[i]} |\n")
             out.write("\n")
         r = data[0]
-        if "k_msgs" in r[name_i] or "bp" in r[name_i]:
+        if "k_msgs" in r[name_i] and "bp_run" not in r[name_i]:          # a per-sweep launch only (a bp_run launch = many sweeps)
             def mb(k):
                 v, u = float(r[hdr.index(k)]), units[hdr.index(k)]
                 return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]

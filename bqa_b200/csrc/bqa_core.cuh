@@ -174,13 +174,13 @@ BQA_HDN void node_gram_impl(G g, int d, int D_, const cx<R>* T, const cx<R>* con
   }
 }
 
-// bond dimensions 2, 4, 8, 16 get the compile-time variant (D = 8 in the r2 capture: index arithmetic, loop control and the
+// bond dimensions 2, 4, 8 get the compile-time variant (16 as well was measured and dropped: the unrolled 16 x 16
+// products raise the kernels' register count from 96 to 128 and cost every shape occupancy: D = 16 BP run 544 -> 631 ms) (D = 8 in the r2 capture: index arithmetic, loop control and the
 // dynamically indexed fibre made up most of the 7.5 G warp instructions of a 20k-node BP run)
 template <typename R, typename G>
 BQA_HDN void node_gram(G g, int d, int D, const cx<R>* T, const cx<R>* const* msgs, cx<R>* P, cx<R>* E,
                        cx<R>* gram) {
-  if (D == 16) node_gram_impl<R, G, 16>(g, d, D, T, msgs, P, E, gram);
-  else if (D == 8) node_gram_impl<R, G, 8>(g, d, D, T, msgs, P, E, gram);
+  if (D == 8) node_gram_impl<R, G, 8>(g, d, D, T, msgs, P, E, gram);
   else if (D == 4) node_gram_impl<R, G, 4>(g, d, D, T, msgs, P, E, gram);
   else if (D == 2) node_gram_impl<R, G, 2>(g, d, D, T, msgs, P, E, gram);
   else node_gram_impl<R, G, 0>(g, d, D, T, msgs, P, E, gram);

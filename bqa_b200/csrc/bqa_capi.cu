@@ -184,9 +184,9 @@ int bqa_b200_ext_msgs_classes(int prec, int n_classes, const bqa_b200_class* cls
   cudaStream_t st = (cudaStream_t)stream;
   if (prec == BQA_C64)
     return launch_multiclass<float>(0, n_classes, cls, D, D, (void*)msgs_cur, ext, 0, nullptr, nullptr, ztime, 0.0, 0.0, 0.0,
-                                    0, nullptr, nullptr, workspace, workspace_bytes, st);
+                                    0, nullptr, nullptr, workspace, workspace_bytes, st, g_kernel_mode.load() != 1);
   return launch_multiclass<double>(0, n_classes, cls, D, D, (void*)msgs_cur, ext, 0, nullptr, nullptr, ztime, 0.0, 0.0, 0.0,
-                                   0, nullptr, nullptr, workspace, workspace_bytes, st);
+                                   0, nullptr, nullptr, workspace, workspace_bytes, st, g_kernel_mode.load() != 1);
 }
 
 int bqa_b200_apply_update_classes(int prec, int n_classes, const bqa_b200_class* cls, int D, int D_new, const void* canon,
@@ -198,9 +198,9 @@ int bqa_b200_apply_update_classes(int prec, int n_classes, const bqa_b200_class*
   cudaStream_t st = (cudaStream_t)stream;
   if (prec == BQA_C64)
     return launch_multiclass<float>(1, n_classes, cls, D, D_new, nullptr, msgs_out, 0, canon, lmbds, ztime, xtime, 0.0, 0.0,
-                                    0, nullptr, nullptr, workspace, workspace_bytes, st);
+                                    0, nullptr, nullptr, workspace, workspace_bytes, st, g_kernel_mode.load() != 1);
   return launch_multiclass<double>(1, n_classes, cls, D, D_new, nullptr, msgs_out, 0, canon, lmbds, ztime, xtime, 0.0, 0.0,
-                                   0, nullptr, nullptr, workspace, workspace_bytes, st);
+                                   0, nullptr, nullptr, workspace, workspace_bytes, st, g_kernel_mode.load() != 1);
 }
 
 int bqa_b200_bp_run_classes(int prec, int n_classes, const bqa_b200_class* cls, int D, void* msgs0, void* msgs1, int parity,
@@ -212,9 +212,9 @@ int bqa_b200_bp_run_classes(int prec, int n_classes, const bqa_b200_class* cls, 
   cudaStream_t st = (cudaStream_t)stream;
   if (prec == BQA_C64)
     return launch_multiclass<float>(2, n_classes, cls, D, D, msgs0, msgs1, parity, nullptr, nullptr, 0.0, 0.0, damping,
-                                    bp_eps, max_iters, resid, status, workspace, workspace_bytes, st);
+                                    bp_eps, max_iters, resid, status, workspace, workspace_bytes, st, g_kernel_mode.load() != 1);
   return launch_multiclass<double>(2, n_classes, cls, D, D, msgs0, msgs1, parity, nullptr, nullptr, 0.0, 0.0, damping,
-                                   bp_eps, max_iters, resid, status, workspace, workspace_bytes, st);
+                                   bp_eps, max_iters, resid, status, workspace, workspace_bytes, st, g_kernel_mode.load() != 1);
 }
 
 int bqa_b200_gauge_msgs(int prec, int D_old, int D_new, long long L, const void* lmbds, void* msgs_out, void* stream) {

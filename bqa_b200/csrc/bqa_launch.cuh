@@ -56,7 +56,7 @@ template <typename R>
 int launch_multiclass(int kind, int n_classes, const bqa_b200_class* cls, int D, int Dn, void* msgs0, void* msgs1,
                       int parity, const void* canon, const void* lmbds, double ztime, double xtime, double damping,
                       double bp_eps, int max_iters, void* resid, int32_t* status, void* ws, size_t ws_bytes,
-                      cudaStream_t st);
+                      cudaStream_t st, bool allow_fast);
 
 // specialised kernels (bqa_fast_d3D4.cu): degree 3, D = 4, complex64
 bool fast_d3D4_available(int prec, int degree, int D, long long B);

@@ -10,7 +10,10 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include "../../include/bqa_b200.h"
+#include "bqa_fast_gram_d3D8.cuh"
 #include "bqa_generic.cuh"
 
 namespace bqa {
@@ -42,6 +45,7 @@ struct MultiArgs {
   cx<R>* ws;
   size_t ws_per_warp;
   int ws_in_smem;                  // the per-warp scratch fits into shared memory (small D): no global-memory round trips
+  int fast_gram_off;               // FAST kernels: byte offset of the gram8 scratch in the CTA's dynamic shared memory
   long long timeout_cycles;
 };
 
@@ -53,6 +57,25 @@ __device__ __forceinline__ cx<R>* warp_scratch(const MultiArgs<R>& a, long long 
                       : a.ws + (size_t)warp * a.ws_per_warp;
 }
 
+// Gram parts of one node: the shared-memory routine for degree 3 at D = 8 in complex64 (FAST kernels, launched only for
+// that bond dimension and precision), else the generic one
+template <typename R, bool FAST>
+__device__ __forceinline__ void mc_node_gram(const MultiArgs<R>& a, int d, int D, const cx<R>* T, const cx<R>* const* mp,
+                                             cx<R>* P, cx<R>* E, cx<R>* gram) {
+  if constexpr (FAST) {
+    if (d == 3) {
+      extern __shared__ __align__(16) unsigned char mc_smem[];
+      float2* sm = reinterpret_cast<float2*>(mc_smem + a.fast_gram_off) + (size_t)(threadIdx.x >> 5) * gram8::kWarpElems;
+      gram8::node_gram_d3D8(reinterpret_cast<const float2*>(T), reinterpret_cast<const float2*>(mp[0]),
+                            reinterpret_cast<const float2*>(mp[1]), reinterpret_cast<const float2*>(mp[2]),
+                            reinterpret_cast<float2*>(gram), sm);
+      return;
+    }
+  }
+  GroupWarp g;
+  node_gram<R>(g, d, D, T, mp, P, E, gram);
+}
+
 template <typename R>
 __device__ __forceinline__ int find_class(const MultiArgs<R>& a, long long item) {
   int k = 0;
@@ -61,7 +84,7 @@ __device__ __forceinline__ int find_class(const MultiArgs<R>& a, long long item)
 }
 
 // one BP sweep over every class: reads `cur`, writes `out`; folds the residual maxima of sweep `it` into a.resid
-template <typename R>
+template <typename R, bool FAST>
 __device__ __forceinline__ void mc_sweep(const MultiArgs<R>& a, const cx<R>* cur, cx<R>* out, int it, int write_undamped) {
   GroupWarp g;
   const int lane = threadIdx.x & 31;
@@ -78,7 +101,7 @@ __device__ __forceinline__ void mc_sweep(const MultiArgs<R>& a, const cx<R>* cur
     cx<R>* gram = E + W;
     const cx<R>* mp[BQA_MAX_DEGREE];
     for (int j = 0; j < d; ++j) mp[j] = cur + (size_t)c.in_pos[(size_t)j * c.B + node] * DD;
-    node_gram<R>(g, d, D, c.T + (size_t)node * W, mp, P, E, gram);
+    mc_node_gram<R, FAST>(a, d, D, c.T + (size_t)node * W, mp, P, E, gram);
     for (int k = 0; k < d; ++k) {
       const cx<R>* g0 = gram + (size_t)k * 2 * DD;
       const size_t slot = (size_t)c.out_pos[(size_t)k * c.B + node];
@@ -120,14 +143,14 @@ __device__ __forceinline__ bool mc_grid_barrier(unsigned* counter, unsigned& gen
 }
 
 // the whole BP run (reference _run_bp, state.py:97-124): status[0] = converged, status[1] = sweeps executed
-template <typename R>
+template <typename R, bool FAST>
 __global__ void __launch_bounds__(128) k_mc_bp_run(const __grid_constant__ MultiArgs<R> a) {
   unsigned* counter = reinterpret_cast<unsigned*>(a.status + 2);
   unsigned generation = 0;
   int sweeps = a.max_iters, converged = 0;
   for (int it = 0; it < a.max_iters; ++it) {
     const int cur = (a.parity + it) & 1;
-    mc_sweep<R>(a, a.msgs[cur], a.msgs[cur ^ 1], it, it == a.max_iters - 1);    // cap: the undamped sweep is kept (:122-123)
+    mc_sweep<R, FAST>(a, a.msgs[cur], a.msgs[cur ^ 1], it, it == a.max_iters - 1);    // cap: the undamped sweep is kept (:122-123)
     if (!mc_grid_barrier(counter, generation, a.status, a.timeout_cycles)) return;
     const R num = __ldcg(a.resid + 2 * it), den = __ldcg(a.resid + 2 * it + 1);
     if (msqrt(num / den) < a.bp_eps) { sweeps = it + 1; converged = 1; break; }
@@ -136,7 +159,7 @@ __global__ void __launch_bounds__(128) k_mc_bp_run(const __grid_constant__ Multi
 }
 
 // ZZ-extended messages of every class (_get_extended_msgs, state.py:127-139): msgs[0] -> ext in msgs[1]
-template <typename R>
+template <typename R, bool FAST>
 __global__ void __launch_bounds__(128) k_mc_ext(const __grid_constant__ MultiArgs<R> a) {
   GroupWarp g;
   const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -151,7 +174,7 @@ __global__ void __launch_bounds__(128) k_mc_ext(const __grid_constant__ MultiArg
     cx<R>* gram = E + W;
     const cx<R>* mp[BQA_MAX_DEGREE];
     for (int j = 0; j < d; ++j) mp[j] = a.msgs[0] + (size_t)c.in_pos[(size_t)j * c.B + node] * DD;
-    node_gram<R>(g, d, D, c.T + (size_t)node * W, mp, P, E, gram);
+    mc_node_gram<R, FAST>(a, d, D, c.T + (size_t)node * W, mp, P, E, gram);
     for (int k = 0; k < d; ++k) {
       const cx<R>* g0 = gram + (size_t)k * 2 * DD;
       const size_t slot = (size_t)c.out_pos[(size_t)k * c.B + node];
@@ -198,7 +221,7 @@ template <typename R>
 int launch_multiclass(int kind, int n_classes, const bqa_b200_class* cls, int D, int Dn, void* msgs0, void* msgs1,
                       int parity, const void* canon, const void* lmbds, double ztime, double xtime, double damping,
                       double bp_eps, int max_iters, void* resid, int32_t* status, void* ws, size_t ws_bytes,
-                      cudaStream_t st) {
+                      cudaStream_t st, bool allow_fast) {
   if (n_classes < 1 || n_classes > BQA_MAX_CLASSES) return set_error("%d degree classes outside [1, %d]", n_classes, BQA_MAX_CLASSES);
   MultiArgs<R> a{};
   a.n_classes = 0; a.D = D; a.Dn = Dn;
@@ -243,7 +266,23 @@ int launch_multiclass(int kind, int n_classes, const bqa_b200_class* cls, int D,
     a.ws_in_smem = smem_mode >= 0 ? (smem_mode != 0 && smem <= 100 * 1024) : (smem >= 72 * 1024 && smem <= 100 * 1024 && blocks <= fit);
   }
   if (!a.ws_in_smem) smem = 0;
-  const void* fn = kind == 0 ? (const void*)k_mc_ext<R> : (kind == 1 ? (const void*)k_mc_apply<R> : (const void*)k_mc_bp_run<R>);
+  // degree 3 at D = 8 in complex64: the node contraction out of shared memory (bqa_fast_gram_d3D8.cuh); P / E of the other
+  // classes and the Gram parts stay in the global workspace
+  bool fast = false;
+  if constexpr (std::is_same<R, float>::value) {
+    if (allow_fast && kind != 1 && D == 8)
+      for (int k = 0; k < a.n_classes; ++k) fast = fast || a.c[k].d == 3;
+  }
+  if (fast) {
+    a.ws_in_smem = 0;
+    a.fast_gram_off = 0;
+    smem = (size_t)4 * gram8::kWarpBytes;
+  }
+  const void* fn = nullptr;
+  if constexpr (std::is_same<R, float>::value) {
+    if (fast) fn = kind == 0 ? (const void*)k_mc_ext<R, true> : (const void*)k_mc_bp_run<R, true>;
+  }
+  if (!fn) fn = kind == 0 ? (const void*)k_mc_ext<R, false> : (kind == 1 ? (const void*)k_mc_apply<R> : (const void*)k_mc_bp_run<R, false>);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(multiclass): %s", cudaGetErrorString(e));
@@ -252,29 +291,26 @@ int launch_multiclass(int kind, int n_classes, const bqa_b200_class* cls, int D,
     int dev = 0, sms = 0, occ = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mc_bp_run<R>, 128, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 128, smem);
     if (occ < 1 || sms < 1) return set_error("bp_run_classes: the kernel cannot be made resident");
     if (blocks > (long long)occ * sms) blocks = (long long)occ * sms;
   }
   if (!a.ws_in_smem && ws_bytes < per_warp * sizeof(cx<R>) * (size_t)blocks * 4)
     return set_error("workspace too small: need %zu bytes, got %zu", per_warp * sizeof(cx<R>) * (size_t)blocks * 4, ws_bytes);
-  if (kind == 0) {
-    k_mc_ext<R><<<(int)blocks, 128, smem, st>>>(a);
-    return after_launch("ext_msgs_classes");
-  }
-  if (kind == 1) {
-    k_mc_apply<R><<<(int)blocks, 128, smem, st>>>(a);
-    return after_launch("apply_update_classes");
-  }
   void* params[] = {&a};
-  cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_mc_bp_run<R>, dim3((unsigned)blocks), dim3(128), params, smem, st);
-  if (e != cudaSuccess) return set_error("cudaLaunchCooperativeKernel(k_mc_bp_run): %s", cudaGetErrorString(e));
-  return after_launch("bp_run_classes");
+  if (kind == 2) {
+    cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)blocks), dim3(128), params, smem, st);
+    if (e != cudaSuccess) return set_error("cudaLaunchCooperativeKernel(k_mc_bp_run): %s", cudaGetErrorString(e));
+    return after_launch("bp_run_classes");
+  }
+  cudaError_t e = cudaLaunchKernel(fn, dim3((unsigned)blocks), dim3(128), params, smem, st);
+  if (e != cudaSuccess) return set_error("cudaLaunchKernel(multiclass): %s", cudaGetErrorString(e));
+  return after_launch(kind == 0 ? "ext_msgs_classes" : "apply_update_classes");
 }
 
 #define BQA_INSTANTIATE_MULTICLASS(R)                                                                                \
   template int launch_multiclass<R>(int, int, const bqa_b200_class*, int, int, void*, void*, int, const void*,        \
                                     const void*, double, double, double, double, int, void*, int32_t*, void*, size_t, \
-                                    cudaStream_t);
+                                    cudaStream_t, bool);
 
 }  // namespace bqa

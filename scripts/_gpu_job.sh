@@ -1,6 +1,8 @@
 mkdir -p gpurun_out
-N=$1
-for z in 1 0 1 0; do
-BQA_B200_EXT_AHEAD=$z timeout 600 torchrun --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 40 --warmup 5 --no-config5 > gpurun_out/r2z_ab_n${N}_ahead$z.json 2> gpurun_out/r2z_ab.err; python -c "
-import json; d=json.load(open('gpurun_out/r2z_ab_n${N}_ahead$z.json')); print('ahead $z', round(d['value'],1), round(d['e2e']['value'],1), d['parity_vs_1gpu']['max_abs'], {k:round(v,4) for k,v in d['kernel_ms_per_step'].items()})" || tail -5 gpurun_out/r2z_ab.err
-done
+timeout 600 python -m pytest tests/test_gpu_parity.py -q -x -k "fast_gram_d3D8" 2>&1 | tail -15
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -4
+timeout 900 python scripts/profile_generic_D.py --dmax 8 2>/dev/null | tee gpurun_out/r3a_generic_D8.json
+timeout 600 python scripts/run_small_configs.py > gpurun_out/r3a_small.jsonl 2>/dev/null; python -c "
+import json
+for l in open('gpurun_out/r3a_small.jsonl'):
+    d=json.loads(l); print({k:(round(v,6) if isinstance(v,float) else v) for k,v in d.items() if k.startswith('steps_per_s') or 'diff' in k or 'equal' in k})"

@@ -227,6 +227,73 @@ def test_fast_d3D4_kernels_match_generic_and_oracle(lib, B):
         assert np.abs(fast[2][out_pos[j]] - want_ext[j]).max() < 2e-6
 
 
+@pytest.mark.parametrize("B", [1, 5, 130, 1003])
+def test_fast_gram_d3D8_matches_generic_and_oracle(lib, B):
+    """Degree 3, D = 8, complex64: the shared-memory node contraction (bqa_fast_gram_d3D8.cuh, taken by the table-driven
+    kernels) against the generic contraction (kernel mode 1) and against the oracle's pass_msgs (reference
+    backends.py:381-408) -- BP messages of a whole run of 2 sweeps incl. residuals, and the ZZ-extended messages -- on a
+    table of two classes (degree 2 rides along on the generic path) with scattered message slots."""
+    import ctypes as C
+    import torch
+    from bqa_b200 import _lib
+    from oracle import bqa_oracle as O
+    D = 8
+    rng = np.random.default_rng(100 + B)
+    B2 = 3
+    nslots = 3 * B + 2 * B2 + 5
+    perm_in, perm_out = rng.permutation(nslots), rng.permutation(nslots)
+    in3, out3 = perm_in[: 3 * B].reshape(3, B).astype(np.int32), perm_out[: 3 * B].reshape(3, B).astype(np.int32)
+    in2 = perm_in[3 * B: 3 * B + 2 * B2].reshape(2, B2).astype(np.int32)
+    out2 = perm_out[3 * B: 3 * B + 2 * B2].reshape(2, B2).astype(np.int32)
+    t3, _, th3 = instances.random_node_batch(B, 3, D, seed=11 + B)
+    t2, _, th2 = instances.random_node_batch(B2, 2, D, seed=12 + B)
+    cur = instances.random_psd_msgs(rng, nslots, D).astype(np.complex64)
+    t3, t2 = t3.astype(np.complex64), t2.astype(np.complex64)
+    dev = torch.device("cuda:0")
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    T3, T2, Cm = up(t3.reshape(-1)), up(t2.reshape(-1)), up(cur.reshape(-1))
+    i3, o3, i2, o2 = up(in3), up(out3), up(in2), up(out2)
+    e3, e2 = up(np.stack(th3).astype(np.float32)), up(np.stack(th2).astype(np.float32))
+    rows = (_lib.ClassDesc * 2)()
+    for r, (deg, b, T, ip, op, ea) in zip(rows, ((2, B2, T2, i2, o2, e2), (3, B, T3, i3, o3, e3))):
+        r.degree, r.B, r.T_in, r.T_out = deg, b, T.data_ptr(), None
+        r.in_pos, r.out_pos, r.lmbd_pos, r.node_ampls, r.edge_ampls = ip.data_ptr(), op.data_ptr(), None, None, ea.data_ptr()
+    ws = torch.zeros(max(lib.workspace_bytes(_lib.C64, 3, D, D), lib.workspace_bytes(_lib.C64, 2, D, D)),
+                     dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    out = {}
+    for mode in (1, 0):
+        lib.set_kernel_mode(mode)
+        try:
+            m0, m1 = Cm.clone(), Cm.clone()
+            resid = torch.zeros(2 * 4, dtype=torch.float32, device=dev)
+            status = torch.zeros(4, dtype=torch.int32, device=dev)
+            lib.bp_run_classes(_lib.C64, 2, C.byref(rows), D, m0.data_ptr(), m1.data_ptr(), 0, 0.25, 1e-30, 2,
+                               resid.data_ptr(), status.data_ptr(), ws.data_ptr(), ws.numel(), st)
+            ext = torch.zeros(nslots * 4 * D * D, dtype=torch.complex64, device=dev)
+            lib.ext_msgs_classes(_lib.C64, 2, C.byref(rows), D, Cm.data_ptr(), ext.data_ptr(), 0.7, ws.data_ptr(), ws.numel(), st)
+            torch.cuda.synchronize()
+            out[mode] = (m1.cpu().numpy().reshape(-1, D, D), m0.cpu().numpy().reshape(-1, D, D),
+                         resid.cpu().numpy().astype(np.float64), ext.cpu().numpy().reshape(-1, 2 * D, 2 * D),
+                         status.cpu().numpy())
+        finally:
+            lib.set_kernel_mode(0)
+    gen, fast = out[1], out[0]
+    assert fast[4][1] == 2 and gen[4][1] == 2 and fast[4][0] == 0                  # two sweeps, cap reached
+    for k in (0, 1, 3):
+        assert np.abs(fast[k] - gen[k]).max() < 3e-6
+    assert np.allclose(fast[2][:4], gen[2][:4], rtol=1e-3)
+    # oracle (complex128) on the same complex64 inputs: first sweep (damped, into buffer 1) and extended messages
+    for t, ip, op, th in ((t3, in3, out3, th3), (t2, in2, out2, th2)):
+        msgs = [cur[ip[j]].astype(np.complex128) for j in range(ip.shape[0])]
+        want = O.pass_msgs(t.astype(np.complex128), msgs)
+        want_ext = O.pass_msgs(t.astype(np.complex128), msgs,
+                               [(0.7 * x.astype(np.float32).astype(np.float64)).astype(np.complex128) for x in th])
+        for j in range(ip.shape[0]):
+            assert np.abs(fast[0][op[j]] - (0.25 * cur[op[j]] + 0.75 * want[j])).max() < 3e-6
+            assert np.abs(fast[3][op[j]] - want_ext[j]).max() < 3e-6
+
+
 def _graded_ext_msgs(rng, L, n=8):
     """Hermitian PSD trace-1 matrices with the graded spectra extended messages have in the symmetric gauge.
     The spectrum stays clear of the pinv_eps = 1e-6 mask (kept values >= 3e-6, masked ones <= 1e-7): an

@@ -264,8 +264,8 @@ int bqa_b200_canonicalize_ordered(int prec, int D, long long L, const void* ext,
   }
   if (g_kernel_mode.load() == 2 && prec == BQA_C64 && D == 4)
     return launch_fast_canon8(L, ext, canon, lmbds, colmax, pinv_eps, n_cols, st);
-  if (prec == BQA_C64) return launch_canonicalize<float>(D, L, ext, canon, lmbds, colmax, pinv_eps, st);
-  return launch_canonicalize<double>(D, L, ext, canon, lmbds, colmax, pinv_eps, st);
+  if (prec == BQA_C64) return launch_canonicalize<float>(D, L, ext, canon, lmbds, colmax, pinv_eps, st, g_kernel_mode.load() != 1);
+  return launch_canonicalize<double>(D, L, ext, canon, lmbds, colmax, pinv_eps, st, g_kernel_mode.load() != 1);
 }
 
 int bqa_b200_apply_update(int prec, int degree, int D, int D_new, long long B, const void* T_in, void* T_out,

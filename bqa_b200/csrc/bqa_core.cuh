@@ -360,11 +360,20 @@ BQA_HDN void jacobi_svd(G g, int n, int ld, cx<R>* A, cx<R>* V, R* sigma, int* o
 template <typename R>
 BQA_HD size_t edge_scratch_elems(int n) { return (size_t)6 * n * (n + 1); }
 
-template <typename R, typename G>
+// which SVD edge_canonicalize runs: the serial cyclic Jacobi above (any group), or a policy of the caller's
+// (bqa_generic.cuh: round-robin ordering over the lanes of a warp for n = 16 / 32); `prm` = n / 2 x 4 reals of scratch
+struct SerialJacobi {
+  template <typename R, typename G>
+  static BQA_HDN void run(G g, int n, int ld, cx<R>* A, cx<R>* V, R* sigma, int* order, R* /*prm*/) {
+    jacobi_svd<R>(g, n, ld, A, V, sigma, order);
+  }
+};
+
+template <typename R, typename G, typename SVD = SerialJacobi>
 BQA_HDN void edge_canonicalize(G g, int n, const cx<R>* ext_f, const cx<R>* ext_b, R pinv_eps,
                                cx<R>* scratch, R* rscratch, int* iscratch,
                                cx<R>* canon_at_e /* backward */, cx<R>* canon_at_eL /* forward */,
-                               R* lmbd_out /* n */) {
+                               R* lmbd_out /* n */, R* prm = nullptr) {
   const int nn = n * n, ld = n + 1, sz = n * ld;              // scratch matrices: row stride ld (see jacobi_svd)
   cx<R>* Af = scratch;           cx<R>* Vf = scratch + sz;
   cx<R>* Ab = scratch + 2 * sz;  cx<R>* Vb = scratch + 3 * sz;
@@ -377,8 +386,8 @@ BQA_HDN void edge_canonicalize(G g, int n, const cx<R>* ext_f, const cx<R>* ext_
     Ab[at] = ext_b[i];
   }
   g.sync();
-  jacobi_svd<R>(g, n, ld, Af, Vf, sf, of);
-  jacobi_svd<R>(g, n, ld, Ab, Vb, sb, ob);
+  SVD::template run<R>(g, n, ld, Af, Vf, sf, of, prm);
+  SVD::template run<R>(g, n, ld, Ab, Vb, sb, ob, prm);
   // ker[i][j] = sum_k lu_f[i][k] lu_b[j][k],  lu[i][k] = sqrt(s_i) conj(V[k][col_i])  (masked s_i > pinv_eps)
   for (int o = g.rank(); o < nn; o += g.size()) {
     const int i = o / n, j = o - i * n;
@@ -406,7 +415,7 @@ BQA_HDN void edge_canonicalize(G g, int n, const cx<R>* ext_f, const cx<R>* ext_
     }
   }
   g.sync();
-  jacobi_svd<R>(g, n, ld, K, Vk, sk, ok);
+  SVD::template run<R>(g, n, ld, K, Vk, sk, ok, prm);
   // lambda = masked singular values, L2 normalised (reference state.py:200)
   R nrm2 = 0;
   for (int j = 0; j < n; ++j) { const R s = sk[ok[j]]; if (s > pinv_eps) nrm2 += s * s; }

@@ -110,24 +110,172 @@ __global__ void __launch_bounds__(128) k_node_msgs(NodeArgs<R> a) {
 }
 
 // ---- canonicalizers ------------------------------------------------------------------------------
+// One-sided Jacobi SVD of an N x N complex matrix (N = 16, 32) by one warp with ROUND-ROBIN ordering: a sweep is N - 1
+// rounds of N / 2 disjoint column pairs, and all pairs of a round are handled together --
+//   1. every lane forms the four partial sums (|a_p|^2, |a_q|^2, <a_p, a_q>) of each pair from its row,
+//   2. one butterfly reduce-scatter over the lanes leaves the four totals of pair i on the lanes with
+//      (lane mod N/2) == i  (36 shuffles for N = 16, 64 for N = 32, against 20 per pair one after the other),
+//   3. those lanes derive the rotation of their pair concurrently and publish it through shared memory,
+//   4. every lane applies the N / 2 rotations to its row of A and of V (N = 16: lanes 16..31 take the rows of V).
+// Same rotation formulas, thresholds and stopping rule as the serial cyclic routine jacobi_svd (bqa_core.cuh), which
+// handles one pair at a time with a warp-wide reduction and a dependent parameter chain each (r2 capture of the n = 16
+// kernel: issue slots 34 % used, the warp waits on its own shuffle / square-root latencies).  The order of the rotations
+// differs, so results agree with the serial routine to rounding, not bit for bit.
+// one step of the butterfly reduce-scatter: the lanes whose bit MASK is set keep the upper half of the CNT values
+template <typename R, int NV, int CNT, int MASK>
+__device__ __forceinline__ void reduce_scatter_step(R (&v)[NV], int lane) {
+  if constexpr (MASK >= 1) {
+    const bool up = (lane & MASK) != 0;
+#pragma unroll
+    for (int j = 0; j < CNT / 2; ++j) {
+      const R send = up ? v[j] : v[j + CNT / 2];
+      const R keep = up ? v[j + CNT / 2] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, MASK);
+    }
+    reduce_scatter_step<R, NV, CNT / 2, MASK / 2>(v, lane);
+  }
+}
+
+template <typename R, int N>
+__device__ void jacobi_svd_round_robin(int ld, cx<R>* A, cx<R>* V, R* sigma, int* order, R* prm) {
+  constexpr int H = N / 2, M1 = N - 1, NV = 4 * H;
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  for (int i = lane; i < N * N; i += 32) V[(i / N) * ld + i % N] = mk<R>((i / N == i % N) ? R(1) : R(0), R(0));
+  const R tol = num_traits<R>::eps() * R(2) * msqrt((R)N);
+  R fro2 = 0;
+  if (lane < N)
+    for (int j = 0; j < N; ++j) fro2 += norm2(A[lane * ld + j]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) fro2 += __shfl_xor_sync(full, fro2, o);
+  const R nul = num_traits<R>::eps() * num_traits<R>::eps() * fro2;
+  __syncwarp();
+  // pair i of round t (circle method: column N - 1 stays, the others rotate)
+  auto pair_of = [&](int t, int i, int& p, int& q) {
+    int a = t + i, b = t + M1 - i;
+    if (a >= M1) a -= M1;
+    if (b >= M1) b -= M1;
+    if (i == 0) a = M1;
+    p = a < b ? a : b;
+    q = a < b ? b : a;
+  };
+  for (int sweep = 0; sweep < 40; ++sweep) {
+    bool rotated = false;
+    for (int t = 0; t < M1; ++t) {
+      R v[NV];
+#pragma unroll
+      for (int i = 0; i < H; ++i) {
+        int p, q;
+        pair_of(t, i, p, q);
+        cx<R> ap = mk<R>(0, 0), aq = ap;
+        if (lane < N) { ap = A[lane * ld + p]; aq = A[lane * ld + q]; }
+        v[4 * i] = norm2(ap);
+        v[4 * i + 1] = norm2(aq);
+        v[4 * i + 2] = ap.re * aq.re + ap.im * aq.im;        // conj(ap) * aq
+        v[4 * i + 3] = ap.re * aq.im - ap.im * aq.re;
+      }
+      // reduce-scatter over the pair index (lane bits log2(H) - 1 .. 0), all-reduce over the remaining lane bits
+      reduce_scatter_step<R, NV, NV, H / 2>(v, lane);
+#pragma unroll
+      for (int mask = H; mask < 32; mask *= 2) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] += __shfl_xor_sync(full, v[j], mask);
+      }
+      const R al = v[0], be = v[1], gr = v[2], gi = v[3];
+      const R g2 = gr * gr + gi * gi;
+      const bool rot = !(al <= nul || be <= nul || g2 <= tol * tol * al * be);
+      R c = R(1), sn = R(0), phr = R(1), phi = R(0);
+      if (rot) {
+        const R ag = msqrt(g2);
+        const R zeta = (be - al) / (R(2) * ag);
+        const R tt = ((zeta >= R(0)) ? R(1) : R(-1)) / (mabs(zeta) + msqrt(R(1) + zeta * zeta));
+        c = R(1) / msqrt(R(1) + tt * tt);
+        sn = c * tt;
+        phr = gr / ag;                                   // e^{-i arg(gamma)}
+        phi = -gi / ag;
+      }
+      if (lane < H) { prm[4 * lane] = c; prm[4 * lane + 1] = sn; prm[4 * lane + 2] = phr; prm[4 * lane + 3] = phi; }
+      rotated = rotated || __any_sync(full, rot);
+      __syncwarp();
+      // rows: N = 16: lanes 0..15 own the rows of A, lanes 16..31 the rows of V; N = 32: every lane one row of each
+#pragma unroll
+      for (int pass = 0; pass < (N == 32 ? 2 : 1); ++pass) {
+        cx<R>* row = (N == 32 ? (pass == 0 ? A : V) : (lane < 16 ? A : V)) + (lane & (N - 1)) * ld;
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+          int p, q;
+          pair_of(t, i, p, q);
+          const R ci = prm[4 * i], si = prm[4 * i + 1];
+          const cx<R> ph = mk<R>(prm[4 * i + 2], prm[4 * i + 3]);
+          if (si != R(0)) {                              // identity: the pair was skipped
+            const cx<R> ap = row[p], aq = ph * row[q];
+            row[p] = ci * ap - si * aq;
+            row[q] = si * ap + ci * aq;
+          }
+        }
+      }
+      __syncwarp();
+    }
+    if (!rotated) break;
+  }
+  for (int j = 0; j < N; ++j) {                          // singular values = column norms (as in jacobi_svd)
+    R a = 0;
+    if (lane < N) a = norm2(A[lane * ld + j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(full, a, o);
+    if (lane == 0) sigma[j] = msqrt(a);
+  }
+  __syncwarp();
+  if (lane == 0) {
+    for (int j = 0; j < N; ++j) order[j] = j;
+    for (int i = 1; i < N; ++i) {                        // stable insertion sort, descending
+      const int oi = order[i];
+      int j = i - 1;
+      while (j >= 0 && sigma[order[j]] < sigma[oi]) { order[j + 1] = order[j]; --j; }
+      order[j + 1] = oi;
+    }
+  }
+  __syncwarp();
+}
+
+struct RoundRobinJacobi {
+  template <typename R, typename G>
+  static __device__ void run(G g, int n, int ld, cx<R>* A, cx<R>* V, R* sigma, int* order, R* prm) {
+    if (n == 16) jacobi_svd_round_robin<R, 16>(ld, A, V, sigma, order, prm);
+    else if (n == 32) jacobi_svd_round_robin<R, 32>(ld, A, V, sigma, order, prm);
+    else jacobi_svd<R>(g, n, ld, A, V, sigma, order);
+  }
+};
+
 template <typename R>
+__host__ __device__ inline size_t canon_warp_bytes(int n) {        // matrices | 3 n reals | 3 n ints | 2 n reals (rotations)
+  const size_t b = edge_scratch_elems<R>(n) * sizeof(cx<R>) + 3 * n * sizeof(R) + 3 * n * sizeof(int) + 2 * n * sizeof(R);
+  return (b + 15) / 16 * 16;
+}
+
+template <typename R, bool PAR>
 __global__ void __launch_bounds__(256) k_canonicalize(int D, long long L, const cx<R>* ext, cx<R>* canon,
                                                       R* lmbds, R* colmax, R pinv_eps) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GroupWarp g;
   const int n = 2 * D, nn = n * n;
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const size_t per_warp = edge_scratch_elems<R>(n) * sizeof(cx<R>) + 3 * n * sizeof(R) + 3 * n * sizeof(int);
-  unsigned char* base = smem_raw + (size_t)wib * ((per_warp + 15) / 16 * 16);
+  unsigned char* base = smem_raw + (size_t)wib * canon_warp_bytes<R>(n);
   cx<R>* scratch = reinterpret_cast<cx<R>*>(base);
   R* rs = reinterpret_cast<R*>(scratch + edge_scratch_elems<R>(n));
   int* is = reinterpret_cast<int*>(rs + 3 * n);
+  R* prm = reinterpret_cast<R*>(is + 3 * n);
   const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   R cm = 0;
   for (long long e = warp; e < L; e += nwarps) {
-    edge_canonicalize<R>(g, n, ext + (size_t)e * nn, ext + (size_t)(e + L) * nn, pinv_eps, scratch, rs, is,
-                         canon + (size_t)e * nn, canon + (size_t)(e + L) * nn, lmbds + (size_t)e * n);
+    if constexpr (PAR)
+      edge_canonicalize<R, GroupWarp, RoundRobinJacobi>(g, n, ext + (size_t)e * nn, ext + (size_t)(e + L) * nn, pinv_eps,
+                                                        scratch, rs, is, canon + (size_t)e * nn,
+                                                        canon + (size_t)(e + L) * nn, lmbds + (size_t)e * n, prm);
+    else
+      edge_canonicalize<R>(g, n, ext + (size_t)e * nn, ext + (size_t)(e + L) * nn, pinv_eps, scratch, rs, is,
+                           canon + (size_t)e * nn, canon + (size_t)(e + L) * nn, lmbds + (size_t)e * n);
     g.sync();
     if (lane < n) cm = max(cm, lmbds[(size_t)e * n + lane]);
   }
@@ -295,24 +443,32 @@ int launch_node_msgs(bool ext, int d, int D, long long B, const void* T, const v
 
 template <typename R>
 int launch_canonicalize(int D, long long L, const void* ext, void* canon, void* lmbds, void* colmax,
-                        double pinv_eps, cudaStream_t st) {
+                        double pinv_eps, cudaStream_t st, bool round_robin) {
   if (L == 0) return 0;
   const int n = 2 * D;
-  size_t per_warp = edge_scratch_elems<R>(n) * sizeof(cx<R>) + 3 * n * sizeof(R) + 3 * n * sizeof(int);
-  per_warp = (per_warp + 15) / 16 * 16;
+  const size_t per_warp = canon_warp_bytes<R>(n);
   int wpb = (int)((size_t)200 * 1024 / per_warp);
   if (wpb > 8) wpb = 8;
   if (wpb < 1) return set_error("canonicalize: bond dimension %d needs %zu bytes of shared memory per edge", D, per_warp);
   const size_t smem = per_warp * wpb;
+  // n = 16, 32: all column pairs of a round together (jacobi_svd_round_robin); smaller n: the serial routine
+  const bool par = round_robin && (n == 16 || n == 32);
+  const void* fn = par ? (const void*)k_canonicalize<R, true> : (const void*)k_canonicalize<R, false>;
   if (smem > 48 * 1024) {                      // per device and per size: set on every call (microseconds per step)
-    cudaError_t e = cudaFuncSetAttribute(k_canonicalize<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(canonicalize): %s", cudaGetErrorString(e));
   }
   long long blocks = (L + wpb - 1) / wpb;
   const long long cap = (long long)148 * 8;
   if (blocks > cap) blocks = cap;
-  k_canonicalize<R><<<(int)blocks, wpb * 32, smem, st>>>(D, L, (const cx<R>*)ext, (cx<R>*)canon, (R*)lmbds,
-                                                         (R*)colmax, (R)pinv_eps);
+  const cx<R>* e_ = (const cx<R>*)ext;
+  cx<R>* c_ = (cx<R>*)canon;
+  R* l_ = (R*)lmbds;
+  R* m_ = (R*)colmax;
+  R eps = (R)pinv_eps;
+  void* params[] = {&D, &L, &e_, &c_, &l_, &m_, &eps};
+  cudaError_t e = cudaLaunchKernel(fn, dim3((unsigned)blocks), dim3(wpb * 32), params, smem, st);
+  if (e != cudaSuccess) return set_error("cudaLaunchKernel(canonicalize): %s", cudaGetErrorString(e));
   return after_launch("canonicalize(generic)");
 }
 
@@ -377,7 +533,7 @@ int launch_threshold(int d, int D, long long B, void* T, const int32_t* node_ids
   template int launch_node_msgs<R>(bool, int, int, long long, const void*, const void*, void*, const int32_t*,     \
                                    const int32_t*, const void*, double, double, int, double, int, void*, int32_t*, \
                                    void*, size_t, const int32_t*, void* const*, cudaStream_t);                                                   \
-  template int launch_canonicalize<R>(int, long long, const void*, void*, void*, void*, double, cudaStream_t);     \
+  template int launch_canonicalize<R>(int, long long, const void*, void*, void*, void*, double, cudaStream_t, bool); \
   template int launch_apply_update<R>(int, int, int, long long, const void*, void*, const void*, const void*,      \
                                       void*, const int32_t*, const int32_t*, const int32_t*, const void*,          \
                                       const void*, double, double, void*, size_t, cudaStream_t);                   \

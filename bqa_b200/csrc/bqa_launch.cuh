@@ -33,7 +33,7 @@ int launch_node_msgs(bool ext, int d, int D, long long B, const void* T, const v
                      void* ws, size_t ws_bytes, const int32_t* remote_pos, void* const* peers, cudaStream_t st);
 template <typename R>
 int launch_canonicalize(int D, long long L, const void* ext, void* canon, void* lmbds, void* colmax,
-                        double pinv_eps, cudaStream_t st);
+                        double pinv_eps, cudaStream_t st, bool round_robin);
 template <typename R>
 int launch_apply_update(int d, int D, int Dn, long long B, const void* T_in, void* T_out, const void* canon,
                         const void* lmbds, void* msgs_out, const int32_t* in_pos, const int32_t* out_pos,

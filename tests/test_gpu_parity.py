@@ -356,6 +356,59 @@ def test_fast_canon8_matches_oracle(lib, L):
         assert np.abs(np.abs(G) - s_ref[:, :, None] * np.eye(4)).max() < (6e-5 if mode == 0 else 2e-5), mode
 
 
+@pytest.mark.parametrize("precision", ["single", "double"])
+@pytest.mark.parametrize("D,L", [(8, 1), (8, 37), (16, 9)])
+def test_generic_canonicalizer_round_robin_matches_serial_and_oracle(lib, D, L, precision):
+    """n = 16 / 32 canonicalizer: the round-robin Jacobi over the lanes of a warp (mode 0, jacobi_svd_round_robin) and the
+    serial cyclic routine (mode 1) against the oracle's _get_canonicalizers restatement (reference state.py:171-200) in
+    complex128 -- lambdas, column maxima and the defining property of the canonicalizers (see
+    test_fast_canon8_matches_oracle) on the D kept columns."""
+    import torch
+    from bqa_b200 import _lib
+    from oracle import bqa_oracle as O
+    n = 2 * D
+    rng = np.random.default_rng(1000 * D + L)
+    kept = np.array([0.5, 0.25, 0.12, 0.06, 0.03, 0.015, 7e-3, 3e-3, 1e-3, 3e-4, 1.2e-4, 5e-5, 2e-5, 9e-6][: min(n - 2, 14)])
+    spec = np.concatenate([kept, np.full(n - kept.size, 2e-9)])
+
+    def psd():
+        q = np.linalg.qr(rng.normal(size=(L, n, n)) + 1j * rng.normal(size=(L, n, n)))[0]
+        q = np.linalg.qr(np.eye(n) + 0.05 * q)[0]
+        sp = spec * np.exp(rng.normal(scale=0.2, size=(L, n)))
+        m = (q * (sp / sp.sum(1, keepdims=True))[:, None, :]) @ np.swapaxes(q.conj(), 1, 2)
+        return 0.5 * (m + np.swapaxes(m.conj(), 1, 2))
+    cdt, rdt, prec = (np.complex64, np.float32, _lib.C64) if precision == "single" else (np.complex128, np.float64, _lib.C128)
+    ext = np.concatenate([psd(), psd()], 0).astype(cdt)
+    ext128 = ext.astype(np.complex128)
+    lm_ref, _ = O.canonicalizers(ext128, 1e-6, np.complex128)
+    lm_ref = lm_ref.real
+    u, lam, uh = O.masked_svd(ext128, 1e-6, np.complex128)
+    lu = np.sqrt(lam)[..., :, None] * uh
+    ker = lu[:L] @ np.swapaxes(lu[L:], 1, 2)
+    s_ref = np.linalg.svd(ker, compute_uv=False)[:, :D]
+    dev = torch.device("cuda:0")
+    e = torch.from_numpy(ext.reshape(-1)).to(dev)
+    st = torch.cuda.current_stream().cuda_stream
+    # complex64 at n = 32 with a spectrum five decades deep: the columns of the smallest kept singular values carry 1e-4
+    tol_l, tol_g = (5e-6, 6e-5 if D == 8 else 3e-4) if precision == "single" else (1e-12, 1e-10)
+    for mode in (1, 0):
+        lib.set_kernel_mode(mode)
+        try:
+            canon = torch.zeros_like(e)
+            lm = torch.zeros(L * n, dtype=torch.from_numpy(np.zeros(1, rdt)).dtype, device=dev)
+            colmax = torch.zeros(n, dtype=lm.dtype, device=dev)
+            lib.canonicalize(prec, D, L, e.data_ptr(), canon.data_ptr(), lm.data_ptr(), colmax.data_ptr(), 1e-6, D, st)
+        finally:
+            lib.set_kernel_mode(0)
+        lmh = lm.cpu().numpy().reshape(L, n).astype(np.float64)
+        c = canon.cpu().numpy().reshape(2 * L, n, n).astype(np.complex128)
+        af, ab = lu[:L] @ c[L:, :, :D], lu[L:] @ c[:L, :, :D]
+        G = np.swapaxes(af.conj(), 1, 2) @ ker @ ab.conj()
+        assert np.abs(colmax.cpu().numpy() - lmh.max(0)).max() == 0.0
+        assert np.abs(lmh[:, :D] - lm_ref[:, :D]).max() < tol_l, mode
+        assert np.abs(np.abs(G) - s_ref[:, :, None] * np.eye(D)).max() < tol_g, mode
+
+
 def test_partitioned_nccl(lib):
     """Node-partitioned engine over NCCL on 2 GPUs == single-GPU engine (skipped on a 1-GPU box; the gloo
     world_size-2/3 tests in tests/test_partitioned.py cover the same logic on CPU)."""

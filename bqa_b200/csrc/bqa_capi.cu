@@ -17,6 +17,14 @@ static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
 // 0: specialised kernels where they exist, 1: generic kernels only, 2: like 0 but the first-design n = 8 canonicalizer
 static std::atomic<int> g_kernel_mode{0};
+// side-by-side switches for the two D >= 8 pieces (read once): BQA_B200_FAST_GRAM=0 keeps the generic node contraction at
+// D = 8, BQA_B200_ROUND_ROBIN=0 the serial Jacobi in the n = 16 / 32 canonicalizer
+static bool env_on(const char* name) {
+  const char* e = getenv(name);
+  return !(e && e[0] == '0');
+}
+static bool fast_gram_on() { static const bool on = env_on("BQA_B200_FAST_GRAM"); return on && g_kernel_mode.load() != 1; }
+static bool round_robin_on() { static const bool on = env_on("BQA_B200_ROUND_ROBIN"); return on && g_kernel_mode.load() != 1; }
 
 int set_error(const char* fmt, ...) {
   va_list ap;
@@ -184,9 +192,9 @@ int bqa_b200_ext_msgs_classes(int prec, int n_classes, const bqa_b200_class* cls
   cudaStream_t st = (cudaStream_t)stream;
   if (prec == BQA_C64)
     return launch_multiclass<float>(0, n_classes, cls, D, D, (void*)msgs_cur, ext, 0, nullptr, nullptr, ztime, 0.0, 0.0, 0.0,
-                                    0, nullptr, nullptr, workspace, workspace_bytes, st, g_kernel_mode.load() != 1);
+                                    0, nullptr, nullptr, workspace, workspace_bytes, st, fast_gram_on());
   return launch_multiclass<double>(0, n_classes, cls, D, D, (void*)msgs_cur, ext, 0, nullptr, nullptr, ztime, 0.0, 0.0, 0.0,
-                                   0, nullptr, nullptr, workspace, workspace_bytes, st, g_kernel_mode.load() != 1);
+                                   0, nullptr, nullptr, workspace, workspace_bytes, st, fast_gram_on());
 }
 
 int bqa_b200_apply_update_classes(int prec, int n_classes, const bqa_b200_class* cls, int D, int D_new, const void* canon,
@@ -198,9 +206,9 @@ int bqa_b200_apply_update_classes(int prec, int n_classes, const bqa_b200_class*
   cudaStream_t st = (cudaStream_t)stream;
   if (prec == BQA_C64)
     return launch_multiclass<float>(1, n_classes, cls, D, D_new, nullptr, msgs_out, 0, canon, lmbds, ztime, xtime, 0.0, 0.0,
-                                    0, nullptr, nullptr, workspace, workspace_bytes, st, g_kernel_mode.load() != 1);
+                                    0, nullptr, nullptr, workspace, workspace_bytes, st, fast_gram_on());
   return launch_multiclass<double>(1, n_classes, cls, D, D_new, nullptr, msgs_out, 0, canon, lmbds, ztime, xtime, 0.0, 0.0,
-                                   0, nullptr, nullptr, workspace, workspace_bytes, st, g_kernel_mode.load() != 1);
+                                   0, nullptr, nullptr, workspace, workspace_bytes, st, fast_gram_on());
 }
 
 int bqa_b200_bp_run_classes(int prec, int n_classes, const bqa_b200_class* cls, int D, void* msgs0, void* msgs1, int parity,
@@ -212,9 +220,9 @@ int bqa_b200_bp_run_classes(int prec, int n_classes, const bqa_b200_class* cls, 
   cudaStream_t st = (cudaStream_t)stream;
   if (prec == BQA_C64)
     return launch_multiclass<float>(2, n_classes, cls, D, D, msgs0, msgs1, parity, nullptr, nullptr, 0.0, 0.0, damping,
-                                    bp_eps, max_iters, resid, status, workspace, workspace_bytes, st, g_kernel_mode.load() != 1);
+                                    bp_eps, max_iters, resid, status, workspace, workspace_bytes, st, fast_gram_on());
   return launch_multiclass<double>(2, n_classes, cls, D, D, msgs0, msgs1, parity, nullptr, nullptr, 0.0, 0.0, damping,
-                                   bp_eps, max_iters, resid, status, workspace, workspace_bytes, st, g_kernel_mode.load() != 1);
+                                   bp_eps, max_iters, resid, status, workspace, workspace_bytes, st, fast_gram_on());
 }
 
 int bqa_b200_gauge_msgs(int prec, int D_old, int D_new, long long L, const void* lmbds, void* msgs_out, void* stream) {
@@ -241,7 +249,7 @@ int bqa_b200_canonicalize_p2p(int prec, int D, long long L, const void* ext, voi
                               void* const* peer_canon, void* const* peer_lmbds, const long long* peer_L, void* stream) {
   if (int rc = check_shape(prec, 0, D)) return rc;
   if (n_cols < 1 || n_cols > 2 * D) return set_error("n_cols %d outside [1, %d]", n_cols, 2 * D);
-  if (g_kernel_mode.load() == 0 && prec == BQA_C64 && D == 4 && owned && remote)
+  if (g_kernel_mode.load() == 0 && prec == BQA_C64 && D == 4 && n_cols <= D && owned && remote)
     return launch_fast_canon8v2(L, ext, canon, lmbds, colmax, pinv_eps, n_cols, owned, nullptr, (cudaStream_t)stream, n_owned,
                                 remote, peer_canon, peer_lmbds, peer_L);
   // no single-owner path for this shape: every rank decomposes all of its local edges (identical results)
@@ -257,15 +265,20 @@ int bqa_b200_canonicalize_ordered(int prec, int D, long long L, const void* ext,
   if (int rc = check_shape(prec, 0, D)) return rc;
   if (n_cols < 1 || n_cols > 2 * D) return set_error("n_cols %d outside [1, %d]", n_cols, 2 * D);
   cudaStream_t st = (cudaStream_t)stream;
-  if (g_kernel_mode.load() == 0 && prec == BQA_C64 && D == 4) {
+  // The Cholesky-factor kernels (v2 / v3) resolve the small end of a spectrum to about 3e-5 of its top: good
+  // for the truncation to D columns, not for the decision how far the bond dimension may GROW -- on the MaxCut config
+  // (degenerate spectra, pinv_eps 1e-5, max_bond_dim 16) they let D leave 4 six steps early and the anneal took a harder
+  // trajectory (4 x the BP sweeps).  They are therefore used only where the bond dimension is capped at D (n_cols <= D);
+  // while it may still grow, the first-design kernel (rotations accumulated, 1e-6) decides.
+  if (g_kernel_mode.load() == 0 && prec == BQA_C64 && D == 4 && n_cols <= D) {
     if (canon_variant() == 2 || order || cost)                 // the edge-order experiment lives in the v2 layout
       return launch_fast_canon8v2(L, ext, canon, lmbds, colmax, pinv_eps, n_cols, order, cost, st);
     return launch_fast_canon8v3(L, ext, canon, lmbds, colmax, pinv_eps, n_cols, st);
   }
-  if (g_kernel_mode.load() == 2 && prec == BQA_C64 && D == 4)
+  if (g_kernel_mode.load() != 1 && prec == BQA_C64 && D == 4)
     return launch_fast_canon8(L, ext, canon, lmbds, colmax, pinv_eps, n_cols, st);
-  if (prec == BQA_C64) return launch_canonicalize<float>(D, L, ext, canon, lmbds, colmax, pinv_eps, st, g_kernel_mode.load() != 1);
-  return launch_canonicalize<double>(D, L, ext, canon, lmbds, colmax, pinv_eps, st, g_kernel_mode.load() != 1);
+  if (prec == BQA_C64) return launch_canonicalize<float>(D, L, ext, canon, lmbds, colmax, pinv_eps, st, round_robin_on());
+  return launch_canonicalize<double>(D, L, ext, canon, lmbds, colmax, pinv_eps, st, round_robin_on());
 }
 
 int bqa_b200_apply_update(int prec, int degree, int D, int D_new, long long B, const void* T_in, void* T_out,

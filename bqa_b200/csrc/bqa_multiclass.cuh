@@ -57,12 +57,14 @@ __device__ __forceinline__ cx<R>* warp_scratch(const MultiArgs<R>& a, long long 
                       : a.ws + (size_t)warp * a.ws_per_warp;
 }
 
-// Gram parts of one node: the shared-memory routine for degree 3 at D = 8 in complex64 (FAST kernels, launched only for
-// that bond dimension and precision), else the generic one
-template <typename R, bool FAST>
+// Gram parts of one node.  MODE 2 (launched only for D = 8 in complex64): the shared-memory routine for degree 3, the
+// generic one for the other classes; MODE 1 (D = 2, 4, 8): the generic routine with the bond dimension as a compile-time
+// constant; MODE 0 (any other D): the runtime-D routine alone, so that e.g. D = 16 keeps the 72 registers per thread and the
+// occupancy it had before the unrolled variants existed (measured: BP run at D = 16 544 ms against 625 ms)
+template <typename R, int MODE>
 __device__ __forceinline__ void mc_node_gram(const MultiArgs<R>& a, int d, int D, const cx<R>* T, const cx<R>* const* mp,
                                              cx<R>* P, cx<R>* E, cx<R>* gram) {
-  if constexpr (FAST) {
+  if constexpr (MODE == 2) {
     if (d == 3) {
       extern __shared__ __align__(16) unsigned char mc_smem[];
       float2* sm = reinterpret_cast<float2*>(mc_smem + a.fast_gram_off) + (size_t)(threadIdx.x >> 5) * gram8::kWarpElems;
@@ -73,7 +75,8 @@ __device__ __forceinline__ void mc_node_gram(const MultiArgs<R>& a, int d, int D
     }
   }
   GroupWarp g;
-  node_gram<R>(g, d, D, T, mp, P, E, gram);
+  if constexpr (MODE == 0) node_gram_impl<R, GroupWarp, 0>(g, d, D, T, mp, P, E, gram);     // any D: fewest registers
+  else node_gram<R>(g, d, D, T, mp, P, E, gram);                                           // D = 2, 4, 8 unrolled
 }
 
 template <typename R>
@@ -84,7 +87,7 @@ __device__ __forceinline__ int find_class(const MultiArgs<R>& a, long long item)
 }
 
 // one BP sweep over every class: reads `cur`, writes `out`; folds the residual maxima of sweep `it` into a.resid
-template <typename R, bool FAST>
+template <typename R, int MODE>
 __device__ __forceinline__ void mc_sweep(const MultiArgs<R>& a, const cx<R>* cur, cx<R>* out, int it, int write_undamped) {
   GroupWarp g;
   const int lane = threadIdx.x & 31;
@@ -101,7 +104,7 @@ __device__ __forceinline__ void mc_sweep(const MultiArgs<R>& a, const cx<R>* cur
     cx<R>* gram = E + W;
     const cx<R>* mp[BQA_MAX_DEGREE];
     for (int j = 0; j < d; ++j) mp[j] = cur + (size_t)c.in_pos[(size_t)j * c.B + node] * DD;
-    mc_node_gram<R, FAST>(a, d, D, c.T + (size_t)node * W, mp, P, E, gram);
+    mc_node_gram<R, MODE>(a, d, D, c.T + (size_t)node * W, mp, P, E, gram);
     for (int k = 0; k < d; ++k) {
       const cx<R>* g0 = gram + (size_t)k * 2 * DD;
       const size_t slot = (size_t)c.out_pos[(size_t)k * c.B + node];
@@ -143,14 +146,14 @@ __device__ __forceinline__ bool mc_grid_barrier(unsigned* counter, unsigned& gen
 }
 
 // the whole BP run (reference _run_bp, state.py:97-124): status[0] = converged, status[1] = sweeps executed
-template <typename R, bool FAST>
+template <typename R, int MODE>
 __global__ void __launch_bounds__(128) k_mc_bp_run(const __grid_constant__ MultiArgs<R> a) {
   unsigned* counter = reinterpret_cast<unsigned*>(a.status + 2);
   unsigned generation = 0;
   int sweeps = a.max_iters, converged = 0;
   for (int it = 0; it < a.max_iters; ++it) {
     const int cur = (a.parity + it) & 1;
-    mc_sweep<R, FAST>(a, a.msgs[cur], a.msgs[cur ^ 1], it, it == a.max_iters - 1);    // cap: the undamped sweep is kept (:122-123)
+    mc_sweep<R, MODE>(a, a.msgs[cur], a.msgs[cur ^ 1], it, it == a.max_iters - 1);    // cap: the undamped sweep is kept (:122-123)
     if (!mc_grid_barrier(counter, generation, a.status, a.timeout_cycles)) return;
     const R num = __ldcg(a.resid + 2 * it), den = __ldcg(a.resid + 2 * it + 1);
     if (msqrt(num / den) < a.bp_eps) { sweeps = it + 1; converged = 1; break; }
@@ -159,7 +162,7 @@ __global__ void __launch_bounds__(128) k_mc_bp_run(const __grid_constant__ Multi
 }
 
 // ZZ-extended messages of every class (_get_extended_msgs, state.py:127-139): msgs[0] -> ext in msgs[1]
-template <typename R, bool FAST>
+template <typename R, int MODE>
 __global__ void __launch_bounds__(128) k_mc_ext(const __grid_constant__ MultiArgs<R> a) {
   GroupWarp g;
   const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -174,7 +177,7 @@ __global__ void __launch_bounds__(128) k_mc_ext(const __grid_constant__ MultiArg
     cx<R>* gram = E + W;
     const cx<R>* mp[BQA_MAX_DEGREE];
     for (int j = 0; j < d; ++j) mp[j] = a.msgs[0] + (size_t)c.in_pos[(size_t)j * c.B + node] * DD;
-    mc_node_gram<R, FAST>(a, d, D, c.T + (size_t)node * W, mp, P, E, gram);
+    mc_node_gram<R, MODE>(a, d, D, c.T + (size_t)node * W, mp, P, E, gram);
     for (int k = 0; k < d; ++k) {
       const cx<R>* g0 = gram + (size_t)k * 2 * DD;
       const size_t slot = (size_t)c.out_pos[(size_t)k * c.B + node];
@@ -280,9 +283,12 @@ int launch_multiclass(int kind, int n_classes, const bqa_b200_class* cls, int D,
   }
   const void* fn = nullptr;
   if constexpr (std::is_same<R, float>::value) {
-    if (fast) fn = kind == 0 ? (const void*)k_mc_ext<R, true> : (const void*)k_mc_bp_run<R, true>;
+    if (fast) fn = kind == 0 ? (const void*)k_mc_ext<R, 2> : (const void*)k_mc_bp_run<R, 2>;
   }
-  if (!fn) fn = kind == 0 ? (const void*)k_mc_ext<R, false> : (kind == 1 ? (const void*)k_mc_apply<R> : (const void*)k_mc_bp_run<R, false>);
+  const bool unrolled = D == 2 || D == 4 || D == 8;
+  if (!fn && kind == 1) fn = (const void*)k_mc_apply<R>;
+  if (!fn && unrolled) fn = kind == 0 ? (const void*)k_mc_ext<R, 1> : (const void*)k_mc_bp_run<R, 1>;
+  if (!fn) fn = kind == 0 ? (const void*)k_mc_ext<R, 0> : (const void*)k_mc_bp_run<R, 0>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(multiclass): %s", cudaGetErrorString(e));

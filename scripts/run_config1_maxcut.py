@@ -31,6 +31,8 @@ def main():
                         "actions": [{"weight": 1.0, "steps_number": 1000, "final_mixing": 0.0}]}}
     ctx = config_to_context(cfg)
     eng = Engine(ctx, precision="single")
+    if os.environ.get("BQA_B200_KERNEL_MODE"):           # 1: generic kernels only, 2: round-1 n = 8 canonicalizer
+        eng.lib.set_kernel_mode(int(os.environ["BQA_B200_KERNEL_MODE"]))
     layers = [i for i in ctx.instructions if isinstance(i, dict)][:steps]
     t0 = time.perf_counter()
     marks = {}
@@ -42,7 +44,11 @@ def main():
     t_anneal = time.perf_counter() - t0
     out = {"config": "configs[0] random 3-regular MaxCut, 1000 qubits, max_bond_dim 16, complex64, generic kernels",
            "steps": len(layers), "anneal_s": t_anneal, "first_step_with_bond_dim": marks,
-           "bp_sweeps_last10": eng.stats["bp_sweeps"][-10:], "final_bond_dim": eng.D}
+           "bp_sweeps_last10": eng.stats["bp_sweeps"][-10:], "bp_sweeps_total": int(sum(eng.stats["bp_sweeps"])),
+           "bp_sweeps_by_50_steps": [int(sum(eng.stats["bp_sweeps"][i:i + 50])) for i in range(0, len(layers), 50)],
+           "final_bond_dim": eng.D,
+           "switches": {k: os.environ.get(k, "default") for k in ("BQA_B200_FAST_GRAM", "BQA_B200_ROUND_ROBIN",
+                                                                    "BQA_B200_KERNEL_MODE")}}
     if "--measure" in sys.argv:
         t0 = time.perf_counter()
         s = eng.measure()
@@ -51,6 +57,7 @@ def main():
     else:
         b = eng.bloch_vectors()
         out["energy_of_sign_z"] = ising_energy(edges, nodes, np.where(b[:, 2] > 0, 1, -1))
+        out["bloch_abs_mean_xyz"] = [float(v) for v in np.abs(b).mean(0)]
     print(json.dumps(out), flush=True)
 
 

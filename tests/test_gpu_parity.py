@@ -622,6 +622,30 @@ def test_config1_maxcut_shape_double_vs_oracle(lib):
     _oracle_vs_gpu(cfg, lib, 1e-6)
 
 
+def test_config1_maxcut_shape_single_bond_dimension_growth(lib):
+    """The same shape in complex64 through the growth of the bond dimension past 4 (130 steps: 1, 2, 3, 4, 5, 6).  How far
+    D may grow is decided by singular values around pinv_eps = 1e-5 of degenerate spectra: a canonicalizer that resolves the
+    small end of the spectrum only to 3e-5 (the Cholesky-factor n = 8 kernel, meant for the truncation at D = max_bond_dim)
+    lets D leave 4 six steps early and sends the anneal onto a trajectory with four times the BP sweeps.  The bond
+    dimensions must appear within two steps of the complex128 oracle's and the sweep totals must agree."""
+    from bqa_b200.benchmarking import generate_qubo_on_random_regular_graph
+    from oracle import bqa_oracle as O
+    nodes, edges = generate_qubo_on_random_regular_graph(200, 3, seed=42, node_ampl_func=lambda *_: 0.0,
+                                                         edge_ampl_func=lambda *_: 1.0)
+    cfg = {"nodes": nodes, "edges": edges, "max_bond_dim": 16, "measurement_threshold": 0.99, "damping": 0.5,
+           "bp_eps": 1e-5, "pinv_eps": 1e-5, "max_bp_iter_number": 250,
+           "schedule": {"total_time": 26.0, "starting_mixing": 1.0,
+                        "actions": [{"weight": 1.0, "steps_number": 130, "final_mixing": 0.87}, "get_bloch_vectors"]}}
+    _, octx, ost = O.run_qa(cfg, return_state=True)
+    _, eng = _run(cfg, "single")
+    first = lambda dims: {d: dims.index(d) for d in sorted(set(dims))}
+    want, got = first(ost.stats["bond_dims"]), first(eng.stats["bond_dims"])
+    assert max(want) >= 5, want                                   # the window does reach the growth past 4
+    assert set(got) == set(want), (got, want)
+    assert max(abs(got[d] - want[d]) for d in want) <= 2, (got, want)
+    assert abs(sum(eng.stats["bp_sweeps"]) - sum(ost.stats["bp_sweeps"])) <= 0.1 * sum(ost.stats["bp_sweeps"])
+
+
 @pytest.mark.parametrize("precision,tol", [("double", 1e-12), ("single", 1e-5)])
 def test_isolated_qubit_gpu(lib, precision, tol):
     """Degree-0 class on the GPU: the isolated qubit follows its exact single-qubit evolution; the other qubits

@@ -40,7 +40,10 @@ long long bqa_b200_launch_count(void);
 /* 0 (default): specialised kernels where one exists for (precision, degree, D), generic kernels otherwise;
  * 1: generic kernels only (used by the tests to check the specialised kernels against the generic ones);
  * 2: like 0 with the first-design n = 8 canonicalizer (bqa_fast_canon8.cu) instead of the current one
- *    (bqa_fast_canon8v2.cu): kept for side-by-side measurements */
+ *    (bqa_fast_canon8v2.cu): kept for side-by-side measurements.
+ * Environment switches read once (side-by-side measurements, results stay within the stated tolerances):
+ * BQA_B200_FAST_GRAM=0 (generic node contraction at D = 8), BQA_B200_ROUND_ROBIN=0 (serial Jacobi at n = 16 / 32),
+ * BQA_B200_BP_ZIGZAG=0, BQA_B200_FENCE=0|1|2, BQA_B200_MC_SMEM=0|1, BQA_B200_CANON_V=3, BQA_B200_CANON_CONV. */
 int bqa_b200_set_kernel_mode(int mode);
 
 /* how long an in-kernel grid barrier or cross-GPU handshake waits before it gives up, sets status[3] (sticky: the engine
@@ -163,7 +166,11 @@ int bqa_b200_ext_msgs(int prec, int degree, int D, long long B, const void* T, c
  * lmbds = s / |s|.  ext, canon: (2L, 2D, 2D); lmbds: real (L, 2D); colmax: real (2D), zeroed by the
  * caller, receives the column-wise max of lmbds over all edges (truncate_lmbds, backends.py:297-299).
  * n_cols: number of leading canonicalizer columns the caller will use (>= min(2D, max_bond_dim), the largest
- * bond dimension the truncation can keep, state.py:233-235); columns >= n_cols of canon may be left unwritten. */
+ * bond dimension the truncation can keep, state.py:233-235); columns >= n_cols of canon may be left unwritten.
+ * Kernels: n = 8 in complex64 with n_cols <= D (the bond dimension is capped at D): the Cholesky-factor kernel
+ * (bqa_fast_canon8v2.cu); n = 8 in complex64 while the bond dimension may still grow (n_cols > D): the
+ * accumulated-rotation kernel (bqa_fast_canon8.cu), whose small singular values are accurate enough for the rank
+ * decision at pinv_eps; n = 16 / 32: round-robin Jacobi over the lanes of a warp; else the serial generic routine. */
 int bqa_b200_canonicalize(int prec, int D, long long L, const void* ext, void* canon, void* lmbds,
                           void* colmax, double pinv_eps, int n_cols, void* stream);
 /* The same with the edges visited in the order `order` (int32 permutation of 0 .. L-1, NULL = identity) and the cost of

@@ -355,10 +355,12 @@ BQA_HDN void jacobi_svd(G g, int n, int ld, cx<R>* A, cx<R>* V, R* sigma, int* o
 
 // ------------------------------------------------------------------------------------------------
 // canonicalizers of one undirected edge (forward message slot e, backward slot e + L)
-//   scratch: 6 matrices of n rows with stride n + 1 (complex) + 3 n reals + 3 n ints  (see edge_scratch_elems)
+//   scratch: 5 matrices of n rows with stride n + 1 (complex) + 3 n reals + 3 n ints  (see edge_scratch_elems);
+//   V of the ker decomposition reuses the storage of V_f, which is dead once ker is built (at n = 32 the sixth matrix
+//   cost a quarter of the warps that fit an SM)
 // ------------------------------------------------------------------------------------------------
 template <typename R>
-BQA_HD size_t edge_scratch_elems(int n) { return (size_t)6 * n * (n + 1); }
+BQA_HD size_t edge_scratch_elems(int n) { return (size_t)5 * n * (n + 1); }
 
 // which SVD edge_canonicalize runs: the serial cyclic Jacobi above (any group), or a policy of the caller's
 // (bqa_generic.cuh: round-robin ordering over the lanes of a warp for n = 16 / 32); `prm` = n / 2 x 4 reals of scratch
@@ -377,7 +379,7 @@ BQA_HDN void edge_canonicalize(G g, int n, const cx<R>* ext_f, const cx<R>* ext_
   const int nn = n * n, ld = n + 1, sz = n * ld;              // scratch matrices: row stride ld (see jacobi_svd)
   cx<R>* Af = scratch;           cx<R>* Vf = scratch + sz;
   cx<R>* Ab = scratch + 2 * sz;  cx<R>* Vb = scratch + 3 * sz;
-  cx<R>* K = scratch + 4 * sz;   cx<R>* Vk = scratch + 5 * sz;
+  cx<R>* K = scratch + 4 * sz;   cx<R>* Vk = Vf;              // V_f is dead after the ker build below
   R* sf = rscratch;  R* sb = rscratch + n;  R* sk = rscratch + 2 * n;
   int* of = iscratch;  int* ob = iscratch + n;  int* ok = iscratch + 2 * n;
   for (int i = g.rank(); i < nn; i += g.size()) {

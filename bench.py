@@ -620,7 +620,7 @@ def measure_roofline(eng, lib, layers, torch, dev) -> dict:
 
 def measure_e2e(eng, snapshot, layers, torch, dev, bloch_resident, world, dist) -> dict:
     """Same K steps driven from HOST buffers through the public engine API: load_state (pinned host -> HBM; every rank
-    its own shard), K x run_layer (each reads its bond-dimension decision and BP control block back), bloch_vectors
+    its own shard), run_layers over the K steps (each reads its bond-dimension decision and BP control block back), bloch_vectors
     (HBM -> host, gathered over the ranks).  Wall clock between barriers, max over ranks; bytes summed over ranks."""
     h2d = sum(int(t.numel() * t.element_size()) for t in snapshot["_pinned"].values())
     if world > 1:
@@ -644,7 +644,7 @@ def measure_e2e(eng, snapshot, layers, torch, dev, bloch_resident, world, dist) 
         dt, h2d, d2h = float(tmax[0]), float(t[1]), float(t[2])
     assert np.abs(b - bloch_resident).max() < 1e-6, "end-to-end run disagrees with the HBM-resident run"
     return {"value": K / dt, "unit": "steps/s", "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
-            "what": "Engine.load_state(pinned host snapshot) + K x Engine.run_layer + Engine.bloch_vectors(), "
+            "what": "Engine.load_state(pinned host snapshot) + Engine.run_layers(K steps) + Engine.bloch_vectors(), "
                     "wall clock incl. all copies"}
 
 

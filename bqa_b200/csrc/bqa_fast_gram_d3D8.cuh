@@ -43,8 +43,8 @@ __device__ __forceinline__ void mode_product(const float2* src, float2* dst, int
     v0[b] = x2::pk(a.x, a.y); r0[b] = x2::pk(-a.y, a.x);        // i * v
     v1[b] = x2::pk(c.x, c.y); r1[b] = x2::pk(-c.y, c.x);
   }
-#pragma unroll
-  for (int x = 0; x < 8; ++x) {
+#pragma unroll 1                     // rolled: fully unrolled, the routine's five products and three contractions came to about
+  for (int x = 0; x < 8; ++x) {      // 75 KB of straight-line code and "no instruction" was the largest stall (r2 capture)
     p2 a0 = x2::pk(0.f, 0.f), a1 = a0;
 #pragma unroll
     for (int b2 = 0; b2 < 4; ++b2) {
@@ -74,7 +74,7 @@ __device__ __forceinline__ void gram_outer(const float2* T, const float2* E, int
   const float2* tp = T + x * XS;
   const float2* e0p = E + (2 * yq) * XS;
   const float2* e1p = e0p + XS;
-#pragma unroll
+#pragma unroll 1
   for (int o = 0; o < 8; ++o) {
 #pragma unroll
     for (int c2 = 0; c2 < 4; ++c2) {
@@ -92,7 +92,7 @@ __device__ __forceinline__ void gram_outer(const float2* T, const float2* E, int
 // open leg = 2 (innermost): gram[x][y] = sum_{a, b} conj(T[a, b, x]) E[a, b, y]
 __device__ __forceinline__ void gram_inner(const float2* T, const float2* E, int x, int yq, float2* out) {
   p2 acc0 = x2::pk(0.f, 0.f), acc1 = acc0;
-#pragma unroll
+#pragma unroll 1
   for (int a = 0; a < 8; ++a) {
 #pragma unroll
     for (int b = 0; b < 8; ++b) {

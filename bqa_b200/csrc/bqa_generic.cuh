@@ -253,8 +253,10 @@ __host__ __device__ inline size_t canon_warp_bytes(int n) {        // matrices |
   return (b + 15) / 16 * 16;
 }
 
-template <typename R, bool PAR>
-__global__ void __launch_bounds__(256) k_canonicalize(int D, long long L, const cx<R>* ext, cx<R>* canon,
+// MINB = 2 (n = 16 in complex64): the round-robin routine took 251 registers, one CTA of 8 warps per SM; capped at 128 two
+// CTAs fit (the n = 32 branch, dead at that size, is what spills)
+template <typename R, bool PAR, int MINB = 1>
+__global__ void __launch_bounds__(256, MINB) k_canonicalize(int D, long long L, const cx<R>* ext, cx<R>* canon,
                                                       R* lmbds, R* colmax, R pinv_eps) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GroupWarp g;
@@ -454,6 +456,7 @@ int launch_canonicalize(int D, long long L, const void* ext, void* canon, void* 
   // n = 16, 32: all column pairs of a round together (jacobi_svd_round_robin); smaller n: the serial routine
   const bool par = round_robin && (n == 16 || n == 32);
   const void* fn = par ? (const void*)k_canonicalize<R, true> : (const void*)k_canonicalize<R, false>;
+  if (par && n == 16 && sizeof(R) == 4) fn = (const void*)k_canonicalize<R, true, 2>;
   if (smem > 48 * 1024) {                      // per device and per size: set on every call (microseconds per step)
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(canonicalize): %s", cudaGetErrorString(e));
